@@ -1,0 +1,340 @@
+"""Drop-in for the reference's `bialignment` module (s-will/BiAlign, src/bialignment.pyx).
+
+Same Python surface -- `BiAligner(seqA, seqB, strA, strB, **params)`, `optimize()`,
+`traceback()`, `decode_trace()`, `decode_trace_full()`, `eval_trace()`, `outmodes`, the module
+helpers -- but the dynamic program (pyx:443-586) runs on the GPU through the C ABI of
+include/bialign_b200.h.  There is no CPU implementation of the DP in this package: without the
+built CUDA library and an sm_100 device, `optimize()` raises.
+
+Observable behaviour kept from the reference (file:line into src/bialignment.pyx):
+  * constructor errors: `ERROR: ...` on stdout + sys.exit(-1) (pyx:207-210, 355-358); KeyError for
+    a missing required parameter (pyx:186-190);
+  * optimize() returns numpy.int64 (pyx:509 / pyx:471); KeyError for a residue that the similarity
+    matrix does not know (pyx:407);
+  * traceback() returns forward-ordered columns, lists for the affine model (pyx:568,586), tuples
+    for the non-affine one (pyx:526,531), and prints the incomplete-traceback warning (pyx:584-585).
+"""
+import sys
+from math import sqrt
+
+import numpy as np
+
+from . import encoding
+from ._capi import BialignError, get_engine
+from .encoding import read_simmatrix  # noqa: F401  (re-exported like the reference, pyx:3-4)
+from .presentation import (breaklines, consensus_sbpp, consensus_sequence, highlight_sequence_identity,  # noqa: F401
+                           mea, parse_dotbracket, plot_alignment, read_molecule, read_molecule_from_file)
+
+__version__ = "0.3"  # surface version of the reference this module mirrors (nonpyx:3)
+
+
+def guard_case(o, x, max_shift):
+    """pyx:133-148: predecessor x - o is non-negative and inside the shift band."""
+    return (x[0] - o[0] >= 0 and x[1] - o[1] >= 0 and x[2] - o[2] >= 0 and x[3] - o[3] >= 0
+            and abs(x[2] - o[2] - (x[0] - o[0])) <= max_shift and abs(x[3] - o[3] - (x[1] - o[1])) <= max_shift)
+
+
+def argmin(xs):
+    return min(enumerate(xs), key=lambda x: x[1])[0]
+
+
+def _column_score_affine(state, x, mu1, mu2, beta, gamma, Delta):
+    """Score of one column given the source state (behaviour of pyx:84-131); used by eval_trace only."""
+    score = Delta * (abs(x[0] - x[2]) + abs(x[1] - x[3]))
+    for a, b, mu in ((0, 1, mu1), (2, 3, mu2)):
+        if x[a] and x[b]:
+            score += mu
+        elif x[a] or x[b]:
+            score += gamma
+            if not (state[a] == x[a] and state[b] == x[b]):
+                score += beta
+    return score
+
+
+class BiAligner:
+    nl = 14
+    outmodes = {
+        "default": [1, 3, 6, 8, 12, 13],
+        "sorted": [0, 1, 5, 3, 2, 4, nl] + [7, 6, 10, 8, 9, 11, nl] + [12, 13],
+        "sorted_sym": [0, 1, 3, 2, 5, 4, nl] + [6, 7, 9, 8, 11, 10, nl] + [12, 13],
+        "sorted_terse": [1, 5, 3, 4, nl] + [6, 10, 8, 11, nl] + [12, 13],
+        "raw": [1, 3, 7, 9],
+        "raw_struct": list(range(4)) + list(range(6, 10)),
+        "full": range(nl),
+    }
+
+    def __init__(self, seqA, seqB, strA, strB, **params):
+        self._params = params
+        self.molA = self._preprocess_seq(seqA, strA)
+        self.molB = self._preprocess_seq(seqB, strB)
+        self.gamma = self._params["gap_cost"]
+        self.beta = self._params["gap_opening_cost"]
+        self.max_shift = self._params["max_shift"]
+        if self._params["simmatrix"]:
+            self._simmatrix = read_simmatrix(self._params["simmatrix"])
+        else:
+            self._simmatrix = None
+        self._score = None
+        self._trace = None
+        self._complete = True
+
+    # ------------------------------------------------------------------ helpers of the surface
+    @property
+    def _is_rna(self):
+        return self._params["type"] == "RNA"
+
+    @property
+    def _affine(self):
+        return self.beta != 0
+
+    @staticmethod
+    def error(text):
+        print("ERROR:", text)
+        sys.exit(-1)
+
+    def _preprocess_seq(self, sequence, structure):
+        x = {"seq": str(sequence)}
+        x["len"] = len(x["seq"])
+        if structure is None:
+            if self._is_rna:
+                # The reference predicts base-pair probabilities with ViennaRNA here (pyx:345-353).
+                # That dependency is outside the scope of this engine: supply dot-bracket structures.
+                import RNA  # noqa: F401  (raises ModuleNotFoundError exactly like the reference without ViennaRNA)
+                raise NotImplementedError("predicted RNA structures are not supported; pass strA/strB")
+            else:
+                self.error("Structures have to be provided when aligning proteins")
+        else:
+            if len(structure) != len(sequence):
+                self.error("Provided structure and sequence must have the same length.")
+            x["structure"] = structure
+            if self._is_rna:
+                x["partner"] = encoding.dotbracket_partners(structure)
+                x["cls"] = encoding.rna_structure_classes(structure)
+        return x
+
+    # scoring functions, 1-based like the reference (pyx:405-440); used by eval_trace
+    def mu1(self, i, j):
+        a, b = self.molA["seq"][i - 1], self.molB["seq"][j - 1]
+        if self._simmatrix:
+            return self._simmatrix[a][b]
+        if a == b:
+            return self._params["sequence_match_similarity"]
+        return self._params["sequence_mismatch_similarity"]
+
+    def mu2(self, i, j):
+        if self._is_rna:
+            ca = self.molA["cls"][i - 1] if i >= 1 else encoding.UNP
+            cb = self.molB["cls"][j - 1] if j >= 1 else encoding.UNP
+            # int(w * (sqrt(upA*upB) + sqrt(downA*downB) + sqrt(unpA*unpB))) with one-hot profiles
+            return int(self._params["structure_weight"] * (1.0 if ca == cb else 0.0))
+        if self.molA["structure"][i - 1] == self.molB["structure"][j - 1]:
+            return self._params["structure_weight"]
+        return 0
+
+    # ------------------------------------------------------------------ the hot path (GPU)
+    def _encoded(self):
+        """(residues A, residues B, classes A, classes B, similarity table) for the C ABI."""
+        sa, sb = self.molA["seq"], self.molB["seq"]
+        if self._simmatrix:
+            symbols, table, known = encoding.simmatrix_table(self._simmatrix)
+            # the reference fails lazily with KeyError at the first unknown residue pair it scores
+            # (pyx:407; the first pair evaluated is (seqA[-1], seqB[-1]))
+            lut = {c: i for i, c in enumerate(symbols)}
+            order_a = ([sa[-1]] if sa else []) + list(sa)
+            order_b = ([sb[-1]] if sb else []) + list(sb)
+            for ch in order_a:
+                if ch not in self._simmatrix:
+                    raise KeyError(ch)
+            cols_ok = set(c for c in symbols if all(known[lut[a], lut[c]] for a in set(sa)))
+            for ch in order_b:
+                if ch not in cols_ok:
+                    raise KeyError(ch)
+            ra = encoding.encode_residues(sa, symbols)
+            rb = encoding.encode_residues(sb, symbols)
+        else:
+            table = encoding.match_table(self._params["sequence_match_similarity"],
+                                         self._params["sequence_mismatch_similarity"])
+            ra, rb = encoding.encode_bytes(sa), encoding.encode_bytes(sb)
+        if self._is_rna:
+            ca, cb = self.molA["cls"], self.molB["cls"]
+        else:
+            ca, cb = encoding.encode_bytes(self.molA["structure"]), encoding.encode_bytes(self.molB["structure"])
+        return ra, rb, ca, cb, table
+
+    def optimize(self):
+        n, m = self.molA["len"], self.molB["len"]
+        if (n == 0) != (m == 0):
+            raise IndexError("string index out of range")  # the reference's seq[-1] on an empty string (pyx:407)
+        ra, rb, ca, cb, table = self._encoded()
+        eng = get_engine()
+        eng.set_scoring(table, self._params["structure_weight"], self.beta, self.gamma, self._params["shift_cost"],
+                        self.max_shift)
+        res = np.concatenate([ra, rb]).astype(np.uint8)
+        cls = np.concatenate([ca, cb]).astype(np.uint8)
+        off = np.array([0, n, n + m], dtype=np.int64)
+        eng.load_sequences(res, cls, off)
+        eng.load_pairs(np.array([0], dtype=np.int32), np.array([1], dtype=np.int32))
+        eng.run(want_trace=True)
+        self._score = np.int64(eng.fetch_scores()[0])
+        cols, offsets, complete = eng.fetch_traces()
+        self._trace = cols[offsets[0]:offsets[1]].copy()
+        self._complete = bool(complete[0])
+        return self._score
+
+    def traceback(self):
+        if self._trace is None:
+            raise TypeError("'NoneType' object is not subscriptable")  # reference: traceback() before optimize()
+        if self.molA["len"] == 0 and self.molB["len"] == 0 and self._affine:
+            raise IndexError("string index out of range")  # pyx:555 -> pyx:260 -> pyx:407 on empty strings
+        cols = [[(c >> 3) & 1, (c >> 2) & 1, (c >> 1) & 1, c & 1] for c in self._trace.tolist()]
+        if self._affine:
+            if not self._complete:
+                print("WARNING: incomplete traceback. Alignment could be garbage.")
+            return cols
+        return [tuple(c) for c in cols]
+
+    # ------------------------------------------------------------------ presentation (host only)
+    @staticmethod
+    def _transfer_gaps(alistr, seqstr):
+        out, pos = [], 0
+        for c in alistr:
+            if c == "-":
+                out.append("-")
+            else:
+                out.append(seqstr[pos])
+                pos += 1
+        return "".join(out)
+
+    @staticmethod
+    def _shift_string(ali, idx):
+        def sym(i):
+            g1, g2 = ali[idx][i] == "-", ali[idx + 2][i] == "-"
+            if g1 == g2:
+                return "."
+            return ">" if g1 else "<"
+
+        return "".join(sym(i) for i in range(len(ali[0])))
+
+    @staticmethod
+    def auto_complete(x, xs):
+        for y in sorted(xs):
+            if y.startswith(x):
+                return y
+        return x
+
+    def _sbpp(self, mol):
+        """Symmetric pair matrix with unpaired probability on the diagonal for a fixed structure
+        (what pyx:378-392 builds); only needed for the RNA consensus-structure rows."""
+        n = mol["len"]
+        m = np.zeros((n + 1, n + 1), dtype=float)
+        partner = mol["partner"]
+        for i in range(1, n + 1):
+            p = int(partner[i])
+            ch = mol["structure"][i - 1]
+            if p:
+                m[i, p] = 1.0
+            elif ch not in "()":
+                m[i, i] = 1.0
+        return m
+
+    def decode_trace_full(self, trace=None):
+        """Trace -> the 14 named rows of pyx:633-707 (same order, same names)."""
+        if trace is None:
+            trace = self.traceback()
+        mols = (self.molA, self.molB, self.molA, self.molB)
+        pos = [0, 0, 0, 0]
+        rows = [[], [], [], []]
+        for y in trace:
+            for q in range(4):
+                if y[q] == 0:
+                    rows[q].append("-")
+                elif y[q] == 1:
+                    rows[q].append(mols[q]["seq"][pos[q]])
+                    pos[q] += 1
+        alignment = ["".join(r) for r in rows]
+        cons_seq = [consensus_sequence(alignment[2 * q], alignment[2 * q + 1]) for q in range(2)]
+
+        anno = []
+        for alistr, mol in zip(alignment, mols):
+            anno.append(self._transfer_gaps(alistr, mol["structure"]))
+            anno.append(alistr)
+        # consensus structure rows: second copy first, then first copy (insertion order of pyx:662-673)
+        for i, j in [(4, 6), (0, 2)]:
+            if self._is_rna:
+                sb = consensus_sbpp(alistrA=anno[i], alistrB=anno[j], sbppA=self._sbpp(self.molA),
+                                    sbppB=self._sbpp(self.molB))
+                structure = mea(sb, brackets="[]")[0]
+            else:
+                structure = consensus_sequence(anno[i], anno[j])
+            anno.insert(j + 2, structure)
+        shifts = [self._shift_string(alignment, q) for q in range(2)]
+        out = anno
+        out.insert(len(out), cons_seq[1])
+        out.insert(len(out) // 2, cons_seq[0])
+        out.extend(shifts)
+        nameA, nameB = self._params["nameA"], self._params["nameB"]
+        ss = " ss"
+        names = [nameA + ss, nameA, nameB + ss, nameB, "consensus" + ss, "consensus"] * 2 + [nameA + " shifts",
+                                                                                             nameB + " shifts"]
+        return list(zip(names, out))
+
+    def decode_trace(self, trace=None):
+        alignment = self.decode_trace_full(trace)
+        width = max(len(name) for name, _ in alignment) + 4
+        if "nodescription" not in self._params or not self._params["nodescription"]:
+            alignment = ["{:{width}}{}".format(name, s, width=width) for name, s in alignment]
+        else:
+            alignment = [s for _, s in alignment]
+        alignment.append("")
+        if "outmode" not in self._params:
+            self._params["outmode"] = "default"
+        mode = self.auto_complete(self._params["outmode"], self.outmodes.keys())
+        if mode in self.outmodes:
+            order = self.outmodes[mode]
+        else:
+            print("WARNING: unknown output mode. Expect one of " + str(list(self.outmodes.keys())))
+            order = self.outmodes["sorted"]
+        return [alignment[i] for i in order]
+
+    # ------------------------------------------------------------------ trace evaluation (-v)
+    def _nonaffine_cases(self, idx):
+        i, j, k, l = idx
+        m1, m2 = self.mu1(i, j), self.mu2(k, l)
+        g, D = self.gamma, self._params["shift_cost"]
+        return [((1, 1, 1, 1), m1 + m2), ((1, 0, 1, 0), g + g), ((0, 1, 0, 1), g + g), ((1, 1, 0, 0), m1 + D),
+                ((0, 0, 1, 1), m2 + D), ((1, 0, 0, 0), g + D), ((0, 1, 0, 0), g + D), ((0, 0, 1, 0), g + D),
+                ((0, 0, 0, 1), g + D), ((1, 0, 1, 1), g + m2 + D), ((0, 1, 1, 1), g + m2 + D),
+                ((1, 1, 1, 0), g + m1 + D), ((1, 1, 0, 1), g + m1 + D)]
+
+    def eval_trace(self, trace=None):
+        """Per-column score listing (pyx:745-832).  For the non-affine model the reference prints the
+        DP value of the previous cell plus the column score; along an optimal trace that is the
+        running total, which is what is printed here."""
+        if trace is None:
+            trace = self.traceback()
+        Delta = self._params["shift_cost"]
+        idx = [0, 0, 0, 0]
+        total = 0
+        if self._affine:
+            state = [1, 1, 1, 1]
+            for y in trace:
+                y = list(y)
+                for q in range(4):
+                    idx[q] += y[q]
+                i, j, k, l = idx
+                score = _column_score_affine(state, y, self.mu1(i, j), self.mu2(k, l), self.beta, self.gamma, Delta)
+                total += score
+                if y[0] or y[1]:
+                    state[0], state[1] = y[0], y[1]
+                if y[2] or y[3]:
+                    state[2], state[3] = y[2], y[3]
+                yield " ".join(str(item) for item in [idx, y, score, "-->", total])
+            return
+        for y in trace:
+            for q in range(4):
+                idx[q] += y[q]
+            for x, sc in self._nonaffine_cases(idx):
+                if x == y:
+                    total += sc
+                    yield " ".join(str(item) for item in [idx, y, sc, "-->", total])
+                    break

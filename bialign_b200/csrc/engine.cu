@@ -1,0 +1,540 @@
+// C ABI of the engine (include/bialign_b200.h): device memory, wave scheduling, launches.
+//
+// Data layout in HBM (all owned here, grow-only):
+//   res/cls     concatenated uint8 residue codes / structure classes of the sequence table
+//   sim         nsym x nsym int32 similarity table
+//   desc        PairDesc per pair, sorted by decreasing cost (LPT order inside the device)
+//   codes       traceback-code arena: one uint64 per band cell, nibble t = winning case of state t;
+//               pairs are processed in waves that fit the arena, traceback runs per wave
+//   trace       one slot of 2(n+m)+2 bytes per pair, columns written backwards by the traceback
+//   scores/start_state/end_values/trace_len/complete   per pair, caller order
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/bialign_b200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+using namespace ba;
+
+namespace {
+std::string g_create_error;
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t ensure(size_t need) {
+        if (need <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(need, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = need;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+template <class T>
+struct PinnedBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t need) {
+        if (need <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaHostAlloc((void**)&p, std::max<size_t>(need, 1) * sizeof(T), cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = need;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+}  // namespace
+
+struct ba_engine {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    bool have_scoring = false, have_seqs = false, have_pairs = false, ran = false, ran_trace = false;
+    Scoring sc{};
+    int64_t max_abs_sim = 0;
+    DevBuf<int> d_sim;
+
+    std::vector<int64_t> h_off;
+    int64_t n_seq = 0;
+    int max_residue = 0;
+    DevBuf<uint8_t> d_res, d_cls;
+
+    std::vector<int32_t> h_pa, h_pb;
+    int64_t n_pairs = 0;
+
+    std::vector<PairDesc> h_desc;          // sorted order
+    std::vector<int64_t> h_slot_off;       // caller order
+    std::vector<int32_t> h_slot_cap;       // caller order
+    std::vector<int64_t> h_last_code_off;  // caller order; -1 if not in the last wave
+    DevBuf<PairDesc> d_desc;
+    DevBuf<uint64_t> d_codes;
+    DevBuf<int> d_scratch;
+    DevBuf<int> d_counter;
+    DevBuf<long long> d_scores;
+    DevBuf<uint8_t> d_start, d_complete, d_trace;
+    DevBuf<int> d_endv, d_tlen;
+    PinnedBuf<uint8_t> h_stage;
+    std::vector<int32_t> h_tlen;
+    bool have_tlen = false;
+
+    int64_t opt_code_arena_bytes = 0;  // 0 = auto
+    int opt_kernel = -1;               // -1 auto
+    ba_stats stats{};
+};
+
+namespace {
+
+int fail(ba_engine* e, int code, const std::string& msg) {
+    if (e) e->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t _e = (call);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return fail(e, _e == cudaErrorMemoryAllocation ? BA_ERR_OOM : BA_ERR_CUDA,               \
+                        std::string(#call) + ": " + cudaGetErrorString(_e));                         \
+    } while (0)
+
+int64_t band_cells(int64_t n, int64_t m, int64_t s) {
+    // C(n,m,s) of SURVEY 8: exact count of band-valid cells (k in [max(0,i-s), min(n,i+s)] etc.)
+    auto one = [&](int64_t len) {
+        int64_t c = 0;
+        for (int64_t d = -s; d <= s; ++d) {
+            int64_t ad = d < 0 ? -d : d;
+            if (len + 1 - ad > 0) c += len + 1 - ad;
+        }
+        return c;
+    };
+    return one(n) * one(m);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ba_version(void) { return "bialign_b200 0.1 (sm_100a)"; }
+
+int ba_engine_create(int device, ba_engine** out) {
+    ba_engine* e = nullptr;
+    if (!out) return fail(nullptr, BA_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(nullptr, BA_ERR_NO_DEVICE,
+                    std::string("no CUDA device: ") + (ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce)) +
+                        " (bialign_b200 has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(nullptr, BA_ERR_INVALID_ARG, "device ordinal out of range");
+    cudaDeviceProp prop;
+    if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(nullptr, BA_ERR_CUDA, cudaGetErrorString(ce));
+    if (prop.major != 10)
+        return fail(nullptr, BA_ERR_NO_DEVICE,
+                    std::string("device '") + prop.name + "' is not sm_100 (kernels are built for sm_100a only)");
+    if ((ce = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, BA_ERR_CUDA, cudaGetErrorString(ce));
+    e = new ba_engine();
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete e;
+        return fail(nullptr, BA_ERR_CUDA, cudaGetErrorString(ce));
+    }
+    e->stats.device = device;
+    *out = e;
+    return BA_OK;
+}
+
+void ba_engine_destroy(ba_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    e->d_sim.release(); e->d_res.release(); e->d_cls.release(); e->d_desc.release(); e->d_codes.release();
+    e->d_scratch.release(); e->d_counter.release(); e->d_scores.release(); e->d_start.release();
+    e->d_complete.release(); e->d_trace.release(); e->d_endv.release(); e->d_tlen.release(); e->h_stage.release();
+    cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+const char* ba_last_error(const ba_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int ba_set_option(ba_engine* e, const char* key, int64_t value) {
+    if (!e || !key) return BA_ERR_INVALID_ARG;
+    if (!strcmp(key, "code_arena_bytes")) e->opt_code_arena_bytes = value;
+    else if (!strcmp(key, "kernel")) e->opt_kernel = (int)value;
+    else return fail(e, BA_ERR_INVALID_ARG, std::string("unknown option ") + key);
+    return BA_OK;
+}
+
+int ba_set_scoring(ba_engine* e, const int32_t* sim, int nsym, int structure_weight, int gap_opening_cost,
+                   int gap_cost, int shift_cost, int max_shift) {
+    if (!e) return BA_ERR_INVALID_ARG;
+    if (!sim || nsym <= 0 || nsym > 256) return fail(e, BA_ERR_INVALID_ARG, "sim is NULL or nsym not in 1..256");
+    if (max_shift < 0 || max_shift > BA_MAX_SHIFT)
+        return fail(e, BA_ERR_INVALID_ARG, "max_shift must be in 0.." + std::to_string(BA_MAX_SHIFT));
+    CU(cudaSetDevice(e->device));
+    e->sc = Scoring{structure_weight, gap_opening_cost, gap_cost, shift_cost, max_shift, nsym};
+    e->max_abs_sim = 0;
+    for (int q = 0; q < nsym * nsym; ++q) e->max_abs_sim = std::max<int64_t>(e->max_abs_sim, std::llabs((long long)sim[q]));
+    CU(e->d_sim.ensure((size_t)nsym * nsym));
+    CU(cudaMemcpyAsync(e->d_sim.p, sim, sizeof(int) * nsym * nsym, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->have_scoring = true;
+    e->ran = false;
+    return BA_OK;
+}
+
+int ba_load_sequences(ba_engine* e, const uint8_t* residues, const uint8_t* classes, const int64_t* offsets,
+                      int64_t n_seq) {
+    if (!e) return BA_ERR_INVALID_ARG;
+    if (!offsets || n_seq < 0) return fail(e, BA_ERR_INVALID_ARG, "offsets is NULL or n_seq < 0");
+    for (int64_t q = 0; q < n_seq; ++q)
+        if (offsets[q + 1] < offsets[q] || offsets[q] < 0) return fail(e, BA_ERR_INVALID_ARG, "offsets not monotone");
+    const int64_t total = n_seq ? offsets[n_seq] : 0;
+    if (total > 0 && (!residues || !classes)) return fail(e, BA_ERR_INVALID_ARG, "residues/classes NULL");
+    if (total - (n_seq ? offsets[0] : 0) > (int64_t)1 << 40) return fail(e, BA_ERR_INVALID_ARG, "sequence table too large");
+    CU(cudaSetDevice(e->device));
+    e->h_off.assign(offsets, offsets + n_seq + 1);
+    e->n_seq = n_seq;
+    int mx = 0;
+    for (int64_t q = 0; q < total; ++q) mx = std::max<int>(mx, residues[q]);
+    e->max_residue = mx;
+    CU(e->d_res.ensure((size_t)total));
+    CU(e->d_cls.ensure((size_t)total));
+    if (total) {
+        CU(cudaMemcpyAsync(e->d_res.p, residues, (size_t)total, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(e->d_cls.p, classes, (size_t)total, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    e->have_seqs = true;
+    e->have_pairs = false;
+    e->ran = false;
+    return BA_OK;
+}
+
+int ba_load_pairs(ba_engine* e, const int32_t* seq_a, const int32_t* seq_b, int64_t n_pairs) {
+    if (!e) return BA_ERR_INVALID_ARG;
+    if (!e->have_seqs) return fail(e, BA_ERR_STATE, "ba_load_sequences first");
+    if (n_pairs < 0 || (n_pairs > 0 && (!seq_a || !seq_b))) return fail(e, BA_ERR_INVALID_ARG, "pair arrays NULL");
+    if (n_pairs > 0x7fffffff) return fail(e, BA_ERR_INVALID_ARG, "too many pairs for one call");
+    for (int64_t p = 0; p < n_pairs; ++p)
+        if (seq_a[p] < 0 || seq_a[p] >= e->n_seq || seq_b[p] < 0 || seq_b[p] >= e->n_seq)
+            return fail(e, BA_ERR_INVALID_ARG, "pair " + std::to_string(p) + " references a sequence outside the table");
+    e->h_pa.assign(seq_a, seq_a + n_pairs);
+    e->h_pb.assign(seq_b, seq_b + n_pairs);
+    e->n_pairs = n_pairs;
+    e->have_pairs = true;
+    e->ran = false;
+    return BA_OK;
+}
+
+int ba_run(ba_engine* e, int want_trace) {
+    if (!e) return BA_ERR_INVALID_ARG;
+    if (!e->have_scoring) return fail(e, BA_ERR_STATE, "ba_set_scoring first");
+    if (!e->have_pairs) return fail(e, BA_ERR_STATE, "ba_load_sequences and ba_load_pairs first");
+    if (e->sc.beta == 0) return fail(e, BA_ERR_INVALID_ARG, "non-affine model (gap_opening_cost == 0) is not available in this build");
+    CU(cudaSetDevice(e->device));
+    const int64_t N = e->n_pairs;
+    const int s = e->sc.s;
+    e->ran = false;
+    e->have_tlen = false;
+    e->stats = ba_stats{};
+    e->stats.device = e->device;
+    e->stats.pairs = N;
+    if (e->max_residue >= e->sc.nsym)
+        return fail(e, BA_ERR_ALPHABET, "residue code " + std::to_string(e->max_residue) + " >= nsym " + std::to_string(e->sc.nsym));
+
+    // ---- schedule: descending cost (LPT inside the device), waves that fit the code arena
+    std::vector<int32_t> order((size_t)N);
+    std::iota(order.begin(), order.end(), 0);
+    std::vector<int32_t> ln((size_t)N), lm((size_t)N);
+    int nmax = 0, mmax = 0;
+    int64_t cs = 0;
+    for (int64_t p = 0; p < N; ++p) {
+        ln[p] = (int32_t)(e->h_off[e->h_pa[p] + 1] - e->h_off[e->h_pa[p]]);
+        lm[p] = (int32_t)(e->h_off[e->h_pb[p] + 1] - e->h_off[e->h_pb[p]]);
+        nmax = std::max(nmax, ln[p]);
+        mmax = std::max(mmax, lm[p]);
+        cs += 9 * band_cells(ln[p], lm[p], s);
+    }
+    e->stats.cell_states = cs;
+    {   // int32 exactness bound of SURVEY 8a-6
+        const int64_t col = e->max_abs_sim + std::llabs((long long)e->sc.w) + 2 * std::llabs((long long)e->sc.beta) +
+                            2 * std::llabs((long long)e->sc.gamma) + 2 * std::llabs((long long)e->sc.delta);
+        if ((int64_t)(nmax + mmax + 2) * col >= ((int64_t)1 << 30))
+            return fail(e, BA_ERR_SCORE_RANGE, "score bound exceeds int32 range (needs the reference's int64 tables)");
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+        return (int64_t)(ln[x] + 1) * (lm[x] + 1) > (int64_t)(ln[y] + 1) * (lm[y] + 1);
+    });
+
+    e->h_desc.resize((size_t)N);
+    e->h_slot_off.assign((size_t)N, 0);
+    e->h_slot_cap.assign((size_t)N, 0);
+    e->h_last_code_off.assign((size_t)N, -1);
+    int64_t trace_total = 0;
+    if (want_trace)
+        for (int64_t p = 0; p < N; ++p) {
+            e->h_slot_off[p] = trace_total;
+            e->h_slot_cap[p] = 2 * (ln[p] + lm[p]) + 2;
+            trace_total += (e->h_slot_cap[p] + 15) & ~15;
+        }
+
+    // code arena
+    size_t arena_words = 0;
+    std::vector<int64_t> wave_begin;  // indices into sorted order
+    if (want_trace && N) {
+        int64_t total_words = 0, max_words = 0;
+        for (int64_t p = 0; p < N; ++p) {
+            const int64_t wds = code_words(ln[p], lm[p], s);
+            total_words += wds;
+            max_words = std::max(max_words, wds);
+        }
+        int64_t budget_bytes = e->opt_code_arena_bytes;
+        if (budget_bytes <= 0) {
+            size_t fr = 0, tot = 0;
+            CU(cudaMemGetInfo(&fr, &tot));
+            budget_bytes = (int64_t)(fr + e->d_codes.cap * 8) / 2;
+        }
+        int64_t budget_words = std::max<int64_t>(budget_bytes / 8, max_words);
+        arena_words = (size_t)std::min(budget_words, total_words);
+        cudaError_t ce = e->d_codes.ensure(arena_words);
+        if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "traceback-code arena: " + std::string(cudaGetErrorString(ce)));
+    }
+    {
+        int64_t used = 0;
+        wave_begin.push_back(0);
+        for (int64_t q = 0; q < N; ++q) {
+            const int32_t p = order[q];
+            PairDesc& d = e->h_desc[q];
+            d.offA = e->h_off[e->h_pa[p]];
+            d.offB = e->h_off[e->h_pb[p]];
+            d.n = ln[p];
+            d.m = lm[p];
+            d.orig = p;
+            d.trace_off = e->h_slot_off[p];
+            d.trace_cap = e->h_slot_cap[p];
+            d.code_off = 0;
+            if (want_trace) {
+                const int64_t wds = code_words(d.n, d.m, s);
+                if (used + wds > (int64_t)arena_words) {
+                    wave_begin.push_back(q);
+                    used = 0;
+                }
+                d.code_off = used;
+                used += wds;
+            }
+        }
+        wave_begin.push_back(N);
+    }
+    const int n_waves = (int)wave_begin.size() - 1;
+
+    // ---- buffers
+    CU(e->d_desc.ensure((size_t)N));
+    CU(e->d_scores.ensure((size_t)N));
+    CU(e->d_start.ensure((size_t)N));
+    CU(e->d_endv.ensure((size_t)N * 9));
+    CU(e->d_counter.ensure((size_t)std::max(n_waves, 1)));
+    if (want_trace) {
+        CU(e->d_tlen.ensure((size_t)N));
+        CU(e->d_complete.ensure((size_t)N));
+        CU(e->d_trace.ensure((size_t)trace_total));
+    }
+    if (N == 0) {
+        e->ran = true;
+        e->ran_trace = want_trace != 0;
+        return BA_OK;
+    }
+    const int kernel = 0;  // generic level kernel
+    const int max_grid = e->sm_count * 2;
+    size_t scratch_stride = generic_scratch_ints(nmax, s);
+    {
+        int64_t biggest_wave = 0;
+        for (int w = 0; w < n_waves; ++w) biggest_wave = std::max(biggest_wave, wave_begin[w + 1] - wave_begin[w]);
+        const int grid = (int)std::min<int64_t>(biggest_wave, max_grid);
+        cudaError_t ce = e->d_scratch.ensure(scratch_stride * grid);
+        if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "fill scratch: " + std::string(cudaGetErrorString(ce)));
+    }
+    CU(cudaMemcpyAsync(e->d_desc.p, e->h_desc.data(), sizeof(PairDesc) * N, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemsetAsync(e->d_counter.p, 0, sizeof(int) * n_waves, e->stream));
+
+    std::vector<cudaEvent_t> ev((size_t)n_waves * 3 + 1);
+    for (auto& x : ev) CU(cudaEventCreate(&x));
+    CU(cudaEventRecord(ev[0], e->stream));
+    for (int w = 0; w < n_waves; ++w) {
+        const int64_t b = wave_begin[w], cnt = wave_begin[w + 1] - b;
+        FillArgs A{};
+        A.res = e->d_res.p; A.cls = e->d_cls.p; A.sim = e->d_sim.p; A.sc = e->sc;
+        A.pairs = e->d_desc.p + b; A.npairs = (int)cnt; A.counter = e->d_counter.p + w;
+        A.scratch = e->d_scratch.p; A.scratch_stride = scratch_stride;
+        A.codes = want_trace ? e->d_codes.p : nullptr;
+        A.scores = e->d_scores.p; A.start_state = e->d_start.p; A.end_values = e->d_endv.p;
+        const int grid = (int)std::min<int64_t>(cnt, max_grid);
+        launch_fill_generic(A, grid, want_trace != 0, e->stream);
+        e->stats.kernel_launches++;
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ev[1 + 3 * w], e->stream));
+        if (want_trace) {
+            TraceArgs T{};
+            T.pairs = e->d_desc.p + b; T.npairs = (int)cnt; T.s = s; T.codes = e->d_codes.p;
+            T.start_state = e->d_start.p; T.trace = e->d_trace.p; T.trace_len = e->d_tlen.p; T.complete = e->d_complete.p;
+            launch_traceback(T, e->stream);
+            e->stats.kernel_launches++;
+            CU(cudaGetLastError());
+        }
+        CU(cudaEventRecord(ev[2 + 3 * w], e->stream));
+        CU(cudaEventRecord(ev[3 + 3 * w], e->stream));
+    }
+    CU(cudaStreamSynchronize(e->stream));
+    {
+        float ms = 0;
+        for (int w = 0; w < n_waves; ++w) {
+            const cudaEvent_t prev = (w == 0) ? ev[0] : ev[3 * w];
+            CU(cudaEventElapsedTime(&ms, prev, ev[1 + 3 * w]));
+            e->stats.fill_ms += ms;
+            CU(cudaEventElapsedTime(&ms, ev[1 + 3 * w], ev[2 + 3 * w]));
+            e->stats.traceback_ms += ms;
+        }
+        CU(cudaEventElapsedTime(&ms, ev[0], ev[3 * n_waves]));
+        e->stats.total_ms = ms;
+    }
+    for (auto& x : ev) cudaEventDestroy(x);
+    if (want_trace) {
+        for (int64_t q = wave_begin[n_waves - 1]; q < N; ++q) e->h_last_code_off[e->h_desc[q].orig] = e->h_desc[q].code_off;
+        int64_t cb = 0;
+        for (int64_t p = 0; p < N; ++p) cb += code_words(ln[p], lm[p], s) * 8;
+        e->stats.code_bytes = cb;
+    }
+    e->stats.waves = n_waves;
+    e->stats.kernel_kind = kernel;
+    e->ran = true;
+    e->ran_trace = want_trace != 0;
+    return BA_OK;
+}
+
+int ba_fetch_scores(ba_engine* e, int64_t* scores) {
+    if (!e) return BA_ERR_INVALID_ARG;
+    if (!e->ran) return fail(e, BA_ERR_STATE, "ba_run first");
+    if (e->n_pairs == 0) return BA_OK;
+    if (!scores) return fail(e, BA_ERR_INVALID_ARG, "scores is NULL");
+    CU(cudaSetDevice(e->device));
+    static_assert(sizeof(long long) == sizeof(int64_t), "");
+    CU(cudaMemcpyAsync(scores, e->d_scores.p, sizeof(int64_t) * e->n_pairs, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return BA_OK;
+}
+
+static int fetch_lens(ba_engine* e) {
+    if (e->have_tlen) return BA_OK;
+    e->h_tlen.resize((size_t)e->n_pairs);
+    if (e->n_pairs) {
+        CU(cudaMemcpyAsync(e->h_tlen.data(), e->d_tlen.p, sizeof(int32_t) * e->n_pairs, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    e->have_tlen = true;
+    return BA_OK;
+}
+
+int ba_trace_bytes(ba_engine* e, int64_t* total) {
+    if (!e || !total) return BA_ERR_INVALID_ARG;
+    if (!e->ran || !e->ran_trace) return fail(e, BA_ERR_STATE, "ba_run(want_trace=1) first");
+    CU(cudaSetDevice(e->device));
+    int rc = fetch_lens(e);
+    if (rc) return rc;
+    int64_t t = 0;
+    for (int32_t x : e->h_tlen) t += x;
+    *total = t;
+    return BA_OK;
+}
+
+int ba_fetch_traces(ba_engine* e, uint8_t* cols, int64_t* offsets, uint8_t* complete) {
+    if (!e) return BA_ERR_INVALID_ARG;
+    if (!e->ran || !e->ran_trace) return fail(e, BA_ERR_STATE, "ba_run(want_trace=1) first");
+    if (!offsets) return fail(e, BA_ERR_INVALID_ARG, "offsets is NULL");
+    CU(cudaSetDevice(e->device));
+    int rc = fetch_lens(e);
+    if (rc) return rc;
+    const int64_t N = e->n_pairs;
+    offsets[0] = 0;
+    if (N == 0) return BA_OK;
+    if (!complete) return fail(e, BA_ERR_INVALID_ARG, "complete is NULL");
+    const size_t slot_bytes = (size_t)e->h_slot_off[N - 1] + ((e->h_slot_cap[N - 1] + 15) & ~15);
+    CU(e->h_stage.ensure(slot_bytes));
+    CU(cudaMemcpyAsync(e->h_stage.p, e->d_trace.p, slot_bytes, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(complete, e->d_complete.p, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    int64_t pos = 0;
+    for (int64_t p = 0; p < N; ++p) {
+        const int32_t len = e->h_tlen[p];
+        if (len && !cols) return fail(e, BA_ERR_INVALID_ARG, "cols is NULL");
+        if (len) memcpy(cols + pos, e->h_stage.p + e->h_slot_off[p] + e->h_slot_cap[p] - len, (size_t)len);
+        pos += len;
+        offsets[p + 1] = pos;
+    }
+    return BA_OK;
+}
+
+int ba_align_batch(ba_engine* e, const uint8_t* residues, const uint8_t* classes, const int64_t* offsets,
+                   int64_t n_seq, const int32_t* seq_a, const int32_t* seq_b, int64_t n_pairs, int want_trace,
+                   int64_t* scores) {
+    int rc;
+    if ((rc = ba_load_sequences(e, residues, classes, offsets, n_seq))) return rc;
+    if ((rc = ba_load_pairs(e, seq_a, seq_b, n_pairs))) return rc;
+    if ((rc = ba_run(e, want_trace))) return rc;
+    return ba_fetch_scores(e, scores);
+}
+
+int ba_get_stats(const ba_engine* e, ba_stats* out) {
+    if (!e || !out) return BA_ERR_INVALID_ARG;
+    *out = e->stats;
+    return BA_OK;
+}
+
+int ba_debug_fetch_codes(ba_engine* e, int64_t pair, uint64_t* out, int64_t words) {
+    if (!e || !out) return BA_ERR_INVALID_ARG;
+    if (!e->ran || !e->ran_trace) return fail(e, BA_ERR_STATE, "ba_run(want_trace=1) first");
+    if (pair < 0 || pair >= e->n_pairs || e->h_last_code_off[pair] < 0)
+        return fail(e, BA_ERR_INVALID_ARG, "pair not in the last wave");
+    CU(cudaSetDevice(e->device));
+    const int n = (int)(e->h_off[e->h_pa[pair] + 1] - e->h_off[e->h_pa[pair]]);
+    const int m = (int)(e->h_off[e->h_pb[pair] + 1] - e->h_off[e->h_pb[pair]]);
+    const int64_t need = code_words(n, m, e->sc.s);
+    if (words < need) return fail(e, BA_ERR_INVALID_ARG, "buffer too small");
+    CU(cudaMemcpyAsync(out, e->d_codes.p + e->h_last_code_off[pair], (size_t)need * 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return BA_OK;
+}
+
+int ba_debug_fetch_end_values(ba_engine* e, int64_t pair, int32_t* out9) {
+    if (!e || !out9) return BA_ERR_INVALID_ARG;
+    if (!e->ran) return fail(e, BA_ERR_STATE, "ba_run first");
+    if (pair < 0 || pair >= e->n_pairs) return fail(e, BA_ERR_INVALID_ARG, "pair out of range");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(out9, e->d_endv.p + pair * 9, sizeof(int) * 9, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return BA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,46 @@
+// GPU traceback: a pure pointer chase over the 4-bit code table written by the fill kernels.
+//
+// The reference re-enumerates the cases at every visited cell and breaks ties by the "fewest
+// shifts" key (pyx:547-571); because that key depends only on (predecessor cell, source state) the
+// fill already stored the winner, so each step here is one 8-byte read, a nibble extract and a
+// table decode.  One thread per pair: the walk is a dependent chain of <= 2(n+m) HBM/L2 reads, so
+// throughput comes from running thousands of pairs side by side, not from parallelism inside one.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace ba {
+
+__global__ void __launch_bounds__(128) traceback_kernel(TraceArgs A) {
+    const int pi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= A.npairs) return;
+    const PairDesc d = A.pairs[pi];
+    const uint64_t* codes = A.codes + d.code_off;
+    const int s = A.s, n = d.n, m = d.m;
+    int i = n, j = m, k = n, l = m;
+    int state = A.start_state[d.orig];
+    uint8_t* out = A.trace + d.trace_off + d.trace_cap;  // one past the end of the slot
+    int len = 0, ok = 0;
+    bool first = true;  // the reference's very first termination test never fires (pyx:551, tuple vs list)
+    while (len < d.trace_cap) {
+        if (!first && (i | j | k | l) == 0 && state == 8) { ok = 1; break; }
+        first = false;
+        const uint64_t wd = __ldg(codes + code_index(m, s, i, j, k - i, l - j));
+        const int id = (int)((wd >> (4 * state)) & 15);
+        if (id == 15) break;  // no case reproduced the value (pyx:570-571)
+        int xb, src;
+        decode_case(state, id, xb, src);
+        *--out = (uint8_t)xb;
+        ++len;
+        i -= (xb >> 3) & 1; j -= (xb >> 2) & 1; k -= (xb >> 1) & 1; l -= xb & 1;
+        state = src;
+    }
+    A.trace_len[d.orig] = len;
+    A.complete[d.orig] = (uint8_t)ok;
+}
+
+void launch_traceback(const TraceArgs& A, cudaStream_t st) {
+    const int threads = 128;
+    traceback_kernel<<<(A.npairs + threads - 1) / threads, threads, 0, st>>>(A);
+}
+
+}  // namespace ba
