@@ -71,8 +71,10 @@ class BatchAligner:
             matrix = encoding.read_simmatrix(simmatrix)
             self.symbols, self.table, _ = encoding.simmatrix_table(matrix)
         else:
+            # match/mismatch scoring (pyx:409-412): residues are raw bytes, re-coded densely per batch
             self.symbols = None
-            self.table = encoding.match_table(sequence_match_similarity, sequence_mismatch_similarity)
+            self._match = (int(sequence_match_similarity), int(sequence_mismatch_similarity))
+            self.table = encoding.match_table(*self._match, nsym=4)
         self._device = device
         self._engine = None
 
@@ -92,7 +94,12 @@ class BatchAligner:
             cls.append(encoding.rna_structure_classes(st) if self.type == "RNA" else encoding.encode_bytes(st))
             off.append(off[-1] + len(sq))
         cat = lambda xs: np.concatenate(xs).astype(np.uint8) if xs else np.zeros(0, dtype=np.uint8)  # noqa: E731
-        return cat(res), cat(cls), np.array(off, dtype=np.int64)
+        res = cat(res)
+        if not self.symbols:
+            used, res = np.unique(res, return_inverse=True)
+            res = res.astype(np.uint8)
+            self.table = encoding.match_table(*self._match, nsym=max(len(used), 1))
+        return res, cat(cls), np.array(off, dtype=np.int64)
 
     def configure(self):
         p = self.params

@@ -152,9 +152,11 @@ class BiAligner:
             ra = encoding.encode_residues(sa, symbols)
             rb = encoding.encode_residues(sb, symbols)
         else:
-            table = encoding.match_table(self._params["sequence_match_similarity"],
-                                         self._params["sequence_mismatch_similarity"])
             ra, rb = encoding.encode_bytes(sa), encoding.encode_bytes(sb)
+            used, inv = np.unique(np.concatenate([ra, rb]), return_inverse=True)
+            ra, rb = inv[:len(ra)].astype(np.uint8), inv[len(ra):].astype(np.uint8)
+            table = encoding.match_table(self._params["sequence_match_similarity"],
+                                         self._params["sequence_mismatch_similarity"], nsym=max(len(used), 1))
         if self._is_rna:
             ca, cb = self.molA["cls"], self.molB["cls"]
         else:

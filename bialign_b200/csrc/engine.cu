@@ -92,6 +92,10 @@ struct ba_engine {
     DevBuf<uint64_t> d_codes;
     DevBuf<int> d_scratch;
     DevBuf<int> d_counter;
+    DevBuf<int> d_simp, d_tbtab, d_bnd;
+    std::vector<int32_t> h_sim;
+    int opt_warps = 4;                 // warps per CTA of the systolic kernel
+    int last_fmt = 0;
     DevBuf<long long> d_scores;
     DevBuf<uint8_t> d_start, d_complete, d_trace;
     DevBuf<int> d_endv, d_tlen;
@@ -130,6 +134,73 @@ int64_t band_cells(int64_t n, int64_t m, int64_t s) {
         return c;
     };
     return one(n) * one(m);
+}
+
+// Host-side plan of the systolic kernel: gcd scaling, tie-break bit budget, "minus infinity".
+struct SysPlan {
+    bool ok = false;
+    int g = 1, tb = 0, negp = 0;
+    std::vector<int> sim_p, tbtab;
+};
+
+int64_t gcd64(int64_t a, int64_t b) {
+    a = std::llabs((long long)a);
+    b = std::llabs((long long)b);
+    while (b) { int64_t t = a % b; a = b; b = t; }
+    return a;
+}
+
+// Exactness conditions of the packed 32-bit domain (DESIGN.md "tie-break packing"): every finite value
+// lies in [-Fn, Fp], "minus infinity" values in [negp - Fn, negp + Fp]; the two ranges must not meet
+// and nothing may leave the (32 - tb)-bit field.
+SysPlan plan_systolic(const ba_engine* e, int nmax, int mmax, bool trace) {
+    SysPlan pl;
+    const Scoring& sc = e->sc;
+    const int S = sc.s, nsym = sc.nsym;
+    if (nsym > 64) return pl;
+    int64_t g = gcd64(gcd64(sc.w, sc.beta), gcd64(sc.gamma, sc.delta));
+    int64_t smax = 0, smin = 0;
+    for (int32_t v : e->h_sim) { g = gcd64(g, v); smax = std::max<int64_t>(smax, v); smin = std::min<int64_t>(smin, v); }
+    if (g == 0) g = 1;
+    const int64_t gb = (int64_t)sc.gamma + sc.beta;
+    auto pos = [](std::initializer_list<int64_t> xs) { int64_t m = 0; for (auto x : xs) m = std::max(m, x); return m; };
+    const int64_t c1p = pos({smax, sc.gamma, gb}), c1n = pos({-smin, -(int64_t)sc.gamma, -gb});
+    const int64_t c2p = pos({sc.w, sc.gamma, gb}), c2n = pos({-(int64_t)sc.w, -(int64_t)sc.gamma, -gb});
+    const int64_t dp = pos({sc.delta}), dn = pos({-(int64_t)sc.delta});
+    const int64_t len = (int64_t)nmax + mmax + 2;
+    const int64_t Fp = len * (c1p + c2p + 2 * dp) / g + 2, Fn = len * (c1n + c2n + 2 * dn) / g + 2;
+    int kb = 0;
+    while ((1 << kb) < (S + 2) * (S + 2)) ++kb;
+    pl.tb = trace ? kb + 5 : 0;
+    const int vb = 32 - pl.tb;
+    const int64_t lim = (int64_t)1 << (vb - 1);
+    if (2 * Fn + Fp + 64 >= lim) return pl;
+    const int64_t negv = trace ? -(lim - Fn - 32) : std::max<int64_t>(-(lim - Fn - 32), -((int64_t)1 << 30));
+    if (negv + Fp + 16 >= -Fn) return pl;
+    pl.g = (int)g;
+    pl.negp = (int)(negv * ((int64_t)1 << pl.tb));
+    pl.sim_p.resize((size_t)nsym * nsym);
+    for (size_t q = 0; q < pl.sim_p.size(); ++q) pl.sim_p[q] = (int)((e->h_sim[q] / g) * ((int64_t)1 << pl.tb));
+    if (trace) {
+        // rank of the tie key (k0,k1) = (|T0|+|T1|, |T1|), T = band offset of the cell + (s0-s2, s1-s3): pyx:541-545
+        const int LPR = 2 * S + 2, P = 2 * S + 2, NK = (S + 2) * (S + 2);
+        std::vector<std::pair<int, int>> keys;
+        for (int k1 = 0; k1 <= S + 1; ++k1)
+            for (int d0 = 0; d0 <= S + 1; ++d0) keys.push_back({d0 + k1, k1});
+        std::sort(keys.begin(), keys.end());
+        pl.tbtab.assign((size_t)P * LPR * 12, 0);
+        for (int bb = 0; bb < 2 * S + 1; ++bb)
+            for (int c = 0; c < 2 * S + 1; ++c)
+                for (int src = 0; src < 9; ++src) {
+                    const int s01 = src / 3, s23 = src % 3;
+                    const int T0 = (c - S) + hb0(s01) - hb0(s23), T1 = (bb - S) + hb1(s01) - hb1(s23);
+                    const int k1 = std::abs(T1), k0 = std::abs(T0) + k1;
+                    const int rank = (int)(std::lower_bound(keys.begin(), keys.end(), std::make_pair(k0, k1)) - keys.begin());
+                    pl.tbtab[((size_t)bb * LPR + c) * 12 + src] = ((NK - 1 - rank) << 5) | (18 - src);
+                }
+    }
+    pl.ok = true;
+    return pl;
 }
 
 }  // namespace
@@ -174,6 +245,7 @@ void ba_engine_destroy(ba_engine* e) {
     e->d_sim.release(); e->d_res.release(); e->d_cls.release(); e->d_desc.release(); e->d_codes.release();
     e->d_scratch.release(); e->d_counter.release(); e->d_scores.release(); e->d_start.release();
     e->d_complete.release(); e->d_trace.release(); e->d_endv.release(); e->d_tlen.release(); e->h_stage.release();
+    e->d_simp.release(); e->d_tbtab.release(); e->d_bnd.release();
     cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -184,6 +256,10 @@ int ba_set_option(ba_engine* e, const char* key, int64_t value) {
     if (!e || !key) return BA_ERR_INVALID_ARG;
     if (!strcmp(key, "code_arena_bytes")) e->opt_code_arena_bytes = value;
     else if (!strcmp(key, "kernel")) e->opt_kernel = (int)value;
+    else if (!strcmp(key, "warps_per_cta")) {
+        if (value < 1 || value > 8) return fail(e, BA_ERR_INVALID_ARG, "warps_per_cta must be in 1..8");
+        e->opt_warps = (int)value;
+    }
     else return fail(e, BA_ERR_INVALID_ARG, std::string("unknown option ") + key);
     return BA_OK;
 }
@@ -196,6 +272,7 @@ int ba_set_scoring(ba_engine* e, const int32_t* sim, int nsym, int structure_wei
         return fail(e, BA_ERR_INVALID_ARG, "max_shift must be in 0.." + std::to_string(BA_MAX_SHIFT));
     CU(cudaSetDevice(e->device));
     e->sc = Scoring{structure_weight, gap_opening_cost, gap_cost, shift_cost, max_shift, nsym};
+    e->h_sim.assign(sim, sim + (size_t)nsym * nsym);
     e->max_abs_sim = 0;
     for (int q = 0; q < nsym * nsym; ++q) e->max_abs_sim = std::max<int64_t>(e->max_abs_sim, std::llabs((long long)sim[q]));
     CU(e->d_sim.ensure((size_t)nsym * nsym));
@@ -367,12 +444,50 @@ int ba_run(ba_engine* e, int want_trace) {
         e->ran_trace = want_trace != 0;
         return BA_OK;
     }
-    const int kernel = 0;  // generic level kernel
-    const int max_grid = e->sm_count * 2;
-    size_t scratch_stride = generic_scratch_ints(nmax, s);
-    {
-        int64_t biggest_wave = 0;
-        for (int w = 0; w < n_waves; ++w) biggest_wave = std::max(biggest_wave, wave_begin[w + 1] - wave_begin[w]);
+    int64_t biggest_wave = 0;
+    for (int w = 0; w < n_waves; ++w) biggest_wave = std::max(biggest_wave, wave_begin[w + 1] - wave_begin[w]);
+    // ---- kernel choice: systolic when its exactness conditions hold, else the generic level kernel
+    SysPlan plan;
+    if (e->opt_kernel != 0) plan = plan_systolic(e, nmax, mmax, want_trace != 0);
+    if (e->opt_kernel == 1 && !plan.ok)
+        return fail(e, BA_ERR_SCORE_RANGE, "systolic kernel requested but its packed-integer range conditions do not hold");
+    const int kernel = plan.ok ? 1 : 0;
+    int max_grid = e->sm_count * 2;
+    size_t scratch_stride = 0, sys_smem = 0;
+    int sysG = e->opt_warps;
+    SysArgs SA{};
+    if (kernel == 1) {
+        while (sysG > 1 && sys_smem_bytes(s, sysG, e->sc.nsym, mmax) > 200 * 1024) --sysG;
+        sys_smem = sys_smem_bytes(s, sysG, e->sc.nsym, mmax);
+        const int occ = sys_occupancy(s, want_trace != 0, sysG, sys_smem);
+        if (occ < 1) return fail(e, BA_ERR_CUDA, "systolic kernel does not fit on an SM (shared memory " + std::to_string(sys_smem) + ")");
+        max_grid = e->sm_count * occ;
+        const int grid = (int)std::min<int64_t>(biggest_wave, max_grid);
+        const int rows_pass = sysG * (32 / (2 * s + 2));
+        const bool multi_pass = nmax + 1 > rows_pass;
+        const int biters = sys_iters(s, sysG, mmax);
+        CU(e->d_simp.ensure(plan.sim_p.size()));
+        CU(cudaMemcpyAsync(e->d_simp.p, plan.sim_p.data(), plan.sim_p.size() * 4, cudaMemcpyHostToDevice, e->stream));
+        if (want_trace) {
+            CU(e->d_tbtab.ensure(plan.tbtab.size()));
+            CU(cudaMemcpyAsync(e->d_tbtab.p, plan.tbtab.data(), plan.tbtab.size() * 4, cudaMemcpyHostToDevice, e->stream));
+        }
+        if (multi_pass) {
+            cudaError_t ce = e->d_bnd.ensure((size_t)grid * 2 * sys_boundary_ints(s, sysG, mmax));
+            if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "boundary streams: " + std::string(cudaGetErrorString(ce)));
+        }
+        const int64_t sh = (int64_t)1 << plan.tb;
+        SA.res = e->d_res.p; SA.cls = e->d_cls.p; SA.sim_p = e->d_simp.p; SA.tbtab = e->d_tbtab.p; SA.sc = e->sc;
+        SA.w_p = (int)(e->sc.w / plan.g * sh); SA.beta_p = (int)(e->sc.beta / plan.g * sh);
+        SA.k_gd = (int)((e->sc.gamma + e->sc.delta) / plan.g * sh); SA.k_2g = (int)(2 * e->sc.gamma / plan.g * sh);
+        SA.k_2g2d = (int)((2 * e->sc.gamma + 2 * e->sc.delta) / plan.g * sh); SA.k_2d = (int)(2 * e->sc.delta / plan.g * sh);
+        SA.negp = plan.negp; SA.tb_bits = plan.tb; SA.gscale = plan.g; SA.mmax = mmax;
+        SA.boff = sys_boff(s, sysG); SA.bpad = sys_bpad(s, sysG, mmax);
+        SA.bnd = e->d_bnd.p; SA.bnd_iters = biters;
+        SA.codes = want_trace ? e->d_codes.p : nullptr;
+        SA.scores = e->d_scores.p; SA.start_state = e->d_start.p; SA.end_values = e->d_endv.p;
+    } else {
+        scratch_stride = generic_scratch_ints(nmax, s);
         const int grid = (int)std::min<int64_t>(biggest_wave, max_grid);
         cudaError_t ce = e->d_scratch.ensure(scratch_stride * grid);
         if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "fill scratch: " + std::string(cudaGetErrorString(ce)));
@@ -392,13 +507,18 @@ int ba_run(ba_engine* e, int want_trace) {
         A.codes = want_trace ? e->d_codes.p : nullptr;
         A.scores = e->d_scores.p; A.start_state = e->d_start.p; A.end_values = e->d_endv.p;
         const int grid = (int)std::min<int64_t>(cnt, max_grid);
-        launch_fill_generic(A, grid, want_trace != 0, e->stream);
+        if (kernel == 1) {
+            SA.pairs = e->d_desc.p + b; SA.npairs = (int)cnt; SA.counter = e->d_counter.p + w;
+            CU(launch_fill_systolic(SA, grid, sysG, sys_smem, want_trace != 0, e->stream));
+        } else {
+            launch_fill_generic(A, grid, want_trace != 0, e->stream);
+        }
         e->stats.kernel_launches++;
         CU(cudaGetLastError());
         CU(cudaEventRecord(ev[1 + 3 * w], e->stream));
         if (want_trace) {
             TraceArgs T{};
-            T.pairs = e->d_desc.p + b; T.npairs = (int)cnt; T.s = s; T.codes = e->d_codes.p;
+            T.pairs = e->d_desc.p + b; T.npairs = (int)cnt; T.s = s; T.codes = e->d_codes.p; T.fmt = kernel;
             T.start_state = e->d_start.p; T.trace = e->d_trace.p; T.trace_len = e->d_tlen.p; T.complete = e->d_complete.p;
             launch_traceback(T, e->stream);
             e->stats.kernel_launches++;
@@ -429,6 +549,7 @@ int ba_run(ba_engine* e, int want_trace) {
     }
     e->stats.waves = n_waves;
     e->stats.kernel_kind = kernel;
+    e->last_fmt = kernel;
     e->ran = true;
     e->ran_trace = want_trace != 0;
     return BA_OK;

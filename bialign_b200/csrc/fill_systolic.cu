@@ -1,0 +1,484 @@
+// Systolic affine fill: the fast path.
+//
+// Mapping.  A lane owns one (row i, first-copy/second-copy row offset a = k-i) pair and walks the
+// linearised (j, b = l-j) axis one band cell per iteration; 2S+2 lanes make a row (2S+1 offsets +
+// one always-invalid pad lane), R = 32/(2S+2) rows make a warp, G warps make a CTA that works as
+// ONE systolic array of G*R rows in lock step.  Lane (row r, column c) is sigma = 2r + c
+// iterations behind lane (0,0), and the b axis has period P = 2S+2 (one pad cell per column), so
+// every one of the 15 predecessor columns x = (x0,x1,x2,x3) is a fixed number of iterations
+//      D(x) = x0 + x1*(P-1) + x2 + x3   >= 1
+// in the past, at lane  lane - (x0*(2S+1) + x2).  Pad lanes/cells and out-of-range cells hold
+// "minus infinity", which replaces every band/range guard of the reference (pyx:133-141).
+//
+// Recurrence.  The 15 cases of pyx:255-296 are evaluated in push form: after a cell's nine state
+// values M are known it publishes three 3x3 blocks of partial maxima,
+//      R[s01][x23] = max_{s23} M[s01][s23] + open(s23, x23)        (second alignment decided)
+//      L[x01][s23] = max_{s01} M[s01][s23] + open(s01, x01)        (first alignment decided)
+//      Q[x01][x23] = max_{s01} R[s01][x23] + open(s01, x01)        (both decided)
+// with open(s, x) = beta if x is a gap column half different from s, else 0.  A target state t
+// then needs only three values: Q of the cell at -(t01,t23), R of the cell at -(00,t23), L of the
+// cell at -(t01,00), plus constants built from mu1, mu2, gamma, Delta (affine_score, pyx:84-131, is
+// separable in the two alignments).  ~90 integer instructions per cell instead of 9*15*2.
+//
+// Transport.  Values with x1 = 0 are 1-3 iterations old: warp shuffles from small history
+// registers.  Values with x1 = 1 are P-1..P+2 iterations old: a per-warp shared-memory ring
+// indexed by iteration.  Row 0 of a warp reads the ring of the warp above; row 0 of warp 0 reads a
+// staging ring fed with cp.async from the boundary stream the previous row block ("pass") left in
+// global memory.  One __syncthreads per iteration orders all of it.
+//
+// Traceback codes.  With TRACE the integers carry the tie-break of pyx:555-564 in their low bits:
+// value << TB | (inverted rank of the tie key (|T0|+|T1|, |T1|) of (cell, source state)) << 5 |
+// id field, so plain integer max implements (value desc, key asc, case id asc) exactly.  The id
+// field of the winner (5 bits per state, 45 bits per cell) is streamed to HBM, one 8-byte word per
+// cell, each lane writing its own contiguous stream.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace ba {
+
+namespace {
+
+__device__ __forceinline__ int vmax(int a, int b) { return max(a, b); }
+__device__ __forceinline__ int vmax3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
+__device__ __forceinline__ int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); }  // max(a+b, c)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {  // L2 only (.cg): never a stale L1 line
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// One 3-way "gap opening" reduction: out[x] for x = 01, 10, 11 from in[s] for s = 01, 10, 11.
+//   x = 11 (match column half): best of all three sources (mu is added at the target)
+//   x = gap half g            : max(in[g], beta + max(other two))          (pyx:108-115)
+__device__ __forceinline__ void open3(int i0, int i1, int i2, int beta, int& o0, int& o1, int& o2) {
+    o2 = vmax3(i0, i1, i2);
+    o0 = addmax(vmax(i1, i2), beta, i0);
+    o1 = addmax(vmax(i0, i2), beta, i1);
+}
+
+constexpr int LA = 8;   // cp.async look-ahead (iterations) of the boundary staging
+constexpr int PRE = 4;  // iterations run before position 0: the virtual row above row 0 is 2 iterations ahead,
+                        // so its first records must be staged before lane (0,0) reaches its first cell
+
+}  // namespace
+
+template <int S>
+struct Geo {
+    static constexpr int W = 2 * S + 1;      // band width
+    static constexpr int P = 2 * S + 2;      // cells per column incl. the pad cell
+    static constexpr int LPR = 2 * S + 2;    // lanes per row incl. the pad lane
+    static constexpr int R = 32 / LPR;       // rows per warp
+    static constexpr int RING = P + 3;       // ring depth in iterations (max delay P+2, +1 so reads never meet the write)
+    static constexpr int NV = 12;            // ring values per lane per iteration
+    static constexpr int NX = 6;             // short-delay values crossing a warp boundary
+    static constexpr int PB = 16;            // prefetch-buffer depth (iterations), power of two > LA
+};
+
+// Shared-memory carve-up (ints unless noted), see sys_smem_bytes().
+//   ring   [(G+1)][RING][NV][32]      ring[0] = staging ring of the virtual warp above warp 0
+//   xs     [(G+1)][4][NX][LPR]        short-delay values of the row above each warp; xs[G] = CTA output
+//   pb     [PB][NV+NX][LPR]           cp.async landing zone for the incoming boundary stream
+//   tb     [P][LPR][12]               tie-break constants per (b, lane column, source state)  (TRACE)
+//   sim    [(nsym+1)][nsym]           similarity table (<< TB), last row zero
+//   resB/clsB  bytes, padded
+template <int S>
+__host__ __device__ inline size_t sys_ring_ints(int G) { return (size_t)(G + 1) * Geo<S>::RING * Geo<S>::NV * 32; }
+
+template <int S, bool TRACE>
+__global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
+    using G_ = Geo<S>;
+    constexpr int W = G_::W, P = G_::P, LPR = G_::LPR, R = G_::R, RING = G_::RING, NV = G_::NV, NX = G_::NX, PB = G_::PB;
+    constexpr int RSLOT = NV * 32;
+    constexpr int REC = (NV + NX) * LPR;   // ints per boundary record (one iteration of one row)
+    constexpr int NVEC = REC / 4;
+    static_assert(REC % 4 == 0, "boundary records are copied in 16-byte pieces");
+    extern __shared__ __align__(16) int smem[];
+    const int G = blockDim.x >> 5;
+    const int RT = G * R;  // rows per pass
+    int* ring = smem;
+    int* xs = ring + (size_t)(G + 1) * RING * RSLOT;
+    int* pb = xs + (G + 1) * 4 * NX * LPR;
+    int* tbtab = pb + PB * (NV + NX) * LPR;
+    int* ssim = tbtab + P * LPR * 12;
+    const int nsym = A.sc.nsym;
+    uint8_t* sresB = reinterpret_cast<uint8_t*>(ssim + (nsym + 1) * nsym);
+    const int bpad = A.bpad, boff = A.boff;
+    uint8_t* sclsB = sresB + bpad;
+    __shared__ int s_pair;
+
+    const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+    const int r = lane / LPR, c = lane - r * LPR;
+    const bool lane_real = (r < R) && (c < W);
+    const int a = c - S;
+    const int sigma = 2 * (g * R + r) + c;
+    const bool row0 = (r == 0);
+    const bool lastrow_cta = (g == G - 1) && (r == R - 1);
+    const int TB = TRACE ? A.tb_bits : 0;
+    const int NEGP = A.negp;
+    const int beta = A.beta_p, kGD = A.k_gd, k2G = A.k_2g, k2G2D = A.k_2g2d, k2D = A.k_2d;
+
+    // ---- one-time shared-memory initialisation: everything "minus infinity"
+    for (int q = tid; q < (int)((G + 1) * RING * RSLOT + (G + 1) * 4 * NX * LPR + PB * (NV + NX) * LPR); q += blockDim.x)
+        smem[q] = NEGP;
+    if (TRACE)
+        for (int q = tid; q < P * LPR * 12; q += blockDim.x) tbtab[q] = A.tbtab[q];
+    for (int q = tid; q < (nsym + 1) * nsym; q += blockDim.x) ssim[q] = (q < nsym * nsym) ? A.sim_p[q] : 0;
+    __syncthreads();
+
+    // per-lane source bases inside the ring array (in ints): U sources sit one row up, W one lane left
+    const int own_ring = (g + 1) * RING * RSLOT;
+    const int up_ring = row0 ? g * RING * RSLOT + R * LPR : own_ring;  // row 0 reads the last row of the warp above
+    const int baseU0 = up_ring + lane - (2 * S + 2);                   // source lane for x0=1,x2=1
+    const int baseU1 = up_ring + lane - (2 * S + 1);                   // x0=1,x2=0
+    const int baseW = own_ring + lane - 1;                             // x0=0,x2=1 (lane 0: masked below)
+    const int baseS = own_ring + lane;                                 // self
+    const int xs_in = g * 4 * NX * LPR;                                // xs block feeding this warp's row 0
+    const int xs_out = (g + 1) * 4 * NX * LPR;
+
+    for (;;) {
+        if (tid == 0) s_pair = atomicAdd(A.counter, 1);
+        __syncthreads();
+        const int pi = s_pair;
+        __syncthreads();
+        if (pi >= A.npairs) return;
+        const PairDesc d = A.pairs[pi];
+        const int n = d.n, m = d.m;
+        const uint8_t* ra = A.res + d.offA;
+        const uint8_t* ca = A.cls + d.offA;
+        // stage molecule B (bytes); 1-based position l -> sclsB[l + boff]; 255 (B) / 254 (A) never match
+        for (int q = tid; q < bpad; q += blockDim.x) {
+            const int l = q - boff;
+            sresB[q] = (l >= 1 && l <= m) ? A.res[d.offB + l - 1] : 0;
+            sclsB[q] = (l >= 1 && l <= m) ? A.cls[d.offB + l - 1] : 255;
+        }
+        __syncthreads();
+
+        const int npass = (n + RT) / RT;                 // ceil((n+1)/RT)
+        const int nit = (m + 1) * P + 2 * (RT - 1) + LPR + RING;
+        const size_t bstride = (size_t)A.bnd_iters * (NV + NX) * LPR;  // ints per boundary buffer
+        int* bnd_base = A.bnd + (size_t)blockIdx.x * 2 * bstride;
+
+        for (int pass = 0; pass < npass; ++pass) {
+            const int i = pass * RT + g * R + r;
+            const int k = i + a;
+            const bool lane_ok = lane_real && i <= n && k >= 0 && k <= n;
+            const int Ai = (lane_ok && i >= 1) ? ra[i - 1] : nsym;          // zero row for i = 0
+            const int Ak = (lane_ok && k >= 1) ? ca[k - 1] : 254;
+            const int* simrow = ssim + Ai * nsym;
+            const bool has_in = pass > 0, has_out = pass + 1 < npass;
+            const int* bnd_in = bnd_base + (size_t)((pass + 1) & 1) * bstride;
+            int* bnd_out = bnd_base + (size_t)(pass & 1) * bstride;
+            uint64_t* code_ptr = nullptr;
+            if (TRACE && lane_ok) code_ptr = A.codes + d.code_off + ((long long)i * W + c) * (long long)(m + 1) * W;
+
+            // position of this lane one iteration before the first one (q = -PRE)
+            int pos = -PRE - 1 - sigma;
+            int j = -((-pos + P - 1) / P);
+            int bb = pos - j * P;
+            int wslot = (((-PRE - 1) % RING) + RING) % RING;
+
+            // history registers (outputs of the last 1..3 iterations), all "minus infinity"
+            int hQ10[3] = {NEGP, NEGP, NEGP}, hL10[3] = {NEGP, NEGP, NEGP};
+            int hR[3][3];
+#pragma unroll
+            for (int x = 0; x < 3; ++x)
+#pragma unroll
+                for (int y = 0; y < 3; ++y) hR[x][y] = NEGP;
+            int h2Q1010 = NEGP, h2Q1001 = NEGP, h2Q1011 = NEGP, h3Q1011 = NEGP;
+            int h2R11[3] = {NEGP, NEGP, NEGP};
+
+            if (has_in) {  // prime the cp.async pipeline: records for iterations 0..LA-1
+                for (int t0 = -PRE; t0 < LA - PRE; ++t0) {
+                    for (int e4 = tid; e4 < NVEC; e4 += blockDim.x) {
+                        const int rec = t0 + 2 * RT;
+                        if (rec >= 0 && rec < nit) cp_async16(pb + (t0 & (PB - 1)) * REC + 4 * e4, bnd_in + (size_t)rec * REC + 4 * e4);
+                    }
+                    cp_async_commit();
+                }
+            }
+            __syncthreads();
+
+            for (int q = -PRE; q < nit; ++q) {
+                // ---- advance position
+                ++bb;
+                if (bb == P) { bb = 0; ++j; }
+                wslot = (wslot + 1 == RING) ? 0 : wslot + 1;
+                const int l = j + bb - S;
+                const bool valid = lane_ok && (bb < W) && ((unsigned)j <= (unsigned)m) && ((unsigned)l <= (unsigned)m);
+
+                // ---- similarity inputs of the target cell
+                const int cB = sclsB[l + boff];
+                const int rB = sresB[j + boff];
+                const int mu1 = simrow[rB];
+                const int mu2 = (cB == Ak) ? A.w_p : 0;
+
+                // ---- flush the CTA's last row of iteration q-1 to the outgoing boundary stream
+                if (has_out && q > 0) {
+                    for (int e = tid; e < (NV + NX) * LPR; e += blockDim.x) {
+                        const int v = e / LPR, cs = e - v * LPR;
+                        const int ps = (wslot == 0) ? RING - 1 : wslot - 1;
+                        const int val = (v < NV) ? ring[(G * RING + ps) * RSLOT + v * 32 + (R - 1) * LPR + cs]
+                                                 : xs[(G * 4 + ((q - 1) & 3)) * NX * LPR + (v - NV) * LPR + cs];
+                        bnd_out[(size_t)(q - 1) * (NV + NX) * LPR + e] = val;
+                    }
+                }
+
+                // ---- gather the 27 inputs
+                int rsA = wslot - (P + 2); if (rsA < 0) rsA += RING;   // D = P+2
+                int rsB = wslot - (P + 1); if (rsB < 0) rsB += RING;   // D = P+1
+                int rsC = wslot - P;       if (rsC < 0) rsC += RING;   // D = P
+                int rsD = wslot - (P - 1); if (rsD < 0) rsD += RING;   // D = P-1
+                int inF[9], inH2[9], inH1[9];
+                // long-delay values from the rings (value ids: 0..2 Q[11][01,10,11], 3..5 Q[01][..], 6..8 L[11][..], 9..11 L[01][..])
+                inF[8] = ring[baseU0 + rsA * RSLOT + 2 * 32];            // x=1111 Q[11][11]
+                inF[7] = ring[baseU0 + rsB * RSLOT + 1 * 32];            // x=1110 Q[11][10]
+                inF[6] = ring[baseU1 + rsB * RSLOT + 0 * 32];            // x=1101 Q[11][01]
+                inF[2] = ring[baseW + rsB * RSLOT + 5 * 32];             // x=0111 Q[01][11]
+                inF[1] = ring[baseW + rsC * RSLOT + 4 * 32];             // x=0110 Q[01][10]
+                inF[0] = ring[baseS + rsC * RSLOT + 3 * 32];             // x=0101 Q[01][01]
+#pragma unroll
+                for (int y = 0; y < 3; ++y) {
+                    inH1[6 + y] = ring[baseU1 + rsC * RSLOT + (6 + y) * 32];   // x=1100 L[11][y]
+                    inH1[y] = ring[baseS + rsD * RSLOT + (9 + y) * 32];        // x=0100 L[01][y]
+                }
+                // short-delay values by shuffle
+                inF[5] = __shfl_up_sync(0xffffffffu, h3Q1011, 2 * S + 2);      // x=1011 D=3
+                inF[4] = __shfl_up_sync(0xffffffffu, h2Q1010, 2 * S + 2);      // x=1010 D=2
+                inF[3] = __shfl_up_sync(0xffffffffu, h2Q1001, 2 * S + 1);      // x=1001 D=2
+#pragma unroll
+                for (int y = 0; y < 3; ++y) {
+                    inH1[3 + y] = __shfl_up_sync(0xffffffffu, hL10[y], 2 * S + 1);     // x=1000 D=1  L[10][y]
+                    inH2[3 * y + 2] = __shfl_up_sync(0xffffffffu, h2R11[y], 1);        // x=0011 D=2  R[y][11]
+                    inH2[3 * y + 1] = __shfl_up_sync(0xffffffffu, hR[y][1], 1);        // x=0010 D=1  R[y][10]
+                    inH2[3 * y + 0] = hR[y][0];                                        // x=0001 D=1  R[y][01] (self)
+                }
+                if (row0) {  // the row above lives in another warp (or in the staged boundary)
+                    const int* x3 = xs + xs_in + ((q - 3) & 3) * NX * LPR;
+                    const int* x2 = xs + xs_in + ((q - 2) & 3) * NX * LPR;
+                    const int* x1 = xs + xs_in + ((q - 1) & 3) * NX * LPR;
+                    inF[5] = x3[2 * LPR + c];          // Q[10][11] of lane c (x2=1)
+                    inF[4] = x2[1 * LPR + c];          // Q[10][10]
+                    inF[3] = (c + 1 < LPR) ? x2[0 * LPR + c + 1] : NEGP;   // Q[10][01] of lane c+1 (x2=0)
+#pragma unroll
+                    for (int y = 0; y < 3; ++y) inH1[3 + y] = (c + 1 < LPR) ? x1[(3 + y) * LPR + c + 1] : NEGP;
+                    if (c + 1 >= LPR) { inF[6] = NEGP; inH1[6] = NEGP; inH1[7] = NEGP; inH1[8] = NEGP; }
+                    if (lane == 0) {  // no lane to the left: (i, a-1) is outside the band
+#pragma unroll
+                        for (int y = 0; y < 3; ++y) { inH2[3 * y + 2] = NEGP; inH2[3 * y + 1] = NEGP; }
+                        inF[2] = NEGP; inF[1] = NEGP;
+                    }
+                }
+                // origin: M[1111][0,0,0,0] = 0 (pyx:485) enters as the F input of state 1111 (mu1 = mu2 = 0 there)
+                if (i == 0 && j == 0 && a == 0 && bb == S) inF[8] = 0;
+
+                // ---- the nine target states
+                const int kmm = mu1 + mu2, km1 = mu1 + kGD, km2 = mu2 + kGD;
+                int kF[9] = {k2G, k2G2D, km2, k2G2D, k2G, km2, km1, km1, kmm};
+                int kh2[3], kh1[3];  // per t23 / per t01 (without the tie-break adjustments)
+                kh2[0] = kGD; kh2[1] = kGD; kh2[2] = mu2 + k2D;
+                kh1[0] = kGD; kh1[1] = kGD; kh1[2] = mu1 + k2D;
+                int M[9];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const int t01 = t / 3, t23 = t % 3;
+                    // tie-break id-field adjustments (TRACE): H2 -> 9 - r23, H1 -> 6 - 3*r01 (see engine.cu)
+                    const int c2 = kh2[t23] + (TRACE ? (-9 + 3 * t01) : 0);
+                    const int c1 = kh1[t01] + (TRACE ? (-12 + t23) : 0);
+                    const int v = addmax(inH2[t], c2, inH1[t] + c1);
+                    M[t] = addmax(inF[t], kF[t], v);
+                    M[t] = valid ? M[t] : NEGP;
+                }
+
+                // ---- results at the end cell
+                if (valid && i == n && j == m && a == 0 && bb == S) {
+                    int best = M[0] >> TB;
+#pragma unroll
+                    for (int t = 1; t < 9; ++t) best = max(best, M[t] >> TB);
+                    int st = 0, bsh = 99;
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const int t01 = t / 3, t23 = t % 3;
+                        const int sh = (hb0(t01) != hb0(t23)) + (hb1(t01) != hb1(t23));
+                        if ((M[t] >> TB) == best && sh < bsh) { bsh = sh; st = t; }
+                        A.end_values[(size_t)d.orig * 9 + t] = (M[t] >> TB) * A.gscale;
+                    }
+                    A.scores[d.orig] = (long long)best * A.gscale;
+                    A.start_state[d.orig] = (uint8_t)st;
+                }
+
+                // ---- traceback code word + re-arm the tie-break bits for the role as a source
+                if (TRACE) {
+                    const unsigned lo = (M[0] & 31) | ((M[1] & 31) << 5) | ((M[2] & 31) << 10) | ((M[3] & 31) << 15) |
+                                        ((M[4] & 31) << 20) | ((M[5] & 31) << 25);
+                    const unsigned hi = (M[6] & 31) | ((M[7] & 31) << 5) | ((M[8] & 31) << 10);
+                    if (valid) {
+                        *reinterpret_cast<uint2*>(code_ptr + (long long)j * W + bb) = make_uint2(lo, hi);
+                    }
+                    const int4* tp = reinterpret_cast<const int4*>(tbtab + (bb * LPR + c) * 12);
+                    const int4 ta = tp[0], tbv = tp[1], tc = tp[2];
+                    const int msk = ~((1 << TB) - 1);
+                    M[0] = (M[0] & msk) | ta.x; M[1] = (M[1] & msk) | ta.y; M[2] = (M[2] & msk) | ta.z;
+                    M[3] = (M[3] & msk) | ta.w; M[4] = (M[4] & msk) | tbv.x; M[5] = (M[5] & msk) | tbv.y;
+                    M[6] = (M[6] & msk) | tbv.z; M[7] = (M[7] & msk) | tbv.w; M[8] = (M[8] & msk) | tc.x;
+                }
+
+                // ---- publish: R (second alignment decided), L (first decided), Q (both)
+                int Rv[3][3], Lv[3][3], Qv[3][3];
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    open3(M[3 * x + 0], M[3 * x + 1], M[3 * x + 2], beta, Rv[x][0], Rv[x][1], Rv[x][2]);   // over s23, fixed s01 = x
+                    open3(M[0 + x], M[3 + x], M[6 + x], beta, Lv[0][x], Lv[1][x], Lv[2][x]);               // over s01, fixed s23 = x
+                }
+#pragma unroll
+                for (int y = 0; y < 3; ++y) open3(Rv[0][y], Rv[1][y], Rv[2][y], beta, Qv[0][y], Qv[1][y], Qv[2][y]);
+
+                // ring: long-delay values
+                int* wr = ring + own_ring + wslot * RSLOT + lane;
+#pragma unroll
+                for (int y = 0; y < 3; ++y) {
+                    wr[(0 + y) * 32] = Qv[2][y];
+                    wr[(3 + y) * 32] = Qv[0][y];
+                    wr[(6 + y) * 32] = Lv[2][y];
+                    wr[(9 + y) * 32] = Lv[0][y];
+                }
+                if (r == R - 1 && c < LPR) {  // short-delay values for the warp below / the next pass
+                    int* xo = xs + xs_out + (q & 3) * NX * LPR + c;
+#pragma unroll
+                    for (int y = 0; y < 3; ++y) {
+                        xo[y * LPR] = Qv[1][y];
+                        xo[(3 + y) * LPR] = Lv[1][y];
+                    }
+                }
+                // history shift
+                h3Q1011 = h2Q1011;
+                h2Q1011 = hQ10[2]; h2Q1010 = hQ10[1]; h2Q1001 = hQ10[0];
+#pragma unroll
+                for (int y = 0; y < 3; ++y) {
+                    h2R11[y] = hR[y][2];
+                    hQ10[y] = Qv[1][y];
+                    hL10[y] = Lv[1][y];
+#pragma unroll
+                    for (int z = 0; z < 3; ++z) hR[y][z] = Rv[y][z];
+                }
+
+                // ---- stage the incoming boundary: virtual row above warp 0, iteration q
+                if (has_in) {
+                    cp_async_wait<LA - 1>();
+                    for (int e4 = tid; e4 < NVEC; e4 += blockDim.x) {
+                        const int rec = q + 2 * RT;
+                        int4 val4 = make_int4(NEGP, NEGP, NEGP, NEGP);
+                        if (rec >= 0 && rec < nit) val4 = *reinterpret_cast<const int4*>(pb + (q & (PB - 1)) * REC + 4 * e4);
+                        const int vals[4] = {val4.x, val4.y, val4.z, val4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int e = 4 * e4 + u;
+                            const int v = e / LPR, cs = e - v * LPR;
+                            if (v < NV) ring[(0 * RING + wslot) * RSLOT + v * 32 + (R - 1) * LPR + cs] = vals[u];
+                            else xs[(0 * 4 + (q & 3)) * NX * LPR + (v - NV) * LPR + cs] = vals[u];
+                        }
+                        const int nrec = q + LA + 2 * RT;
+                        if (nrec < nit) cp_async16(pb + ((q + LA) & (PB - 1)) * REC + 4 * e4, bnd_in + (size_t)nrec * REC + 4 * e4);
+                    }
+                    cp_async_commit();
+                }
+                __syncthreads();
+            }  // iterations
+            if (has_out) {  // last iteration's record, then make the stream visible to the next pass
+                for (int e = tid; e < (NV + NX) * LPR; e += blockDim.x) {
+                    const int v = e / LPR, cs = e - v * LPR;
+                    const int val = (v < NV) ? ring[(G * RING + wslot) * RSLOT + v * 32 + (R - 1) * LPR + cs]
+                                             : xs[(G * 4 + ((nit - 1) & 3)) * NX * LPR + (v - NV) * LPR + cs];
+                    bnd_out[(size_t)(nit - 1) * (NV + NX) * LPR + e] = val;
+                }
+                __threadfence();
+            }
+            if (has_in) cp_async_wait<0>();
+            if (!has_out && has_in) {
+                // leaving a multi-pass pair: the staging ring must read "minus infinity" again
+                for (int qq = tid; qq < RING * RSLOT; qq += blockDim.x) ring[qq] = NEGP;
+                for (int qq = tid; qq < 4 * NX * LPR; qq += blockDim.x) xs[qq] = NEGP;
+            }
+            __syncthreads();
+        }  // passes
+    }
+}
+
+// Molecule B is staged with enough slack on both sides for every lane's position during the
+// pipeline fill (negative columns) and drain (columns beyond m).
+int sys_boff(int S, int G) {
+    const int P = 2 * S + 2, RT = G * (32 / P);
+    return (2 * RT + P + 8) / P + 3 + S;
+}
+int sys_bpad(int S, int G, int mmax) {
+    const int P = 2 * S + 2, RT = G * (32 / P);
+    return sys_boff(S, G) + mmax + (2 * RT + 2 * P + 8) / P + S + 6;
+}
+
+template <int S>
+size_t sys_smem_bytes_t(int G, int nsym, int mmax) {
+    using G_ = Geo<S>;
+    size_t ints = (size_t)(G + 1) * G_::RING * G_::NV * 32 + (size_t)(G + 1) * 4 * G_::NX * G_::LPR +
+                  (size_t)G_::PB * (G_::NV + G_::NX) * G_::LPR + (size_t)G_::P * G_::LPR * 12 + (size_t)(nsym + 1) * nsym;
+    size_t bytes = ints * 4 + 2 * (size_t)sys_bpad(S, G, mmax);
+    return (bytes + 15) & ~(size_t)15;
+}
+
+size_t sys_smem_bytes(int S, int G, int nsym, int mmax) {
+    switch (S) {
+        case 0: return sys_smem_bytes_t<0>(G, nsym, mmax);
+        case 1: return sys_smem_bytes_t<1>(G, nsym, mmax);
+        case 2: return sys_smem_bytes_t<2>(G, nsym, mmax);
+        case 3: return sys_smem_bytes_t<3>(G, nsym, mmax);
+        default: return sys_smem_bytes_t<4>(G, nsym, mmax);
+    }
+}
+
+int sys_rows_per_warp(int S) { return 32 / (2 * S + 2); }
+int sys_iters(int S, int G, int m) {
+    const int P = 2 * S + 2;
+    return (m + 1) * P + 2 * (G * (32 / P) - 1) + P + (P + 3);
+}
+size_t sys_boundary_ints(int S, int G, int mmax) { return (size_t)sys_iters(S, G, mmax) * 18 * (2 * S + 2); }
+
+template <int S, bool TRACE>
+static cudaError_t launch_t(const SysArgs& A, int grid, int G, size_t smem, cudaStream_t st) {
+    auto kern = fill_systolic_kernel<S, TRACE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, G * 32, smem, st>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill_systolic(const SysArgs& A, int grid, int G, size_t smem, bool trace, cudaStream_t st) {
+    switch (A.sc.s) {
+        case 0: return trace ? launch_t<0, true>(A, grid, G, smem, st) : launch_t<0, false>(A, grid, G, smem, st);
+        case 1: return trace ? launch_t<1, true>(A, grid, G, smem, st) : launch_t<1, false>(A, grid, G, smem, st);
+        case 2: return trace ? launch_t<2, true>(A, grid, G, smem, st) : launch_t<2, false>(A, grid, G, smem, st);
+        case 3: return trace ? launch_t<3, true>(A, grid, G, smem, st) : launch_t<3, false>(A, grid, G, smem, st);
+        case 4: return trace ? launch_t<4, true>(A, grid, G, smem, st) : launch_t<4, false>(A, grid, G, smem, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int S, bool TRACE>
+static int occ_t(int G, size_t smem) {
+    auto kern = fill_systolic_kernel<S, TRACE>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, G * 32, smem);
+    return nb;
+}
+int sys_occupancy(int S, bool trace, int G, size_t smem) {
+    switch (S) {
+        case 0: return trace ? occ_t<0, true>(G, smem) : occ_t<0, false>(G, smem);
+        case 1: return trace ? occ_t<1, true>(G, smem) : occ_t<1, false>(G, smem);
+        case 2: return trace ? occ_t<2, true>(G, smem) : occ_t<2, false>(G, smem);
+        case 3: return trace ? occ_t<3, true>(G, smem) : occ_t<3, false>(G, smem);
+        default: return trace ? occ_t<4, true>(G, smem) : occ_t<4, false>(G, smem);
+    }
+}
+
+}  // namespace ba

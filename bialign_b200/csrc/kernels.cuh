@@ -20,11 +20,38 @@ struct FillArgs {
     int* end_values;          // [n_pairs][9]  M[t][n,m,n,m]
 };
 
+// Systolic kernel (fill_systolic.cu).  All score constants are divided by the gcd of the scoring
+// parameters (gscale) and, with traceback codes, shifted left by tb_bits.
+struct SysArgs {
+    const uint8_t* res;
+    const uint8_t* cls;
+    const int* sim_p;         // nsym x nsym, scaled and shifted
+    const int* tbtab;         // [P][LPR][12] tie-break constants (TRACE only)
+    Scoring sc;               // unscaled, for s / nsym
+    int w_p, beta_p;          // structure weight, gap opening (scaled, shifted)
+    int k_gd, k_2g, k_2g2d, k_2d;  // gamma+Delta, 2*gamma, 2*gamma+2*Delta, 2*Delta (scaled, shifted)
+    int negp;                 // "minus infinity" in the packed domain
+    int tb_bits;              // low bits reserved for the tie-break (0 when score-only)
+    int gscale;               // gcd the scores were divided by
+    int mmax;                 // longest molecule B of the wave
+    int boff, bpad;           // front offset / total size of the staged molecule-B arrays
+    const PairDesc* pairs;
+    int npairs;
+    int* counter;
+    int* bnd;                 // per CTA: two boundary streams of bnd_iters records
+    int bnd_iters;
+    uint64_t* codes;
+    long long* scores;
+    uint8_t* start_state;
+    int* end_values;
+};
+
 struct TraceArgs {
     const PairDesc* pairs;
     int npairs;
     int s;
     const uint64_t* codes;
+    int fmt;                  // 0: nibble t = case id (generic kernel); 1: 5-bit tie fields (systolic kernel)
     const uint8_t* start_state;
     uint8_t* trace;           // slots; columns are written backwards from the end of each slot
     int* trace_len;           // [n_pairs] caller order
@@ -34,5 +61,13 @@ struct TraceArgs {
 void launch_fill_generic(const FillArgs& A, int grid, bool trace, cudaStream_t st);
 size_t generic_scratch_ints(int nmax, int s);
 void launch_traceback(const TraceArgs& A, cudaStream_t st);
+
+size_t sys_smem_bytes(int S, int G, int nsym, int mmax);
+int sys_iters(int S, int G, int m);
+size_t sys_boundary_ints(int S, int G, int mmax);
+int sys_occupancy(int S, bool trace, int G, size_t smem);
+int sys_boff(int S, int G);
+int sys_bpad(int S, int G, int mmax);
+cudaError_t launch_fill_systolic(const SysArgs& A, int grid, int G, size_t smem, bool trace, cudaStream_t st);
 
 }  // namespace ba

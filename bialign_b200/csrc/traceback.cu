@@ -25,7 +25,20 @@ __global__ void __launch_bounds__(128) traceback_kernel(TraceArgs A) {
         if (!first && (i | j | k | l) == 0 && state == 8) { ok = 1; break; }
         first = false;
         const uint64_t wd = __ldg(codes + code_index(m, s, i, j, k - i, l - j));
-        const int id = (int)((wd >> (4 * state)) & 15);
+        int id;
+        if (A.fmt == 0) {
+            id = (int)((wd >> (4 * state)) & 15);
+        } else {
+            // systolic format: fields 0..5 in the low word, 6..8 in the high word, 5 bits each.  The field
+            // is the id part of the winner's tie-break: 10..18 -> full column, source 18-f (ids 0-8);
+            // 7..9 -> half column x=(0,0,t2,t3), id f+2 (9-11); 0,3,6 -> x=(t0,t1,0,0), id 12+f/3.
+            const unsigned half = state < 6 ? (unsigned)wd : (unsigned)(wd >> 32);
+            const int f = (int)((half >> (5 * (state < 6 ? state : state - 6))) & 31);
+            if (f >= 10 && f <= 18) id = 18 - f;
+            else if (f >= 7 && f <= 9) id = f + 2;
+            else if (f == 0 || f == 3 || f == 6) id = 12 + f / 3;
+            else id = 15;
+        }
         if (id == 15) break;  // no case reproduced the value (pyx:570-571)
         int xb, src;
         decode_case(state, id, xb, src);
@@ -33,6 +46,7 @@ __global__ void __launch_bounds__(128) traceback_kernel(TraceArgs A) {
         ++len;
         i -= (xb >> 3) & 1; j -= (xb >> 2) & 1; k -= (xb >> 1) & 1; l -= xb & 1;
         state = src;
+        if ((i | j | k | l) < 0 || abs(k - i) > s || abs(l - j) > s) break;  // never follows a code out of the band
     }
     A.trace_len[d.orig] = len;
     A.complete[d.orig] = (uint8_t)ok;

@@ -82,22 +82,122 @@ def _random_protein_batch(rng, npairs, lo, hi):
     return seqs, structs, pairs
 
 
-@pytest.mark.parametrize("s", [0, 1, 2, 3])
-def test_random_batch_vs_oracle(s):
-    """Ragged random protein batch vs the CPU oracle: scores, traces and the full code table."""
+def _decode_codes(words, kind):
+    """Device code words -> array [cells, 9] of case ids (15 = none)."""
+    w = words.astype(np.uint64)
+    out = np.zeros((w.size, 9), dtype=np.int64)
+    for t in range(9):
+        if kind == 0:
+            out[:, t] = ((w >> np.uint64(4 * t)) & np.uint64(15)).astype(np.int64)
+        else:
+            sh = 5 * t if t < 6 else 32 + 5 * (t - 6)
+            f = ((w >> np.uint64(sh)) & np.uint64(31)).astype(np.int64)
+            ids = np.full(f.shape, 15, dtype=np.int64)
+            full = (f >= 10) & (f <= 18)
+            ids[full] = 18 - f[full]
+            h2 = (f >= 7) & (f <= 9)
+            ids[h2] = f[h2] + 2
+            h1 = (f == 0) | (f == 3) | (f == 6)
+            ids[h1] = 12 + f[h1] // 3
+            out[:, t] = ids
+    return out
+
+
+def _check_batch(al, seqs, structs, pairs, params, table_pairs=0):
     from bialign_b200.batch import trace_hex
 
+    scores, cols, offsets, complete = al.align(seqs, structs, pairs, want_trace=True)
+    kind = al.engine.stats()["kernel_kind"]
+    for q, (ia, ib) in enumerate(pairs):
+        r = oracle.run(seqs[ia], seqs[ib], structs[ia], structs[ib], params, mode="codes", want_codes=True)
+        assert int(scores[q]) == r["score"], (q, len(seqs[ia]), len(seqs[ib]))
+        assert trace_hex(cols, offsets, q) == r["trace"], (q, len(seqs[ia]), len(seqs[ib]))
+        assert bool(complete[q]) == r["complete"]
+        v, end = oracle.eval_trace(seqs[ia], seqs[ib], structs[ia], structs[ib], params, trace_hex(cols, offsets, q))
+        assert v == r["score"] and end == [len(seqs[ia]), len(seqs[ib])] * 2
+        ev, ov = al.engine.debug_end_values(q).astype(np.int64), r["end_values"].astype(np.int64)
+        fin = ov > -(1 << 29)
+        assert (ev[fin] == ov[fin]).all() and (ev[~fin] < ov[fin].min()).all()
+        if q < table_pairs:
+            # every reachable cell-state's winning case, not only those on the optimal path
+            try:
+                words = al.engine.debug_codes(q, r["codes"].size)
+            except Exception:
+                continue  # pair not in the last wave
+            oc = r["codes"]
+            valid = oc != np.uint64(0xFFFFFFFFFFFFFFFF)
+            want = _decode_codes(oc[valid], 0)
+            got = _decode_codes(words[valid], kind)
+            reach = np.stack([((oc[valid] >> np.uint64(36 + t)) & np.uint64(1)).astype(bool) for t in range(9)], axis=1)
+            reach &= want != 15
+            assert (want[reach] == got[reach]).all(), q
+    # score-only run (no tie-break bits, no code stores) must give the same scores
+    s2 = al.align(seqs, structs, pairs, want_trace=False)
+    assert (s2 == scores).all()
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("s", [0, 1, 2, 3, 4])
+def test_random_batch_vs_oracle(s, kernel):
+    """Ragged random protein batch vs the CPU oracle: scores, traces, end values and code tables."""
     rng = np.random.default_rng(100 + s)
     params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150, gap_cost=-50,
                   shift_cost=-150, max_shift=s)
     seqs, structs, pairs = _random_protein_batch(rng, 24, 1, 70)
     al = _aligner(params)
-    scores, cols, offsets, complete = al.align(seqs, structs, pairs, want_trace=True)
+    al.engine.set_option("kernel", kernel)
+    try:
+        _check_batch(al, seqs, structs, pairs, params, table_pairs=24)
+        assert al.engine.stats()["kernel_kind"] == kernel
+    finally:
+        al.engine.set_option("kernel", -1)
+
+
+@pytest.mark.parametrize("warps", [1, 2, 4, 8])
+def test_systolic_multipass_and_cta_shapes(warps):
+    """Pairs longer than one row block (several passes through the boundary stream), all CTA widths."""
+    rng = np.random.default_rng(500 + warps)
+    for s, tie in ((2, {}), (1, {"shift_cost": 0}), (3, {"structure_weight": 0, "gap_cost": 0})):
+        params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150,
+                      gap_cost=-50, shift_cost=-150, max_shift=s)
+        params.update(tie)
+        seqs, structs, pairs = _random_protein_batch(rng, 6, 60, 150)
+        al = _aligner(params)
+        al.engine.set_option("kernel", 1)
+        al.engine.set_option("warps_per_cta", warps)
+        try:
+            _check_batch(al, seqs, structs, pairs, params, table_pairs=2)
+            assert al.engine.stats()["kernel_kind"] == 1
+        finally:
+            al.engine.set_option("kernel", -1)
+            al.engine.set_option("warps_per_cta", 4)
+
+
+def test_rna_batch_score_only_vs_oracle():
+    """cfg4-shaped: RNA with supplied dot-bracket structures, match/mismatch similarity, score only."""
+    rng = np.random.default_rng(4)
+    params = dict(type="RNA", simmatrix=None, structure_weight=400, gap_opening_cost=-200, gap_cost=-50,
+                  shift_cost=-150, max_shift=2, sequence_match_similarity=100, sequence_mismatch_similarity=0)
+    seqs, structs, pairs = [], [], []
+    for q in range(16):
+        for _ in range(2):
+            L = int(rng.integers(30, 121))
+            seqs.append("".join("ACGU"[i] for i in rng.integers(0, 4, L)))
+            st, stack = [], []
+            for i in range(L):
+                u = rng.random()
+                if u < 0.3:
+                    stack.append(i); st.append("(")
+                elif u < 0.6 and stack and i - stack[-1] >= 3:
+                    stack.pop(); st.append(")")
+                else:
+                    st.append(".")
+            for i in stack:
+                st[i] = "."
+            structs.append("".join(st))
+        pairs.append((2 * q, 2 * q + 1))
+    al = _aligner(params)
+    scores = al.align(seqs, structs, pairs, want_trace=False)
     for q, (ia, ib) in enumerate(pairs):
-        r = oracle.run(seqs[ia], seqs[ib], structs[ia], structs[ib], params, mode="codes", want_codes=(q < 6))
+        r = oracle.run(seqs[ia], seqs[ib], structs[ia], structs[ib], params, mode="codes")
         assert int(scores[q]) == r["score"], q
-        assert trace_hex(cols, offsets, q) == r["trace"], q
-        assert bool(complete[q]) == r["complete"]
-        v, end = oracle.eval_trace(seqs[ia], seqs[ib], structs[ia], structs[ib], params, trace_hex(cols, offsets, q))
-        assert v == r["score"] and end == [len(seqs[ia]), len(seqs[ib])] * 2
-        assert (al.engine.debug_end_values(q) == r["end_values"]).all()
