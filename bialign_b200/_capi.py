@@ -12,7 +12,8 @@ BA_OK, BA_ERR_INVALID_ARG, BA_ERR_NO_DEVICE, BA_ERR_CUDA, BA_ERR_OOM, BA_ERR_SCO
 
 SYMBOLS = ["ba_engine_create", "ba_engine_destroy", "ba_last_error", "ba_set_scoring", "ba_load_sequences",
            "ba_load_pairs", "ba_run", "ba_fetch_scores", "ba_trace_bytes", "ba_fetch_traces", "ba_align_batch",
-           "ba_get_stats", "ba_set_option", "ba_debug_fetch_codes", "ba_debug_fetch_end_values", "ba_version"]
+           "ba_get_stats", "ba_set_option", "ba_debug_fetch_codes", "ba_debug_fetch_end_values", "ba_microbench_int",
+           "ba_version"]
 
 
 class BaStats(ctypes.Structure):
@@ -59,6 +60,7 @@ def load_library():
     L.ba_debug_fetch_codes.argtypes = [vp, i64, vp, i64]
     L.ba_debug_fetch_end_values.argtypes = [vp, i64, vp]
     L.ba_version.restype = ctypes.c_char_p
+    L.ba_microbench_int.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32)]
     _lib = L
     return L
 
@@ -163,6 +165,16 @@ class Engine:
         out = np.empty(9, dtype=np.int32)
         self._check(self._L.ba_debug_fetch_end_values(self._h, int(pair), _ptr(out)))
         return out
+
+
+def microbench_int(device, kind):
+    """Measured integer-pipe rate (thread-instructions/s) and SM count of `device`."""
+    L = load_library()
+    rate, sms = ctypes.c_double(0), ctypes.c_int(0)
+    rc = L.ba_microbench_int(int(device), int(kind), ctypes.byref(rate), ctypes.byref(sms))
+    if rc:
+        raise BialignError(rc, "ba_microbench_int failed")
+    return rate.value, sms.value
 
 
 _engines = {}

@@ -46,6 +46,12 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {  
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    // 4-byte copies go through L1 (.ca); the boundary stream is written by this same SM (write-through
+    // stores keep its L1 coherent), so no stale line can be observed in single-CTA-per-pair mode
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
@@ -133,7 +139,10 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
     const int up_ring = row0 ? g * RING * RSLOT + R * LPR : own_ring;  // row 0 reads the last row of the warp above
     const int baseU0 = up_ring + lane - (2 * S + 2);                   // source lane for x0=1,x2=1
     const int baseU1 = up_ring + lane - (2 * S + 1);                   // x0=1,x2=0
-    const int baseW = own_ring + lane - 1;                             // x0=0,x2=1 (lane 0: masked below)
+    // lane 0 has no left neighbour; lane 31 is a pad or idle lane for every S, i.e. a permanent source of
+    // "minus infinity", so lane 0 reads it instead (no special case in the loop)
+    const int lsrcW = (lane == 0) ? 31 : lane - 1;
+    const int baseW = own_ring + lsrcW;                                // x0=0,x2=1
     const int baseS = own_ring + lane;                                 // self
     const int xs_in = g * 4 * NX * LPR;                                // xs block feeding this warp's row 0
     const int xs_out = (g + 1) * 4 * NX * LPR;
@@ -171,6 +180,15 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
             const bool has_in = pass > 0, has_out = pass + 1 < npass;
             const int* bnd_in = bnd_base + (size_t)((pass + 1) & 1) * bstride;
             int* bnd_out = bnd_base + (size_t)(pass & 1) * bstride;
+            // boundary I/O descriptors: thread e moves record element e (= v*LPR + cs) every iteration
+            const bool io_thread = tid < REC;
+            const int io_v = tid / LPR, io_cs = tid - io_v * LPR;
+            const bool io_ring = io_v < NV;
+            const int io_stride = io_ring ? RSLOT : NX * LPR;
+            const int io_col = io_ring ? io_v * 32 + (R - 1) * LPR + io_cs : (int)((G + 1) * RING * RSLOT) + (io_v - NV) * LPR + io_cs;
+            const int fl_src = io_col + (io_ring ? G * RING * RSLOT : G * 4 * NX * LPR);   // CTA output row
+            const int st_dst = io_col;                                                     // ring[0] / xs[0]
+            const bool io_fast = REC <= (int)blockDim.x;
             uint64_t* code_ptr = nullptr;
             if (TRACE && lane_ok) code_ptr = A.codes + d.code_off + ((long long)i * W + c) * (long long)(m + 1) * W;
 
@@ -190,11 +208,11 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
             int h2Q1010 = NEGP, h2Q1001 = NEGP, h2Q1011 = NEGP, h3Q1011 = NEGP;
             int h2R11[3] = {NEGP, NEGP, NEGP};
 
-            if (has_in) {  // prime the cp.async pipeline: records for iterations 0..LA-1
+            if (has_in) {  // prime the cp.async pipeline: records for iterations -PRE..LA-PRE-1
                 for (int t0 = -PRE; t0 < LA - PRE; ++t0) {
-                    for (int e4 = tid; e4 < NVEC; e4 += blockDim.x) {
+                    for (int e = tid; e < REC; e += blockDim.x) {
                         const int rec = t0 + 2 * RT;
-                        if (rec >= 0 && rec < nit) cp_async16(pb + (t0 & (PB - 1)) * REC + 4 * e4, bnd_in + (size_t)rec * REC + 4 * e4);
+                        if (rec >= 0 && rec < nit) cp_async4(pb + (t0 & (PB - 1)) * REC + e, bnd_in + (size_t)rec * REC + e);
                     }
                     cp_async_commit();
                 }
@@ -217,12 +235,16 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
 
                 // ---- flush the CTA's last row of iteration q-1 to the outgoing boundary stream
                 if (has_out && q > 0) {
-                    for (int e = tid; e < (NV + NX) * LPR; e += blockDim.x) {
-                        const int v = e / LPR, cs = e - v * LPR;
-                        const int ps = (wslot == 0) ? RING - 1 : wslot - 1;
-                        const int val = (v < NV) ? ring[(G * RING + ps) * RSLOT + v * 32 + (R - 1) * LPR + cs]
-                                                 : xs[(G * 4 + ((q - 1) & 3)) * NX * LPR + (v - NV) * LPR + cs];
-                        bnd_out[(size_t)(q - 1) * (NV + NX) * LPR + e] = val;
+                    const int ps = (wslot == 0) ? RING - 1 : wslot - 1;
+                    if (io_fast) {
+                        if (io_thread) bnd_out[(size_t)(q - 1) * REC + tid] = smem[fl_src + (io_ring ? ps : ((q - 1) & 3)) * io_stride];
+                    } else {
+                        for (int e = tid; e < REC; e += blockDim.x) {
+                            const int v = e / LPR, cs = e - v * LPR;
+                            const int val = (v < NV) ? ring[(G * RING + ps) * RSLOT + v * 32 + (R - 1) * LPR + cs]
+                                                     : xs[(G * 4 + ((q - 1) & 3)) * NX * LPR + (v - NV) * LPR + cs];
+                            bnd_out[(size_t)(q - 1) * REC + e] = val;
+                        }
                     }
                 }
 
@@ -251,25 +273,24 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
 #pragma unroll
                 for (int y = 0; y < 3; ++y) {
                     inH1[3 + y] = __shfl_up_sync(0xffffffffu, hL10[y], 2 * S + 1);     // x=1000 D=1  L[10][y]
-                    inH2[3 * y + 2] = __shfl_up_sync(0xffffffffu, h2R11[y], 1);        // x=0011 D=2  R[y][11]
-                    inH2[3 * y + 1] = __shfl_up_sync(0xffffffffu, hR[y][1], 1);        // x=0010 D=1  R[y][10]
+                    inH2[3 * y + 2] = __shfl_sync(0xffffffffu, h2R11[y], lsrcW);       // x=0011 D=2  R[y][11]
+                    inH2[3 * y + 1] = __shfl_sync(0xffffffffu, hR[y][1], lsrcW);       // x=0010 D=1  R[y][10]
                     inH2[3 * y + 0] = hR[y][0];                                        // x=0001 D=1  R[y][01] (self)
                 }
-                if (row0) {  // the row above lives in another warp (or in the staged boundary)
-                    const int* x3 = xs + xs_in + ((q - 3) & 3) * NX * LPR;
-                    const int* x2 = xs + xs_in + ((q - 2) & 3) * NX * LPR;
-                    const int* x1 = xs + xs_in + ((q - 1) & 3) * NX * LPR;
-                    inF[5] = x3[2 * LPR + c];          // Q[10][11] of lane c (x2=1)
-                    inF[4] = x2[1 * LPR + c];          // Q[10][10]
-                    inF[3] = (c + 1 < LPR) ? x2[0 * LPR + c + 1] : NEGP;   // Q[10][01] of lane c+1 (x2=0)
-#pragma unroll
-                    for (int y = 0; y < 3; ++y) inH1[3 + y] = (c + 1 < LPR) ? x1[(3 + y) * LPR + c + 1] : NEGP;
-                    if (c + 1 >= LPR) { inF[6] = NEGP; inH1[6] = NEGP; inH1[7] = NEGP; inH1[8] = NEGP; }
-                    if (lane == 0) {  // no lane to the left: (i, a-1) is outside the band
-#pragma unroll
-                        for (int y = 0; y < 3; ++y) { inH2[3 * y + 2] = NEGP; inH2[3 * y + 1] = NEGP; }
-                        inF[2] = NEGP; inF[1] = NEGP;
-                    }
+                {   // row 0: the row above lives in another warp (or in the staged boundary) -> xs, not shuffles.
+                    // Loads are unconditional (rows > 0 read the same in-bounds words and drop them); the pad lane
+                    // of row 0 reads one element past its row, which is in bounds and never used (its cell is invalid).
+                    const int* x3 = xs + xs_in + ((q - 3) & 3) * NX * LPR + c;
+                    const int* x2 = xs + xs_in + ((q - 2) & 3) * NX * LPR + c;
+                    const int* x1 = xs + xs_in + ((q - 1) & 3) * NX * LPR + c;
+                    const int a5 = x3[2 * LPR], a4 = x2[1 * LPR], a3 = x2[0 * LPR + 1];
+                    const int b0 = x1[3 * LPR + 1], b1 = x1[4 * LPR + 1], b2 = x1[5 * LPR + 1];
+                    inF[5] = row0 ? a5 : inF[5];       // Q[10][11] of lane c   (x2 = 1)
+                    inF[4] = row0 ? a4 : inF[4];       // Q[10][10] of lane c
+                    inF[3] = row0 ? a3 : inF[3];       // Q[10][01] of lane c+1 (x2 = 0)
+                    inH1[3] = row0 ? b0 : inH1[3];     // L[10][*]  of lane c+1
+                    inH1[4] = row0 ? b1 : inH1[4];
+                    inH1[5] = row0 ? b2 : inH1[5];
                 }
                 // origin: M[1111][0,0,0,0] = 0 (pyx:485) enters as the F input of state 1111 (mu1 = mu2 = 0 there)
                 if (i == 0 && j == 0 && a == 0 && bb == S) inF[8] = 0;
@@ -367,20 +388,21 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                 // ---- stage the incoming boundary: virtual row above warp 0, iteration q
                 if (has_in) {
                     cp_async_wait<LA - 1>();
-                    for (int e4 = tid; e4 < NVEC; e4 += blockDim.x) {
-                        const int rec = q + 2 * RT;
-                        int4 val4 = make_int4(NEGP, NEGP, NEGP, NEGP);
-                        if (rec >= 0 && rec < nit) val4 = *reinterpret_cast<const int4*>(pb + (q & (PB - 1)) * REC + 4 * e4);
-                        const int vals[4] = {val4.x, val4.y, val4.z, val4.w};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int e = 4 * e4 + u;
-                            const int v = e / LPR, cs = e - v * LPR;
-                            if (v < NV) ring[(0 * RING + wslot) * RSLOT + v * 32 + (R - 1) * LPR + cs] = vals[u];
-                            else xs[(0 * 4 + (q & 3)) * NX * LPR + (v - NV) * LPR + cs] = vals[u];
+                    const int rec = q + 2 * RT, nrec = rec + LA;
+                    if (io_fast) {
+                        if (io_thread) {
+                            const int val = (rec >= 0 && rec < nit) ? pb[(q & (PB - 1)) * REC + tid] : NEGP;
+                            smem[st_dst + (io_ring ? wslot : (q & 3)) * io_stride] = val;
+                            if (nrec < nit) cp_async4(pb + ((q + LA) & (PB - 1)) * REC + tid, bnd_in + (size_t)nrec * REC + tid);
                         }
-                        const int nrec = q + LA + 2 * RT;
-                        if (nrec < nit) cp_async16(pb + ((q + LA) & (PB - 1)) * REC + 4 * e4, bnd_in + (size_t)nrec * REC + 4 * e4);
+                    } else {
+                        for (int e = tid; e < REC; e += blockDim.x) {
+                            const int v = e / LPR, cs = e - v * LPR;
+                            const int val = (rec >= 0 && rec < nit) ? pb[(q & (PB - 1)) * REC + e] : NEGP;
+                            if (v < NV) ring[(0 * RING + wslot) * RSLOT + v * 32 + (R - 1) * LPR + cs] = val;
+                            else xs[(0 * 4 + (q & 3)) * NX * LPR + (v - NV) * LPR + cs] = val;
+                            if (nrec < nit) cp_async4(pb + ((q + LA) & (PB - 1)) * REC + e, bnd_in + (size_t)nrec * REC + e);
+                        }
                     }
                     cp_async_commit();
                 }

@@ -110,6 +110,10 @@ BA_API int ba_debug_fetch_codes(ba_engine* e, int64_t pair, uint64_t* out, int64
 /* Test hook: the nine end values M[t][n,m,n,m] of pair p. */
 BA_API int ba_debug_fetch_end_values(ba_engine* e, int64_t pair, int32_t* out9);
 
+/* Roofline denominator: measured thread-instructions per second of the integer pipes on `device`
+ * (kind 0: add, 1: xor+max pairs, 2: fused add+max VIADDMNMX).  Used by bench.py only. */
+BA_API int ba_microbench_int(int device, int kind, double* instr_per_s, int* sm_count);
+
 BA_API const char* ba_version(void);
 
 #ifdef __cplusplus
