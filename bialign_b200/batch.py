@@ -131,3 +131,19 @@ class BatchAligner:
 
 def trace_hex(cols, offsets, p):
     return "".join("%x" % c for c in cols[offsets[p]:offsets[p + 1]])
+
+
+def gather_scores(mine, scores, n_total, device=None):
+    """All ranks' scores in caller order.  `mine` = this rank's pair indices (from lpt_shards),
+    `scores` = their scores.  Uses the default torch.distributed group (NCCL on GPUs, gloo in CPU
+    tests); with a single process it is a plain scatter.  This is the only cross-rank step of the
+    batch path -- a result gather, not a data-path collective."""
+    import torch
+    import torch.distributed as dist
+
+    full = torch.zeros(n_total, dtype=torch.int64, device=device)
+    full[torch.as_tensor(np.asarray(mine), dtype=torch.int64, device=device)] = torch.as_tensor(
+        np.asarray(scores, dtype=np.int64), device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(full, op=dist.ReduceOp.SUM)  # shards are disjoint, so SUM == concatenation
+    return full.cpu().numpy()

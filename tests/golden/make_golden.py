@@ -54,9 +54,11 @@ def run_ref(seqA, seqB, strA, strB, params):
         b = bialignment.BiAligner(seqA, seqB, strA, strB, **p)
         score = int(b.optimize())
         tr = b.traceback()
+        full = [[name, row] for name, row in b.decode_trace_full(tr)]
+        ev = list(b.eval_trace(tr))
     return dict(seqA=seqA, seqB=seqB, strA=strA, strB=strB, params=params, score=score,
                 trace="".join("%x" % (8 * x[0] + 4 * x[1] + 2 * x[2] + x[3]) for x in tr),
-                warned="incomplete traceback" in buf.getvalue())
+                warned="incomplete traceback" in buf.getvalue(), full=full, eval_tail=ev[-2:])
 
 
 PROT = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150, gap_cost=-50,

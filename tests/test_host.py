@@ -1,0 +1,172 @@
+"""CPU tests of the host side: C-ABI export list, encoders, scheduler arithmetic, presentation layer
+(against rows recorded from the unmodified reference).  No GPU, no compute calls into the library."""
+import ctypes
+import io
+import contextlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from bialign_b200 import _capi
+
+    header = open(os.path.join(ROOT, "include", "bialign_b200.h")).read()
+    declared = set(re.findall(r"BA_API[^;(]*?\b(ba_[a-z_0-9]+)\s*\(", header))
+    assert declared and declared == set(_capi.SYMBOLS)
+    lib = _capi.load_library()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert b"sm_100a" in lib.ba_version()
+
+
+def test_no_cpu_path_without_device():
+    """The product must fail loudly without a GPU (this container has none; on the GPU box this is skipped)."""
+    from bialign_b200 import _capi
+
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    with pytest.raises(_capi.BialignError) as ei:
+        _capi.Engine(0)
+    assert ei.value.code == _capi.BA_ERR_NO_DEVICE
+    from bialign_b200 import bialignment as ba
+
+    b = ba.BiAligner("AC", "AC", "HH", "HH", type="Protein", gap_cost=-50, gap_opening_cost=-150, max_shift=1,
+                     simmatrix="BLOSUM62", structure_weight=800, shift_cost=-150)
+    with pytest.raises(_capi.BialignError):
+        b.optimize()
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "bialign_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "bialign_oracle" not in txt and "oracle/" not in txt, f
+
+
+def test_band_cells_formula_against_enumeration():
+    from bialign_b200.batch import band_cells
+
+    for n, m, s in [(0, 0, 1), (1, 3, 2), (5, 5, 0), (7, 4, 3), (3, 9, 4), (42, 42, 1)]:
+        cnt = 0
+        for i in range(n + 1):
+            for j in range(m + 1):
+                cnt += (min(n, i + s) - max(0, i - s) + 1) * (min(m, j + s) - max(0, j - s) + 1)
+        assert int(band_cells(n, m, s)) == cnt
+    assert int(band_cells(42, 42, 1)) * 9 == 145161  # config 1
+
+
+def test_lpt_shards_partition_and_balance():
+    from bialign_b200.batch import lpt_shards
+
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 7, 100, 5000):
+        costs = rng.integers(1, 1000, n)
+        for w in (1, 2, 8):
+            sh = lpt_shards(costs, w)
+            allidx = np.sort(np.concatenate(sh)) if n else np.zeros(0)
+            assert allidx.size == n and (allidx == np.arange(n)).all()
+            if n >= 100:
+                loads = np.array([costs[x].sum() for x in sh])
+                assert loads.max() <= loads.mean() * 1.05 + costs.max()
+
+
+def test_encoders_match_oracle_side():
+    import oracle
+    from bialign_b200 import encoding
+
+    t_o = oracle.blosum62_table()
+    m = encoding.read_simmatrix("BLOSUM62")
+    for a in encoding.ALPHABET:
+        for b in encoding.ALPHABET:
+            assert m[a][b] == t_o[ord(a), ord(b)]
+    for st in ["...(((.....))).....", "()", "(())..((", ".(.).", "((.))()", "", "(((", "a(b)c"]:
+        assert (encoding.rna_structure_classes(st) == oracle.rna_classes(st)).all()
+    with pytest.raises(IndexError):
+        encoding.rna_structure_classes("())")  # unbalanced ')' like pyx:387
+
+
+def test_constructor_error_conventions():
+    from bialign_b200 import bialignment as ba
+
+    base = dict(type="Protein", gap_cost=-50, gap_opening_cost=-150, max_shift=1, simmatrix=None)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf), pytest.raises(SystemExit) as ei:
+        ba.BiAligner("ACD", "ACD", None, "HHH", **base)
+    assert ei.value.code == -1 and buf.getvalue().startswith("ERROR: Structures have to be provided")
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf), pytest.raises(SystemExit):
+        ba.BiAligner("ACD", "ACD", "HH", "HHH", **base)
+    assert "must have the same length" in buf.getvalue()
+    with pytest.raises(KeyError):
+        ba.BiAligner("ACD", "ACD", "HHH", "HHH", type="Protein", gap_cost=-50, max_shift=1, simmatrix=None)
+
+
+def _aligner_for(case):
+    from bialign_b200 import bialignment as ba
+
+    return ba.BiAligner(case["seqA"], case["seqB"], case["strA"], case["strB"], nameA="A", nameB="B", **case["params"])
+
+
+def test_decode_trace_full_matches_reference_rows(golden_cases):
+    """The 14 named rows (incl. the RNA consensus structure via the MEA fold) for every golden trace."""
+    checked = 0
+    for c in golden_cases:
+        b = _aligner_for(c)
+        trace = [[int(ch, 16) >> 3 & 1, int(ch, 16) >> 2 & 1, int(ch, 16) >> 1 & 1, int(ch, 16) & 1] for ch in c["trace"]]
+        if c["params"]["gap_opening_cost"] == 0:
+            trace = [tuple(x) for x in trace]
+        got = [[n, r] for n, r in b.decode_trace_full(trace)]
+        assert got == c["full"], (c["seqA"], c["seqB"], c["params"])
+        ev = list(b.eval_trace(trace))
+        assert ev[-2:] == c["eval_tail"]
+        checked += 1
+    assert checked == len(golden_cases)
+
+
+def test_outmodes_and_readme_rna_default_output(golden_cases):
+    from bialign_b200 import bialignment as ba
+
+    c = golden_cases[0]  # README RNA toy (README.md:90-104)
+    b = _aligner_for(c)
+    trace = [[int(ch, 16) >> 3 & 1, int(ch, 16) >> 2 & 1, int(ch, 16) >> 1 & 1, int(ch, 16) & 1] for ch in c["trace"]]
+    lines = b.decode_trace(trace)
+    assert lines == ["A               GCGGGGGAUAUCCCC-AUCG", "B               G---GGGAUAUCCCC-AUCG",
+                     "A ss            ...-(((.....))).....", "B ss            .---(((.....)))-....",
+                     "A shifts        ...<...........>....", "B shifts        ...................."]
+    assert ba.BiAligner.auto_complete("sorted_t", ba.BiAligner.outmodes.keys()) == "sorted_terse"
+    assert ba.BiAligner.auto_complete("s", ba.BiAligner.outmodes.keys()) == "sorted"
+    p = golden_cases[3]  # README protein toy, max_shift 1, sorted mode (README.md:136-152)
+    b = _aligner_for(p)
+    b._params["outmode"] = "sorted"
+    trace = [[int(ch, 16) >> 3 & 1, int(ch, 16) >> 2 & 1, int(ch, 16) >> 1 & 1, int(ch, 16) & 1] for ch in p["trace"]]
+    out = b.decode_trace(trace)
+    assert out[0] == "A ss            -CHHHHHHHHHHHHHCCCCTCEEEEEEECCTCEEEEEEEEC-CC"
+    assert out[2] == "consensus       -.AKLPLKEKKLT.TANYHPGIRYIMTGYSAK.IYSSTYA.-FR"
+    assert out[6] == "" and out[-2] == "A shifts        >............<..................<........>.."
+    b._params["outmode"] = "nonsense"
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        out2 = b.decode_trace(trace)
+    assert buf.getvalue().startswith("WARNING: unknown output mode") and out2 == out
+
+
+def test_cfssp_reader_on_synthetic_report(tmp_path):
+    from bialign_b200 import bialignment as ba
+
+    txt = "Secondary Structure:\n\nQuery 1   MVQIP 5 \nHelix 1   HHH   5 \nStruc 1   EEHHC 5 \n\nQuery 6   AK 7 \nStruc 6   CC 7 \n"
+    assert ba.read_molecule(txt, "Protein") == ["MVQIPAK", "EEHHCCC"]
+    with pytest.raises(IOError):
+        ba.read_molecule(txt, "RNA")
+    f = tmp_path / "x.cfssp"
+    f.write_text(txt)
+    assert ba.read_molecule_from_file(str(f), "Protein") == ["MVQIPAK", "EEHHCCC"]
