@@ -95,6 +95,7 @@ struct ba_engine {
     DevBuf<int> d_simp, d_tbtab, d_bnd;
     std::vector<int32_t> h_sim;
     int opt_warps = 4;                 // warps per CTA of the systolic kernel
+    int opt_pad = -1;                  // systolic flavour: -1 auto, 0 pad-free, 1 padded
     int last_fmt = 0;
     DevBuf<long long> d_scores;
     DevBuf<uint8_t> d_start, d_complete, d_trace;
@@ -139,6 +140,7 @@ int64_t band_cells(int64_t n, int64_t m, int64_t s) {
 // Host-side plan of the systolic kernel: gcd scaling, tie-break bit budget, "minus infinity".
 struct SysPlan {
     bool ok = false;
+    bool pad = true, bneg = false;   // kernel flavour (fill_systolic.cuh)
     int g = 1, tb = 0, negp = 0;
     std::vector<int> sim_p, tbtab;
 };
@@ -174,16 +176,29 @@ SysPlan plan_systolic(const ba_engine* e, int nmax, int mmax, bool trace) {
     pl.tb = trace ? kb + 5 : 0;
     const int vb = 32 - pl.tb;
     const int64_t lim = (int64_t)1 << (vb - 1);
-    if (2 * Fn + Fp + 64 >= lim) return pl;
-    const int64_t negv = trace ? -(lim - Fn - 32) : std::max<int64_t>(-(lim - Fn - 32), -((int64_t)1 << 30));
-    if (negv + Fp + 16 >= -Fn) return pl;
+    pl.bneg = sc.beta < 0;
+    // pad-free flavour: band-edge cases carry a poison of NEGP and values are floored at NEGP, so the most
+    // negative intermediate is (floored source) + two poisons + constants  >=  3*negv - Fn
+    const int64_t negv_nopad = -(Fn + Fp + 64);
+    const bool nopad_ok = pl.bneg && (-3 * negv_nopad + Fn + 64 < lim);
+    const bool pad_ok = (2 * Fn + Fp + 64 < lim);
+    if (e->opt_pad == 0 && !nopad_ok) return pl;
+    if (e->opt_pad == 1 && !pad_ok) return pl;
+    pl.pad = (e->opt_pad == 1) || (e->opt_pad < 0 && !nopad_ok);
+    if (pl.pad && !pad_ok) return pl;
+    int64_t negv = negv_nopad;
+    if (pl.pad) {
+        negv = trace ? -(lim - Fn - 32) : std::max<int64_t>(-(lim - Fn - 32), -((int64_t)1 << 30));
+        if (negv + Fp + 16 >= -Fn) return pl;
+    }
     pl.g = (int)g;
     pl.negp = (int)(negv * ((int64_t)1 << pl.tb));
     pl.sim_p.resize((size_t)nsym * nsym);
     for (size_t q = 0; q < pl.sim_p.size(); ++q) pl.sim_p[q] = (int)((e->h_sim[q] / g) * ((int64_t)1 << pl.tb));
     if (trace) {
         // rank of the tie key (k0,k1) = (|T0|+|T1|, |T1|), T = band offset of the cell + (s0-s2, s1-s3): pyx:541-545
-        const int LPR = 2 * S + 2, P = 2 * S + 2, NK = (S + 2) * (S + 2);
+        const SysGeo geo = sys_geo(S, pl.pad);
+        const int LPR = geo.LPR, P = geo.P, NK = (S + 2) * (S + 2);
         std::vector<std::pair<int, int>> keys;
         for (int k1 = 0; k1 <= S + 1; ++k1)
             for (int d0 = 0; d0 <= S + 1; ++d0) keys.push_back({d0 + k1, k1});
@@ -256,6 +271,7 @@ int ba_set_option(ba_engine* e, const char* key, int64_t value) {
     if (!e || !key) return BA_ERR_INVALID_ARG;
     if (!strcmp(key, "code_arena_bytes")) e->opt_code_arena_bytes = value;
     else if (!strcmp(key, "kernel")) e->opt_kernel = (int)value;
+    else if (!strcmp(key, "pad")) e->opt_pad = (int)value;
     else if (!strcmp(key, "warps_per_cta")) {
         if (value < 1 || value > 8) return fail(e, BA_ERR_INVALID_ARG, "warps_per_cta must be in 1..8");
         e->opt_warps = (int)value;
@@ -457,15 +473,15 @@ int ba_run(ba_engine* e, int want_trace) {
     int sysG = e->opt_warps;
     SysArgs SA{};
     if (kernel == 1) {
-        while (sysG > 1 && sys_smem_bytes(s, sysG, e->sc.nsym, mmax) > 200 * 1024) --sysG;
-        sys_smem = sys_smem_bytes(s, sysG, e->sc.nsym, mmax);
-        const int occ = sys_occupancy(s, want_trace != 0, sysG, sys_smem);
+        while (sysG > 1 && sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax) > 200 * 1024) --sysG;
+        sys_smem = sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax);
+        const int occ = sys_occupancy(s, want_trace != 0, plan.pad, plan.bneg, sysG, sys_smem);
         if (occ < 1) return fail(e, BA_ERR_CUDA, "systolic kernel does not fit on an SM (shared memory " + std::to_string(sys_smem) + ")");
         max_grid = e->sm_count * occ;
         const int grid = (int)std::min<int64_t>(biggest_wave, max_grid);
-        const int rows_pass = sysG * (32 / (2 * s + 2));
+        const int rows_pass = sysG * sys_geo(s, plan.pad).R;
         const bool multi_pass = nmax + 1 > rows_pass;
-        const int biters = sys_iters(s, sysG, mmax);
+        const int biters = sys_iters(s, plan.pad, sysG, mmax);
         CU(e->d_simp.ensure(plan.sim_p.size()));
         CU(cudaMemcpyAsync(e->d_simp.p, plan.sim_p.data(), plan.sim_p.size() * 4, cudaMemcpyHostToDevice, e->stream));
         if (want_trace) {
@@ -473,7 +489,7 @@ int ba_run(ba_engine* e, int want_trace) {
             CU(cudaMemcpyAsync(e->d_tbtab.p, plan.tbtab.data(), plan.tbtab.size() * 4, cudaMemcpyHostToDevice, e->stream));
         }
         if (multi_pass) {
-            cudaError_t ce = e->d_bnd.ensure((size_t)grid * 2 * sys_boundary_ints(s, sysG, mmax));
+            cudaError_t ce = e->d_bnd.ensure((size_t)grid * 2 * sys_boundary_ints(s, plan.pad, sysG, mmax));
             if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "boundary streams: " + std::string(cudaGetErrorString(ce)));
         }
         const int64_t sh = (int64_t)1 << plan.tb;
@@ -482,7 +498,7 @@ int ba_run(ba_engine* e, int want_trace) {
         SA.k_gd = (int)((e->sc.gamma + e->sc.delta) / plan.g * sh); SA.k_2g = (int)(2 * e->sc.gamma / plan.g * sh);
         SA.k_2g2d = (int)((2 * e->sc.gamma + 2 * e->sc.delta) / plan.g * sh); SA.k_2d = (int)(2 * e->sc.delta / plan.g * sh);
         SA.negp = plan.negp; SA.tb_bits = plan.tb; SA.gscale = plan.g; SA.mmax = mmax;
-        SA.boff = sys_boff(s, sysG); SA.bpad = sys_bpad(s, sysG, mmax);
+        SA.boff = sys_boff(s, plan.pad, sysG); SA.bpad = sys_bpad(s, plan.pad, sysG, mmax);
         SA.bnd = e->d_bnd.p; SA.bnd_iters = biters;
         SA.codes = want_trace ? e->d_codes.p : nullptr;
         SA.scores = e->d_scores.p; SA.start_state = e->d_start.p; SA.end_values = e->d_endv.p;
@@ -509,7 +525,7 @@ int ba_run(ba_engine* e, int want_trace) {
         const int grid = (int)std::min<int64_t>(cnt, max_grid);
         if (kernel == 1) {
             SA.pairs = e->d_desc.p + b; SA.npairs = (int)cnt; SA.counter = e->d_counter.p + w;
-            CU(launch_fill_systolic(SA, grid, sysG, sys_smem, want_trace != 0, e->stream));
+            CU(launch_fill_systolic(SA, grid, sysG, sys_smem, want_trace != 0, plan.pad, plan.bneg, e->stream));
         } else {
             launch_fill_generic(A, grid, want_trace != 0, e->stream);
         }
@@ -548,7 +564,7 @@ int ba_run(ba_engine* e, int want_trace) {
         e->stats.code_bytes = cb;
     }
     e->stats.waves = n_waves;
-    e->stats.kernel_kind = kernel;
+    e->stats.kernel_kind = kernel == 0 ? 0 : (plan.pad ? 2 : 1);
     e->last_fmt = kernel;
     e->ran = true;
     e->ran_trace = want_trace != 0;

@@ -1,54 +1,57 @@
-// Systolic affine fill: the fast path.
+// Systolic affine fill: the fast path (template; instantiated per max_shift in fill_systolic_s*.cu).
 //
-// Mapping.  A lane owns one (row i, first-copy/second-copy row offset a = k-i) pair and walks the
-// linearised (j, b = l-j) axis one band cell per iteration; 2S+2 lanes make a row (2S+1 offsets +
-// one always-invalid pad lane), R = 32/(2S+2) rows make a warp, G warps make a CTA that works as
-// ONE systolic array of G*R rows in lock step.  Lane (row r, column c) is sigma = 2r + c
-// iterations behind lane (0,0), and the b axis has period P = 2S+2 (one pad cell per column), so
-// every one of the 15 predecessor columns x = (x0,x1,x2,x3) is a fixed number of iterations
+// Mapping.  A lane owns one (row i, row offset a = k-i) pair and walks the linearised (j, b = l-j)
+// axis one band cell per iteration; LPR lanes make a row, R = 32/LPR rows make a warp, G warps make
+// a CTA that works as ONE systolic array of G*R rows in lock step.  Lane (row r, column c) is
+// sigma = 2r + c iterations behind lane (0,0) and the b axis has period P, so every one of the 15
+// predecessor columns x = (x0,x1,x2,x3) of pyx:255-296 is a fixed number of iterations
 //      D(x) = x0 + x1*(P-1) + x2 + x3   >= 1
-// in the past, at lane  lane - (x0*(2S+1) + x2).  Pad lanes/cells and out-of-range cells hold
-// "minus infinity", which replaces every band/range guard of the reference (pyx:133-141).
+// in the past, at lane  lane - (x0*(LPR-1) + x2).  Cells outside the sequences hold "minus
+// infinity" (NEGP), which replaces the range half of the reference's guard (pyx:133-138); the band
+// half (pyx:139-140) comes in two flavours:
+//   PAD = true   one always-invalid pad lane per row and one pad cell per column (LPR = P = 2S+2):
+//                band-edge sources are pad cells, nothing to mask;
+//   PAD = false  no pads (LPR = P = 2S+1, 20-30% more useful lanes and iterations): band-edge
+//                sources are the wrong cells, so the additive constant of exactly those cases carries
+//                a "poison" of NEGP; every value is clamped from below at NEGP, so at most three
+//                NEGP can pile up -- the host only selects this flavour when that fits the integer
+//                range (engine.cu, plan_systolic).
 //
-// Recurrence.  The 15 cases of pyx:255-296 are evaluated in push form: after a cell's nine state
-// values M are known it publishes three 3x3 blocks of partial maxima,
+// Recurrence.  Push form: after a cell's nine state values M are known it publishes three 3x3
+// blocks of partial maxima,
 //      R[s01][x23] = max_{s23} M[s01][s23] + open(s23, x23)        (second alignment decided)
 //      L[x01][s23] = max_{s01} M[s01][s23] + open(s01, x01)        (first alignment decided)
 //      Q[x01][x23] = max_{s01} R[s01][x23] + open(s01, x01)        (both decided)
-// with open(s, x) = beta if x is a gap column half different from s, else 0.  A target state t
-// then needs only three values: Q of the cell at -(t01,t23), R of the cell at -(00,t23), L of the
-// cell at -(t01,00), plus constants built from mu1, mu2, gamma, Delta (affine_score, pyx:84-131, is
-// separable in the two alignments).  ~90 integer instructions per cell instead of 9*15*2.
+// with open(s, x) = beta if x is a gap half different from s, else 0.  A target state t then needs
+// three values -- Q of the cell at -(t01,t23), R of the cell at -(00,t23), L of the cell at
+// -(t01,00) -- plus constants built from mu1, mu2, gamma, Delta: affine_score (pyx:84-131) is
+// separable in the two alignments.  BNEG (beta < 0) shortens open() to one fused add-max.
 //
-// Transport.  Values with x1 = 0 are 1-3 iterations old: warp shuffles from small history
-// registers.  Values with x1 = 1 are P-1..P+2 iterations old: a per-warp shared-memory ring
-// indexed by iteration.  Row 0 of a warp reads the ring of the warp above; row 0 of warp 0 reads a
-// staging ring fed with cp.async from the boundary stream the previous row block ("pass") left in
-// global memory.  One __syncthreads per iteration orders all of it.
+// Transport.  x1 = 0 values are 1-3 iterations old: warp shuffles from history registers.  x1 = 1
+// values are P-1..P+2 iterations old: a per-warp shared-memory ring indexed by iteration.  Row 0 of
+// a warp reads the ring (and the short-delay exchange block xs) of the warp above; row 0 of warp 0
+// reads a staging ring fed by cp.async from the boundary stream that the previous row block
+// ("pass") left in global memory.  One __syncthreads per iteration orders all of it.
 //
 // Traceback codes.  With TRACE the integers carry the tie-break of pyx:555-564 in their low bits:
 // value << TB | (inverted rank of the tie key (|T0|+|T1|, |T1|) of (cell, source state)) << 5 |
 // id field, so plain integer max implements (value desc, key asc, case id asc) exactly.  The id
 // field of the winner (5 bits per state, 45 bits per cell) is streamed to HBM, one 8-byte word per
 // cell, each lane writing its own contiguous stream.
+#pragma once
 #include "common.cuh"
 #include "kernels.cuh"
 
 namespace ba {
-
-namespace {
+namespace sys {
 
 __device__ __forceinline__ int vmax(int a, int b) { return max(a, b); }
 __device__ __forceinline__ int vmax3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 __device__ __forceinline__ int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); }  // max(a+b, c)
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {  // L2 only (.cg): never a stale L1 line
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
     // 4-byte copies go through L1 (.ca); the boundary stream is written by this same SM (write-through
-    // stores keep its L1 coherent), so no stale line can be observed in single-CTA-per-pair mode
+    // stores keep its L1 coherent), so no stale line can be observed in CTA-per-pair mode
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
@@ -57,57 +60,58 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // One 3-way "gap opening" reduction: out[x] for x = 01, 10, 11 from in[s] for s = 01, 10, 11.
-//   x = 11 (match column half): best of all three sources (mu is added at the target)
-//   x = gap half g            : max(in[g], beta + max(other two))          (pyx:108-115)
+//   x = 11 (match half): best of all three sources (mu is added at the target)
+//   x = gap half g     : max(in[g], beta + max(other two))                       (pyx:108-115)
+// With beta < 0 the own source may join the inner max (beta + in[g] < in[g] never wins).
+template <bool BNEG>
 __device__ __forceinline__ void open3(int i0, int i1, int i2, int beta, int& o0, int& o1, int& o2) {
     o2 = vmax3(i0, i1, i2);
-    o0 = addmax(vmax(i1, i2), beta, i0);
-    o1 = addmax(vmax(i0, i2), beta, i1);
+    if (BNEG) {
+        o0 = addmax(o2, beta, i0);
+        o1 = addmax(o2, beta, i1);
+    } else {
+        o0 = addmax(vmax(i1, i2), beta, i0);
+        o1 = addmax(vmax(i0, i2), beta, i1);
+    }
 }
 
 constexpr int LA = 8;   // cp.async look-ahead (iterations) of the boundary staging
 constexpr int PRE = 4;  // iterations run before position 0: the virtual row above row 0 is 2 iterations ahead,
                         // so its first records must be staged before lane (0,0) reaches its first cell
 
-}  // namespace
-
-template <int S>
+template <int S, bool PAD>
 struct Geo {
-    static constexpr int W = 2 * S + 1;      // band width
-    static constexpr int P = 2 * S + 2;      // cells per column incl. the pad cell
-    static constexpr int LPR = 2 * S + 2;    // lanes per row incl. the pad lane
-    static constexpr int R = 32 / LPR;       // rows per warp
-    static constexpr int RING = P + 3;       // ring depth in iterations (max delay P+2, +1 so reads never meet the write)
-    static constexpr int NV = 12;            // ring values per lane per iteration
-    static constexpr int NX = 6;             // short-delay values crossing a warp boundary
-    static constexpr int PB = 16;            // prefetch-buffer depth (iterations), power of two > LA
+    static constexpr int W = 2 * S + 1;                      // band width
+    static constexpr int LPR = PAD ? 2 * S + 2 : 2 * S + 1;  // lanes per row
+    static constexpr int P = PAD ? 2 * S + 2 : (S == 0 ? 2 : 2 * S + 1);  // cells per column (S = 0 keeps its pad cell: D >= 1)
+    static constexpr int R = 32 / LPR;                       // rows per warp
+    static constexpr int RING = P + 3;                       // ring depth in iterations (max delay P+2; +1: reads never meet the write)
+    static constexpr int NV = 12;                            // ring values per lane per iteration
+    static constexpr int NX = 6;                             // short-delay values crossing a warp boundary
+    static constexpr int PB = 16;                            // prefetch-buffer depth (iterations), power of two > LA
+    static constexpr int REC = (NV + NX) * LPR;              // ints per boundary record (one iteration of one row)
+    static constexpr int RSLOT = NV * 32;
 };
 
-// Shared-memory carve-up (ints unless noted), see sys_smem_bytes().
+// Shared-memory carve-up (ints unless noted):
 //   ring   [(G+1)][RING][NV][32]      ring[0] = staging ring of the virtual warp above warp 0
 //   xs     [(G+1)][4][NX][LPR]        short-delay values of the row above each warp; xs[G] = CTA output
-//   pb     [PB][NV+NX][LPR]           cp.async landing zone for the incoming boundary stream
+//   pb     [PB][REC]                  cp.async landing zone for the incoming boundary stream
 //   tb     [P][LPR][12]               tie-break constants per (b, lane column, source state)  (TRACE)
 //   sim    [(nsym+1)][nsym]           similarity table (<< TB), last row zero
 //   resB/clsB  bytes, padded
-template <int S>
-__host__ __device__ inline size_t sys_ring_ints(int G) { return (size_t)(G + 1) * Geo<S>::RING * Geo<S>::NV * 32; }
-
-template <int S, bool TRACE>
+template <int S, bool TRACE, bool PAD, bool BNEG>
 __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
-    using G_ = Geo<S>;
+    using G_ = Geo<S, PAD>;
     constexpr int W = G_::W, P = G_::P, LPR = G_::LPR, R = G_::R, RING = G_::RING, NV = G_::NV, NX = G_::NX, PB = G_::PB;
-    constexpr int RSLOT = NV * 32;
-    constexpr int REC = (NV + NX) * LPR;   // ints per boundary record (one iteration of one row)
-    constexpr int NVEC = REC / 4;
-    static_assert(REC % 4 == 0, "boundary records are copied in 16-byte pieces");
+    constexpr int RSLOT = G_::RSLOT, REC = G_::REC;
     extern __shared__ __align__(16) int smem[];
     const int G = blockDim.x >> 5;
     const int RT = G * R;  // rows per pass
     int* ring = smem;
     int* xs = ring + (size_t)(G + 1) * RING * RSLOT;
     int* pb = xs + (G + 1) * 4 * NX * LPR;
-    int* tbtab = pb + PB * (NV + NX) * LPR;
+    int* tbtab = pb + PB * REC;
     int* ssim = tbtab + P * LPR * 12;
     const int nsym = A.sc.nsym;
     uint8_t* sresB = reinterpret_cast<uint8_t*>(ssim + (nsym + 1) * nsym);
@@ -121,14 +125,16 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
     const int a = c - S;
     const int sigma = 2 * (g * R + r) + c;
     const bool row0 = (r == 0);
-    const bool lastrow_cta = (g == G - 1) && (r == R - 1);
     const int TB = TRACE ? A.tb_bits : 0;
     const int NEGP = A.negp;
     const int beta = A.beta_p, kGD = A.k_gd, k2G = A.k_2g, k2G2D = A.k_2g2d, k2D = A.k_2d;
+    // band-edge poisons of the pad-free flavour (lane constants): sources at a+1 (x0=1,x2=0) do not exist for
+    // the last column, sources at a-1 (x0=0,x2=1) do not exist for the first one
+    const int pU1 = (!PAD && c == W - 1) ? NEGP : 0;
+    const int pW = (!PAD && c == 0) ? NEGP : 0;
 
     // ---- one-time shared-memory initialisation: everything "minus infinity"
-    for (int q = tid; q < (int)((G + 1) * RING * RSLOT + (G + 1) * 4 * NX * LPR + PB * (NV + NX) * LPR); q += blockDim.x)
-        smem[q] = NEGP;
+    for (int q = tid; q < (int)((G + 1) * RING * RSLOT + (G + 1) * 4 * NX * LPR + PB * REC); q += blockDim.x) smem[q] = NEGP;
     if (TRACE)
         for (int q = tid; q < P * LPR * 12; q += blockDim.x) tbtab[q] = A.tbtab[q];
     for (int q = tid; q < (nsym + 1) * nsym; q += blockDim.x) ssim[q] = (q < nsym * nsym) ? A.sim_p[q] : 0;
@@ -137,10 +143,10 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
     // per-lane source bases inside the ring array (in ints): U sources sit one row up, W one lane left
     const int own_ring = (g + 1) * RING * RSLOT;
     const int up_ring = row0 ? g * RING * RSLOT + R * LPR : own_ring;  // row 0 reads the last row of the warp above
-    const int baseU0 = up_ring + lane - (2 * S + 2);                   // source lane for x0=1,x2=1
-    const int baseU1 = up_ring + lane - (2 * S + 1);                   // x0=1,x2=0
-    // lane 0 has no left neighbour; lane 31 is a pad or idle lane for every S, i.e. a permanent source of
-    // "minus infinity", so lane 0 reads it instead (no special case in the loop)
+    const int baseU0 = up_ring + lane - LPR;                           // source lane for x0=1,x2=1 (same column)
+    const int baseU1 = up_ring + lane - (LPR - 1);                     // x0=1,x2=0 (column + 1)
+    // lane 0 has no left neighbour; lane 31 is a pad or idle lane (PAD) or lane 0's W inputs are poisoned
+    // (!PAD), so lane 0 simply reads lane 31 (no special case in the loop)
     const int lsrcW = (lane == 0) ? 31 : lane - 1;
     const int baseW = own_ring + lsrcW;                                // x0=0,x2=1
     const int baseS = own_ring + lane;                                 // self
@@ -165,16 +171,16 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
         }
         __syncthreads();
 
-        const int npass = (n + RT) / RT;                 // ceil((n+1)/RT)
+        const int npass = (n + RT) / RT;  // ceil((n+1)/RT)
         const int nit = (m + 1) * P + 2 * (RT - 1) + LPR + RING;
-        const size_t bstride = (size_t)A.bnd_iters * (NV + NX) * LPR;  // ints per boundary buffer
+        const size_t bstride = (size_t)A.bnd_iters * REC;  // ints per boundary buffer
         int* bnd_base = A.bnd + (size_t)blockIdx.x * 2 * bstride;
 
         for (int pass = 0; pass < npass; ++pass) {
             const int i = pass * RT + g * R + r;
             const int k = i + a;
             const bool lane_ok = lane_real && i <= n && k >= 0 && k <= n;
-            const int Ai = (lane_ok && i >= 1) ? ra[i - 1] : nsym;          // zero row for i = 0
+            const int Ai = (lane_ok && i >= 1) ? ra[i - 1] : nsym;  // zero row for i = 0
             const int Ak = (lane_ok && k >= 1) ? ca[k - 1] : 254;
             const int* simrow = ssim + Ai * nsym;
             const bool has_in = pass > 0, has_out = pass + 1 < npass;
@@ -185,9 +191,10 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
             const int io_v = tid / LPR, io_cs = tid - io_v * LPR;
             const bool io_ring = io_v < NV;
             const int io_stride = io_ring ? RSLOT : NX * LPR;
-            const int io_col = io_ring ? io_v * 32 + (R - 1) * LPR + io_cs : (int)((G + 1) * RING * RSLOT) + (io_v - NV) * LPR + io_cs;
-            const int fl_src = io_col + (io_ring ? G * RING * RSLOT : G * 4 * NX * LPR);   // CTA output row
-            const int st_dst = io_col;                                                     // ring[0] / xs[0]
+            const int io_col = io_ring ? io_v * 32 + (R - 1) * LPR + io_cs
+                                       : (int)((G + 1) * RING * RSLOT) + (io_v - NV) * LPR + io_cs;
+            const int fl_src = io_col + (io_ring ? G * RING * RSLOT : G * 4 * NX * LPR);  // CTA output row
+            const int st_dst = io_col;                                                    // ring[0] / xs[0]
             const bool io_fast = REC <= (int)blockDim.x;
             uint64_t* code_ptr = nullptr;
             if (TRACE && lane_ok) code_ptr = A.codes + d.code_off + ((long long)i * W + c) * (long long)(m + 1) * W;
@@ -197,6 +204,7 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
             int j = -((-pos + P - 1) / P);
             int bb = pos - j * P;
             int wslot = (((-PRE - 1) % RING) + RING) % RING;
+            int mu1 = 0;
 
             // history registers (outputs of the last 1..3 iterations), all "minus infinity"
             int hQ10[3] = {NEGP, NEGP, NEGP}, hL10[3] = {NEGP, NEGP, NEGP};
@@ -227,10 +235,9 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                 const int l = j + bb - S;
                 const bool valid = lane_ok && (bb < W) && ((unsigned)j <= (unsigned)m) && ((unsigned)l <= (unsigned)m);
 
-                // ---- similarity inputs of the target cell
+                // ---- similarity inputs of the target cell (mu1 changes once per column)
                 const int cB = sclsB[l + boff];
-                const int rB = sresB[j + boff];
-                const int mu1 = simrow[rB];
+                if (bb == 0) mu1 = simrow[sresB[j + boff]];
                 const int mu2 = (cB == Ak) ? A.w_p : 0;
 
                 // ---- flush the CTA's last row of iteration q-1 to the outgoing boundary stream
@@ -249,58 +256,75 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                 }
 
                 // ---- gather the 27 inputs
-                int rsA = wslot - (P + 2); if (rsA < 0) rsA += RING;   // D = P+2
-                int rsB = wslot - (P + 1); if (rsB < 0) rsB += RING;   // D = P+1
-                int rsC = wslot - P;       if (rsC < 0) rsC += RING;   // D = P
-                int rsD = wslot - (P - 1); if (rsD < 0) rsD += RING;   // D = P-1
+                int rsA = wslot - (P + 2); if (rsA < 0) rsA += RING;  // D = P+2
+                int rsB = wslot - (P + 1); if (rsB < 0) rsB += RING;  // D = P+1
+                int rsC = wslot - P;       if (rsC < 0) rsC += RING;  // D = P
+                int rsD = wslot - (P - 1); if (rsD < 0) rsD += RING;  // D = P-1
                 int inF[9], inH2[9], inH1[9];
-                // long-delay values from the rings (value ids: 0..2 Q[11][01,10,11], 3..5 Q[01][..], 6..8 L[11][..], 9..11 L[01][..])
-                inF[8] = ring[baseU0 + rsA * RSLOT + 2 * 32];            // x=1111 Q[11][11]
-                inF[7] = ring[baseU0 + rsB * RSLOT + 1 * 32];            // x=1110 Q[11][10]
-                inF[6] = ring[baseU1 + rsB * RSLOT + 0 * 32];            // x=1101 Q[11][01]
-                inF[2] = ring[baseW + rsB * RSLOT + 5 * 32];             // x=0111 Q[01][11]
-                inF[1] = ring[baseW + rsC * RSLOT + 4 * 32];             // x=0110 Q[01][10]
-                inF[0] = ring[baseS + rsC * RSLOT + 3 * 32];             // x=0101 Q[01][01]
+                // long-delay values from the rings (ids: 0..2 Q[11][01,10,11], 3..5 Q[01][..], 6..8 L[11][..], 9..11 L[01][..])
+                inF[8] = ring[baseU0 + rsA * RSLOT + 2 * 32];  // x=1111 Q[11][11]
+                inF[7] = ring[baseU0 + rsB * RSLOT + 1 * 32];  // x=1110 Q[11][10]
+                inF[6] = ring[baseU1 + rsB * RSLOT + 0 * 32];  // x=1101 Q[11][01]
+                inF[2] = ring[baseW + rsB * RSLOT + 5 * 32];   // x=0111 Q[01][11]
+                inF[1] = ring[baseW + rsC * RSLOT + 4 * 32];   // x=0110 Q[01][10]
+                inF[0] = ring[baseS + rsC * RSLOT + 3 * 32];   // x=0101 Q[01][01]
 #pragma unroll
                 for (int y = 0; y < 3; ++y) {
-                    inH1[6 + y] = ring[baseU1 + rsC * RSLOT + (6 + y) * 32];   // x=1100 L[11][y]
-                    inH1[y] = ring[baseS + rsD * RSLOT + (9 + y) * 32];        // x=0100 L[01][y]
+                    inH1[6 + y] = ring[baseU1 + rsC * RSLOT + (6 + y) * 32];  // x=1100 L[11][y]
+                    inH1[y] = ring[baseS + rsD * RSLOT + (9 + y) * 32];       // x=0100 L[01][y]
                 }
                 // short-delay values by shuffle
-                inF[5] = __shfl_up_sync(0xffffffffu, h3Q1011, 2 * S + 2);      // x=1011 D=3
-                inF[4] = __shfl_up_sync(0xffffffffu, h2Q1010, 2 * S + 2);      // x=1010 D=2
-                inF[3] = __shfl_up_sync(0xffffffffu, h2Q1001, 2 * S + 1);      // x=1001 D=2
+                inF[5] = __shfl_up_sync(0xffffffffu, h3Q1011, LPR);      // x=1011 D=3
+                inF[4] = __shfl_up_sync(0xffffffffu, h2Q1010, LPR);      // x=1010 D=2
+                inF[3] = __shfl_up_sync(0xffffffffu, h2Q1001, LPR - 1);  // x=1001 D=2
 #pragma unroll
                 for (int y = 0; y < 3; ++y) {
-                    inH1[3 + y] = __shfl_up_sync(0xffffffffu, hL10[y], 2 * S + 1);     // x=1000 D=1  L[10][y]
-                    inH2[3 * y + 2] = __shfl_sync(0xffffffffu, h2R11[y], lsrcW);       // x=0011 D=2  R[y][11]
-                    inH2[3 * y + 1] = __shfl_sync(0xffffffffu, hR[y][1], lsrcW);       // x=0010 D=1  R[y][10]
-                    inH2[3 * y + 0] = hR[y][0];                                        // x=0001 D=1  R[y][01] (self)
+                    inH1[3 + y] = __shfl_up_sync(0xffffffffu, hL10[y], LPR - 1);  // x=1000 D=1  L[10][y]
+                    inH2[3 * y + 2] = __shfl_sync(0xffffffffu, h2R11[y], lsrcW);  // x=0011 D=2  R[y][11]
+                    inH2[3 * y + 1] = __shfl_sync(0xffffffffu, hR[y][1], lsrcW);  // x=0010 D=1  R[y][10]
+                    inH2[3 * y + 0] = hR[y][0];                                   // x=0001 D=1  R[y][01] (self)
                 }
                 {   // row 0: the row above lives in another warp (or in the staged boundary) -> xs, not shuffles.
-                    // Loads are unconditional (rows > 0 read the same in-bounds words and drop them); the pad lane
-                    // of row 0 reads one element past its row, which is in bounds and never used (its cell is invalid).
+                    // Loads are unconditional (rows > 0 read the same in-bounds words and drop them); the last lane
+                    // of row 0 reads one element past its row: in bounds, and either invalid (PAD) or poisoned.
                     const int* x3 = xs + xs_in + ((q - 3) & 3) * NX * LPR + c;
                     const int* x2 = xs + xs_in + ((q - 2) & 3) * NX * LPR + c;
                     const int* x1 = xs + xs_in + ((q - 1) & 3) * NX * LPR + c;
                     const int a5 = x3[2 * LPR], a4 = x2[1 * LPR], a3 = x2[0 * LPR + 1];
                     const int b0 = x1[3 * LPR + 1], b1 = x1[4 * LPR + 1], b2 = x1[5 * LPR + 1];
-                    inF[5] = row0 ? a5 : inF[5];       // Q[10][11] of lane c   (x2 = 1)
-                    inF[4] = row0 ? a4 : inF[4];       // Q[10][10] of lane c
-                    inF[3] = row0 ? a3 : inF[3];       // Q[10][01] of lane c+1 (x2 = 0)
-                    inH1[3] = row0 ? b0 : inH1[3];     // L[10][*]  of lane c+1
+                    inF[5] = row0 ? a5 : inF[5];    // Q[10][11] of lane c   (x2 = 1)
+                    inF[4] = row0 ? a4 : inF[4];    // Q[10][10] of lane c
+                    inF[3] = row0 ? a3 : inF[3];    // Q[10][01] of lane c+1 (x2 = 0)
+                    inH1[3] = row0 ? b0 : inH1[3];  // L[10][*]  of lane c+1
                     inH1[4] = row0 ? b1 : inH1[4];
                     inH1[5] = row0 ? b2 : inH1[5];
                 }
                 // origin: M[1111][0,0,0,0] = 0 (pyx:485) enters as the F input of state 1111 (mu1 = mu2 = 0 there)
                 if (i == 0 && j == 0 && a == 0 && bb == S) inF[8] = 0;
 
-                // ---- the nine target states
-                const int kmm = mu1 + mu2, km1 = mu1 + kGD, km2 = mu2 + kGD;
-                int kF[9] = {k2G, k2G2D, km2, k2G2D, k2G, km2, km1, km1, kmm};
-                int kh2[3], kh1[3];  // per t23 / per t01 (without the tie-break adjustments)
-                kh2[0] = kGD; kh2[1] = kGD; kh2[2] = mu2 + k2D;
-                kh1[0] = kGD; kh1[1] = kGD; kh1[2] = mu1 + k2D;
+                // ---- additive constants per case (affine_score minus its gap-opening part), with the poisons
+                // of the pad-free flavour on exactly the cases whose source cell is outside the band:
+                //   pU1: x0=1,x2=0 (lane constant)   pW: x0=0,x2=1 (lane constant)
+                //   pB0: x1=0,x3=1 at b = -S          pB1: x1=1,x3=0 at b = +S
+                const int pB0 = (!PAD && bb == 0) ? NEGP : 0;
+                const int pB1 = (!PAD && bb == W - 1) ? NEGP : 0;
+                int kF[9];
+                kF[0] = k2G;                       // x=0101
+                kF[1] = k2G2D + pW + pB1;          // x=0110
+                kF[2] = mu2 + kGD + pW;            // x=0111
+                kF[3] = k2G2D + pU1 + pB0;         // x=1001
+                kF[4] = k2G;                       // x=1010
+                kF[5] = mu2 + kGD + pB0;           // x=1011
+                kF[6] = mu1 + kGD + pU1;           // x=1101
+                kF[7] = mu1 + kGD + pB1;           // x=1110
+                kF[8] = mu1 + mu2;                 // x=1111
+                int kh2[3], kh1[3];
+                kh2[0] = kGD + pB0;                // x=0001
+                kh2[1] = kGD + pW;                 // x=0010
+                kh2[2] = mu2 + k2D + pW + pB0;     // x=0011
+                kh1[0] = kGD + pB1;                // x=0100
+                kh1[1] = kGD + pU1;                // x=1000
+                kh1[2] = mu1 + k2D + pU1 + pB1;    // x=1100
                 int M[9];
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
@@ -308,7 +332,8 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                     // tie-break id-field adjustments (TRACE): H2 -> 9 - r23, H1 -> 6 - 3*r01 (see engine.cu)
                     const int c2 = kh2[t23] + (TRACE ? (-9 + 3 * t01) : 0);
                     const int c1 = kh1[t01] + (TRACE ? (-12 + t23) : 0);
-                    const int v = addmax(inH2[t], c2, inH1[t] + c1);
+                    const int v1 = addmax(inH1[t], c1, NEGP);  // floor: nothing ever drops below "minus infinity"
+                    const int v = addmax(inH2[t], c2, v1);
                     M[t] = addmax(inF[t], kF[t], v);
                     M[t] = valid ? M[t] : NEGP;
                 }
@@ -335,9 +360,7 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                     const unsigned lo = (M[0] & 31) | ((M[1] & 31) << 5) | ((M[2] & 31) << 10) | ((M[3] & 31) << 15) |
                                         ((M[4] & 31) << 20) | ((M[5] & 31) << 25);
                     const unsigned hi = (M[6] & 31) | ((M[7] & 31) << 5) | ((M[8] & 31) << 10);
-                    if (valid) {
-                        *reinterpret_cast<uint2*>(code_ptr + (long long)j * W + bb) = make_uint2(lo, hi);
-                    }
+                    if (valid) *reinterpret_cast<uint2*>(code_ptr + (long long)j * W + bb) = make_uint2(lo, hi);
                     const int4* tp = reinterpret_cast<const int4*>(tbtab + (bb * LPR + c) * 12);
                     const int4 ta = tp[0], tbv = tp[1], tc = tp[2];
                     const int msk = ~((1 << TB) - 1);
@@ -350,11 +373,11 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                 int Rv[3][3], Lv[3][3], Qv[3][3];
 #pragma unroll
                 for (int x = 0; x < 3; ++x) {
-                    open3(M[3 * x + 0], M[3 * x + 1], M[3 * x + 2], beta, Rv[x][0], Rv[x][1], Rv[x][2]);   // over s23, fixed s01 = x
-                    open3(M[0 + x], M[3 + x], M[6 + x], beta, Lv[0][x], Lv[1][x], Lv[2][x]);               // over s01, fixed s23 = x
+                    open3<BNEG>(M[3 * x + 0], M[3 * x + 1], M[3 * x + 2], beta, Rv[x][0], Rv[x][1], Rv[x][2]);  // over s23, s01 = x
+                    open3<BNEG>(M[0 + x], M[3 + x], M[6 + x], beta, Lv[0][x], Lv[1][x], Lv[2][x]);              // over s01, s23 = x
                 }
 #pragma unroll
-                for (int y = 0; y < 3; ++y) open3(Rv[0][y], Rv[1][y], Rv[2][y], beta, Qv[0][y], Qv[1][y], Qv[2][y]);
+                for (int y = 0; y < 3; ++y) open3<BNEG>(Rv[0][y], Rv[1][y], Rv[2][y], beta, Qv[0][y], Qv[1][y], Qv[2][y]);
 
                 // ring: long-delay values
                 int* wr = ring + own_ring + wslot * RSLOT + lane;
@@ -365,7 +388,7 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                     wr[(6 + y) * 32] = Lv[2][y];
                     wr[(9 + y) * 32] = Lv[0][y];
                 }
-                if (r == R - 1 && c < LPR) {  // short-delay values for the warp below / the next pass
+                if (r == R - 1) {  // short-delay values for the warp below / the next pass
                     int* xo = xs + xs_out + (q & 3) * NX * LPR + c;
 #pragma unroll
                     for (int y = 0; y < 3; ++y) {
@@ -409,11 +432,11 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                 __syncthreads();
             }  // iterations
             if (has_out) {  // last iteration's record, then make the stream visible to the next pass
-                for (int e = tid; e < (NV + NX) * LPR; e += blockDim.x) {
+                for (int e = tid; e < REC; e += blockDim.x) {
                     const int v = e / LPR, cs = e - v * LPR;
                     const int val = (v < NV) ? ring[(G * RING + wslot) * RSLOT + v * 32 + (R - 1) * LPR + cs]
                                              : xs[(G * 4 + ((nit - 1) & 3)) * NX * LPR + (v - NV) * LPR + cs];
-                    bnd_out[(size_t)(nit - 1) * (NV + NX) * LPR + e] = val;
+                    bnd_out[(size_t)(nit - 1) * REC + e] = val;
                 }
                 __threadfence();
             }
@@ -428,79 +451,48 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
     }
 }
 
-// Molecule B is staged with enough slack on both sides for every lane's position during the
-// pipeline fill (negative columns) and drain (columns beyond m).
-int sys_boff(int S, int G) {
-    const int P = 2 * S + 2, RT = G * (32 / P);
-    return (2 * RT + P + 8) / P + 3 + S;
-}
-int sys_bpad(int S, int G, int mmax) {
-    const int P = 2 * S + 2, RT = G * (32 / P);
-    return sys_boff(S, G) + mmax + (2 * RT + 2 * P + 8) / P + S + 6;
-}
-
-template <int S>
-size_t sys_smem_bytes_t(int G, int nsym, int mmax) {
-    using G_ = Geo<S>;
-    size_t ints = (size_t)(G + 1) * G_::RING * G_::NV * 32 + (size_t)(G + 1) * 4 * G_::NX * G_::LPR +
-                  (size_t)G_::PB * (G_::NV + G_::NX) * G_::LPR + (size_t)G_::P * G_::LPR * 12 + (size_t)(nsym + 1) * nsym;
-    size_t bytes = ints * 4 + 2 * (size_t)sys_bpad(S, G, mmax);
+// ---- host-side geometry helpers (mirrored by engine.cu through kernels.cuh)
+template <int S, bool PAD>
+size_t smem_bytes_t(int G, int nsym, int bpad) {
+    using G_ = Geo<S, PAD>;
+    size_t ints = (size_t)(G + 1) * G_::RING * G_::RSLOT + (size_t)(G + 1) * 4 * G_::NX * G_::LPR + (size_t)G_::PB * G_::REC +
+                  (size_t)G_::P * G_::LPR * 12 + (size_t)(nsym + 1) * nsym;
+    size_t bytes = ints * 4 + 2 * (size_t)bpad;
     return (bytes + 15) & ~(size_t)15;
 }
 
-size_t sys_smem_bytes(int S, int G, int nsym, int mmax) {
-    switch (S) {
-        case 0: return sys_smem_bytes_t<0>(G, nsym, mmax);
-        case 1: return sys_smem_bytes_t<1>(G, nsym, mmax);
-        case 2: return sys_smem_bytes_t<2>(G, nsym, mmax);
-        case 3: return sys_smem_bytes_t<3>(G, nsym, mmax);
-        default: return sys_smem_bytes_t<4>(G, nsym, mmax);
-    }
-}
-
-int sys_rows_per_warp(int S) { return 32 / (2 * S + 2); }
-int sys_iters(int S, int G, int m) {
-    const int P = 2 * S + 2;
-    return (m + 1) * P + 2 * (G * (32 / P) - 1) + P + (P + 3);
-}
-size_t sys_boundary_ints(int S, int G, int mmax) { return (size_t)sys_iters(S, G, mmax) * 18 * (2 * S + 2); }
-
-template <int S, bool TRACE>
-static cudaError_t launch_t(const SysArgs& A, int grid, int G, size_t smem, cudaStream_t st) {
-    auto kern = fill_systolic_kernel<S, TRACE>;
+template <int S, bool TRACE, bool PAD, bool BNEG>
+cudaError_t launch_t(const SysArgs& A, int grid, int G, size_t smem, cudaStream_t st) {
+    auto kern = fill_systolic_kernel<S, TRACE, PAD, BNEG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, G * 32, smem, st>>>(A);
     return cudaGetLastError();
 }
 
-cudaError_t launch_fill_systolic(const SysArgs& A, int grid, int G, size_t smem, bool trace, cudaStream_t st) {
-    switch (A.sc.s) {
-        case 0: return trace ? launch_t<0, true>(A, grid, G, smem, st) : launch_t<0, false>(A, grid, G, smem, st);
-        case 1: return trace ? launch_t<1, true>(A, grid, G, smem, st) : launch_t<1, false>(A, grid, G, smem, st);
-        case 2: return trace ? launch_t<2, true>(A, grid, G, smem, st) : launch_t<2, false>(A, grid, G, smem, st);
-        case 3: return trace ? launch_t<3, true>(A, grid, G, smem, st) : launch_t<3, false>(A, grid, G, smem, st);
-        case 4: return trace ? launch_t<4, true>(A, grid, G, smem, st) : launch_t<4, false>(A, grid, G, smem, st);
-    }
-    return cudaErrorInvalidValue;
-}
-
-template <int S, bool TRACE>
-static int occ_t(int G, size_t smem) {
-    auto kern = fill_systolic_kernel<S, TRACE>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int S, bool TRACE, bool PAD, bool BNEG>
+int occ_t(int G, size_t smem) {
+    auto kern = fill_systolic_kernel<S, TRACE, PAD, BNEG>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, G * 32, smem);
     return nb;
 }
-int sys_occupancy(int S, bool trace, int G, size_t smem) {
-    switch (S) {
-        case 0: return trace ? occ_t<0, true>(G, smem) : occ_t<0, false>(G, smem);
-        case 1: return trace ? occ_t<1, true>(G, smem) : occ_t<1, false>(G, smem);
-        case 2: return trace ? occ_t<2, true>(G, smem) : occ_t<2, false>(G, smem);
-        case 3: return trace ? occ_t<3, true>(G, smem) : occ_t<3, false>(G, smem);
-        default: return trace ? occ_t<4, true>(G, smem) : occ_t<4, false>(G, smem);
-    }
+
+// One translation unit per max_shift instantiates the flavours the engine uses:
+// (PAD=false,BNEG=true) fast, (PAD=true,BNEG=true) wide-range, (PAD=true,BNEG=false) positive gap opening.
+template <int S>
+cudaError_t launch_s(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, bool bneg, cudaStream_t st) {
+    if (!pad) return trace ? launch_t<S, true, false, true>(A, grid, G, smem, st) : launch_t<S, false, false, true>(A, grid, G, smem, st);
+    if (bneg) return trace ? launch_t<S, true, true, true>(A, grid, G, smem, st) : launch_t<S, false, true, true>(A, grid, G, smem, st);
+    return trace ? launch_t<S, true, true, false>(A, grid, G, smem, st) : launch_t<S, false, true, false>(A, grid, G, smem, st);
+}
+template <int S>
+int occ_s(bool trace, bool pad, bool bneg, int G, size_t smem) {
+    if (!pad) return trace ? occ_t<S, true, false, true>(G, smem) : occ_t<S, false, false, true>(G, smem);
+    if (bneg) return trace ? occ_t<S, true, true, true>(G, smem) : occ_t<S, false, true, true>(G, smem);
+    return trace ? occ_t<S, true, true, false>(G, smem) : occ_t<S, false, true, false>(G, smem);
 }
 
+}  // namespace sys
 }  // namespace ba

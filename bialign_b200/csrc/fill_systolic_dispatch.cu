@@ -1,0 +1,74 @@
+// Run-time dispatch over max_shift for the systolic fill, plus its host-side geometry
+// (must mirror sys::Geo in fill_systolic.cuh).
+#include "kernels.cuh"
+
+namespace ba {
+
+#define DECL(s)                                                                                                         \
+    cudaError_t launch_fill_systolic_s##s(const SysArgs&, int, int, size_t, bool, bool, bool, cudaStream_t);            \
+    int sys_occupancy_s##s(bool, bool, bool, int, size_t);                                                              \
+    size_t sys_smem_bytes_s##s(bool, int, int, int);
+DECL(0) DECL(1) DECL(2) DECL(3) DECL(4)
+#undef DECL
+
+SysGeo sys_geo(int S, bool pad) {
+    SysGeo g;
+    g.W = 2 * S + 1;
+    g.LPR = pad ? 2 * S + 2 : 2 * S + 1;
+    g.P = pad ? 2 * S + 2 : (S == 0 ? 2 : 2 * S + 1);
+    g.R = 32 / g.LPR;
+    g.RING = g.P + 3;
+    g.REC = 18 * g.LPR;
+    return g;
+}
+
+int sys_iters(int S, bool pad, int G, int m) {
+    const SysGeo g = sys_geo(S, pad);
+    return (m + 1) * g.P + 2 * (G * g.R - 1) + g.LPR + g.RING;
+}
+size_t sys_boundary_ints(int S, bool pad, int G, int mmax) { return (size_t)sys_iters(S, pad, G, mmax) * sys_geo(S, pad).REC; }
+
+// Molecule B is staged with slack on both sides for every lane's position during the pipeline
+// fill (negative columns) and drain (columns beyond m).
+int sys_boff(int S, bool pad, int G) {
+    const SysGeo g = sys_geo(S, pad);
+    return (2 * G * g.R + 4 * g.P + 16) / g.P + 3 + S;
+}
+int sys_bpad(int S, bool pad, int G, int mmax) {
+    const SysGeo g = sys_geo(S, pad);
+    return sys_boff(S, pad, G) + mmax + (2 * G * g.R + 4 * g.P + 16) / g.P + S + 8;
+}
+
+size_t sys_smem_bytes(int S, bool pad, int G, int nsym, int mmax) {
+    const int bpad = sys_bpad(S, pad, G, mmax);
+    switch (S) {
+        case 0: return sys_smem_bytes_s0(pad, G, nsym, bpad);
+        case 1: return sys_smem_bytes_s1(pad, G, nsym, bpad);
+        case 2: return sys_smem_bytes_s2(pad, G, nsym, bpad);
+        case 3: return sys_smem_bytes_s3(pad, G, nsym, bpad);
+        default: return sys_smem_bytes_s4(pad, G, nsym, bpad);
+    }
+}
+
+int sys_occupancy(int S, bool trace, bool pad, bool bneg, int G, size_t smem) {
+    switch (S) {
+        case 0: return sys_occupancy_s0(trace, pad, bneg, G, smem);
+        case 1: return sys_occupancy_s1(trace, pad, bneg, G, smem);
+        case 2: return sys_occupancy_s2(trace, pad, bneg, G, smem);
+        case 3: return sys_occupancy_s3(trace, pad, bneg, G, smem);
+        default: return sys_occupancy_s4(trace, pad, bneg, G, smem);
+    }
+}
+
+cudaError_t launch_fill_systolic(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, bool bneg, cudaStream_t st) {
+    switch (A.sc.s) {
+        case 0: return launch_fill_systolic_s0(A, grid, G, smem, trace, pad, bneg, st);
+        case 1: return launch_fill_systolic_s1(A, grid, G, smem, trace, pad, bneg, st);
+        case 2: return launch_fill_systolic_s2(A, grid, G, smem, trace, pad, bneg, st);
+        case 3: return launch_fill_systolic_s3(A, grid, G, smem, trace, pad, bneg, st);
+        case 4: return launch_fill_systolic_s4(A, grid, G, smem, trace, pad, bneg, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace ba

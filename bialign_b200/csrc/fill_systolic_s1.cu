@@ -1,0 +1,11 @@
+// Instantiations of the systolic fill for max_shift = 1 (see fill_systolic.cuh).
+#include "fill_systolic.cuh"
+namespace ba {
+cudaError_t launch_fill_systolic_s1(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, bool bneg, cudaStream_t st) {
+    return sys::launch_s<1>(A, grid, G, smem, trace, pad, bneg, st);
+}
+int sys_occupancy_s1(bool trace, bool pad, bool bneg, int G, size_t smem) { return sys::occ_s<1>(trace, pad, bneg, G, smem); }
+size_t sys_smem_bytes_s1(bool pad, int G, int nsym, int bpad) {
+    return pad ? sys::smem_bytes_t<1, true>(G, nsym, bpad) : sys::smem_bytes_t<1, false>(G, nsym, bpad);
+}
+}  // namespace ba

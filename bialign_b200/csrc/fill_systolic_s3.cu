@@ -1,0 +1,11 @@
+// Instantiations of the systolic fill for max_shift = 3 (see fill_systolic.cuh).
+#include "fill_systolic.cuh"
+namespace ba {
+cudaError_t launch_fill_systolic_s3(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, bool bneg, cudaStream_t st) {
+    return sys::launch_s<3>(A, grid, G, smem, trace, pad, bneg, st);
+}
+int sys_occupancy_s3(bool trace, bool pad, bool bneg, int G, size_t smem) { return sys::occ_s<3>(trace, pad, bneg, G, smem); }
+size_t sys_smem_bytes_s3(bool pad, int G, int nsym, int bpad) {
+    return pad ? sys::smem_bytes_t<3, true>(G, nsym, bpad) : sys::smem_bytes_t<3, false>(G, nsym, bpad);
+}
+}  // namespace ba

@@ -62,12 +62,14 @@ void launch_fill_generic(const FillArgs& A, int grid, bool trace, cudaStream_t s
 size_t generic_scratch_ints(int nmax, int s);
 void launch_traceback(const TraceArgs& A, cudaStream_t st);
 
-size_t sys_smem_bytes(int S, int G, int nsym, int mmax);
-int sys_iters(int S, int G, int m);
-size_t sys_boundary_ints(int S, int G, int mmax);
-int sys_occupancy(int S, bool trace, int G, size_t smem);
-int sys_boff(int S, int G);
-int sys_bpad(int S, int G, int mmax);
-cudaError_t launch_fill_systolic(const SysArgs& A, int grid, int G, size_t smem, bool trace, cudaStream_t st);
+struct SysGeo { int W, LPR, P, R, RING, REC; };
+SysGeo sys_geo(int S, bool pad);
+size_t sys_smem_bytes(int S, bool pad, int G, int nsym, int mmax);
+int sys_iters(int S, bool pad, int G, int m);
+size_t sys_boundary_ints(int S, bool pad, int G, int mmax);
+int sys_occupancy(int S, bool trace, bool pad, bool bneg, int G, size_t smem);
+int sys_boff(int S, bool pad, int G);
+int sys_bpad(int S, bool pad, int G, int mmax);
+cudaError_t launch_fill_systolic(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, bool bneg, cudaStream_t st);
 
 }  // namespace ba

@@ -136,7 +136,19 @@ def _check_batch(al, seqs, structs, pairs, params, table_pairs=0):
     assert (s2 == scores).all()
 
 
-@pytest.mark.parametrize("kernel", [0, 1])
+def _select(engine, kind):
+    """kind 0 = generic level kernel, 1 = systolic pad-free, 2 = systolic padded."""
+    engine.set_option("kernel", 0 if kind == 0 else 1)
+    engine.set_option("pad", -1 if kind == 0 else kind - 1)
+
+
+def _unselect(engine):
+    engine.set_option("kernel", -1)
+    engine.set_option("pad", -1)
+    engine.set_option("warps_per_cta", 4)
+
+
+@pytest.mark.parametrize("kernel", [0, 1, 2])
 @pytest.mark.parametrize("s", [0, 1, 2, 3, 4])
 def test_random_batch_vs_oracle(s, kernel):
     """Ragged random protein batch vs the CPU oracle: scores, traces, end values and code tables."""
@@ -145,16 +157,17 @@ def test_random_batch_vs_oracle(s, kernel):
                   shift_cost=-150, max_shift=s)
     seqs, structs, pairs = _random_protein_batch(rng, 24, 1, 70)
     al = _aligner(params)
-    al.engine.set_option("kernel", kernel)
+    _select(al.engine, kernel)
     try:
         _check_batch(al, seqs, structs, pairs, params, table_pairs=24)
         assert al.engine.stats()["kernel_kind"] == kernel
     finally:
-        al.engine.set_option("kernel", -1)
+        _unselect(al.engine)
 
 
+@pytest.mark.parametrize("pad", [0, 1])
 @pytest.mark.parametrize("warps", [1, 2, 4, 8])
-def test_systolic_multipass_and_cta_shapes(warps):
+def test_systolic_multipass_and_cta_shapes(warps, pad):
     """Pairs longer than one row block (several passes through the boundary stream), all CTA widths."""
     rng = np.random.default_rng(500 + warps)
     for s, tie in ((2, {}), (1, {"shift_cost": 0}), (3, {"structure_weight": 0, "gap_cost": 0})):
@@ -163,14 +176,27 @@ def test_systolic_multipass_and_cta_shapes(warps):
         params.update(tie)
         seqs, structs, pairs = _random_protein_batch(rng, 6, 60, 150)
         al = _aligner(params)
-        al.engine.set_option("kernel", 1)
+        _select(al.engine, 1 + pad)
         al.engine.set_option("warps_per_cta", warps)
         try:
             _check_batch(al, seqs, structs, pairs, params, table_pairs=2)
-            assert al.engine.stats()["kernel_kind"] == 1
+            assert al.engine.stats()["kernel_kind"] == 1 + pad
         finally:
-            al.engine.set_option("kernel", -1)
-            al.engine.set_option("warps_per_cta", 4)
+            _unselect(al.engine)
+
+
+def test_positive_gap_opening_and_tie_storms():
+    """beta > 0 (general open() reduction, padded flavour) and all-zero costs (every case ties)."""
+    rng = np.random.default_rng(77)
+    for var in ({"gap_opening_cost": 70}, {"shift_cost": 0, "gap_cost": 0, "structure_weight": 0, "gap_opening_cost": -1},
+                {"shift_cost": 40, "gap_cost": -300}):
+        params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150,
+                      gap_cost=-50, shift_cost=-150, max_shift=2)
+        params.update(var)
+        seqs, structs, pairs = _random_protein_batch(rng, 8, 1, 60)
+        al = _aligner(params)
+        _check_batch(al, seqs, structs, pairs, params, table_pairs=8)
+        assert al.engine.stats()["kernel_kind"] in (1, 2)
 
 
 def test_rna_batch_score_only_vs_oracle():
