@@ -499,7 +499,7 @@ int ba_run(ba_engine* e, int want_trace) {
         SA.k_2g2d = (int)((2 * e->sc.gamma + 2 * e->sc.delta) / plan.g * sh); SA.k_2d = (int)(2 * e->sc.delta / plan.g * sh);
         SA.negp = plan.negp; SA.tb_bits = plan.tb; SA.gscale = plan.g; SA.mmax = mmax;
         SA.boff = sys_boff(s, plan.pad, sysG); SA.bpad = sys_bpad(s, plan.pad, sysG, mmax);
-        SA.bnd = e->d_bnd.p; SA.bnd_iters = biters;
+        SA.bnd = e->d_bnd.p; SA.bnd_iters = biters + 8;  // matches sys_boundary_ints: slack records in front
         SA.codes = want_trace ? e->d_codes.p : nullptr;
         SA.scores = e->d_scores.p; SA.start_state = e->d_start.p; SA.end_values = e->d_endv.p;
     } else {

@@ -49,6 +49,16 @@ __device__ __forceinline__ int vmax(int a, int b) { return max(a, b); }
 __device__ __forceinline__ int vmax3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 __device__ __forceinline__ int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); }  // max(a+b, c)
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int lds32(unsigned addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32(unsigned addr, int v) { asm volatile("st.shared.s32 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void cp_async4s(unsigned smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
     // 4-byte copies go through L1 (.ca); the boundary stream is written by this same SM (write-through
     // stores keep its L1 coherent), so no stale line can be observed in CTA-per-pair mode
@@ -105,6 +115,7 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
     using G_ = Geo<S, PAD>;
     constexpr int W = G_::W, P = G_::P, LPR = G_::LPR, R = G_::R, RING = G_::RING, NV = G_::NV, NX = G_::NX, PB = G_::PB;
     constexpr int RSLOT = G_::RSLOT, REC = G_::REC;
+    constexpr bool RP2 = (RING & (RING - 1)) == 0;  // power-of-two ring: slots are masks of the iteration counter
     extern __shared__ __align__(16) int smem[];
     const int G = blockDim.x >> 5;
     const int RT = G * R;  // rows per pass
@@ -196,6 +207,18 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
             const int fl_src = io_col + (io_ring ? G * RING * RSLOT : G * 4 * NX * LPR);  // CTA output row
             const int st_dst = io_col;                                                    // ring[0] / xs[0]
             const bool io_fast = REC <= (int)blockDim.x;
+            // Boundary streams hold record `rec` at offset (rec + PRE + 1) * REC, so the unconditional flush of
+            // "iteration q-1" in the very first iteration lands in a slack record.  Running pointers, shared-memory
+            // addresses in bytes: the fast path is ~7 instructions per direction and iteration.
+            const bool do_flush = has_out && io_fast && io_thread, do_stage = has_in && io_fast && io_thread;
+            int* fl_g = bnd_out + tid;                                                   // record q-1 of iteration q = -PRE
+            const int* st_g = bnd_in + (size_t)(2 * RT + LA + 1) * REC + tid;            // record (q + LA + 2RT) of q = -PRE
+            const unsigned fl_s = smem_u32(smem + fl_src), st_s = smem_u32(smem + st_dst), pb_s = smem_u32(pb + tid);
+            const int io_stride_b = io_stride * 4;
+            const int q_rec_lim = nit - 2 * RT;                                          // records beyond are "minus infinity"
+            // iteration at which this lane sits on the origin / on the end cell (INT_MIN: never)
+            const int q_origin = (i == 0 && a == 0) ? S + sigma : (int)0x80000000;
+            const int q_end = (lane_ok && i == n && a == 0) ? m * P + S + sigma : (int)0x80000000;
             uint64_t* code_ptr = nullptr;
             if (TRACE && lane_ok) code_ptr = A.codes + d.code_off + ((long long)i * W + c) * (long long)(m + 1) * W;
 
@@ -203,7 +226,7 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
             int pos = -PRE - 1 - sigma;
             int j = -((-pos + P - 1) / P);
             int bb = pos - j * P;
-            int wslot = (((-PRE - 1) % RING) + RING) % RING;
+            int wslot = (((-PRE - 1) % RING) + RING) % RING;  // == (q & (RING-1)) below when RING is a power of two
             int mu1 = 0;
 
             // history registers (outputs of the last 1..3 iterations), all "minus infinity"
@@ -220,7 +243,7 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                 for (int t0 = -PRE; t0 < LA - PRE; ++t0) {
                     for (int e = tid; e < REC; e += blockDim.x) {
                         const int rec = t0 + 2 * RT;
-                        if (rec >= 0 && rec < nit) cp_async4(pb + (t0 & (PB - 1)) * REC + e, bnd_in + (size_t)rec * REC + e);
+                        if (rec >= 0 && rec < nit) cp_async4(pb + (t0 & (PB - 1)) * REC + e, bnd_in + (size_t)(rec + PRE + 1) * REC + e);
                     }
                     cp_async_commit();
                 }
@@ -231,7 +254,7 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                 // ---- advance position
                 ++bb;
                 if (bb == P) { bb = 0; ++j; }
-                wslot = (wslot + 1 == RING) ? 0 : wslot + 1;
+                wslot = RP2 ? (q & (RING - 1)) : ((wslot + 1 == RING) ? 0 : wslot + 1);
                 const int l = j + bb - S;
                 const bool valid = lane_ok && (bb < W) && ((unsigned)j <= (unsigned)m) && ((unsigned)l <= (unsigned)m);
 
@@ -241,25 +264,31 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                 const int mu2 = (cB == Ak) ? A.w_p : 0;
 
                 // ---- flush the CTA's last row of iteration q-1 to the outgoing boundary stream
-                if (has_out && q > 0) {
-                    const int ps = (wslot == 0) ? RING - 1 : wslot - 1;
-                    if (io_fast) {
-                        if (io_thread) bnd_out[(size_t)(q - 1) * REC + tid] = smem[fl_src + (io_ring ? ps : ((q - 1) & 3)) * io_stride];
-                    } else {
+                {
+                    const int ps = RP2 ? ((q - 1) & (RING - 1)) : ((wslot == 0) ? RING - 1 : wslot - 1);
+                    if (do_flush) *fl_g = lds32(fl_s + (io_ring ? ps : ((q - 1) & 3)) * io_stride_b);
+                    fl_g += REC;
+                    if (has_out && !io_fast && q > -PRE) {
                         for (int e = tid; e < REC; e += blockDim.x) {
                             const int v = e / LPR, cs = e - v * LPR;
                             const int val = (v < NV) ? ring[(G * RING + ps) * RSLOT + v * 32 + (R - 1) * LPR + cs]
                                                      : xs[(G * 4 + ((q - 1) & 3)) * NX * LPR + (v - NV) * LPR + cs];
-                            bnd_out[(size_t)(q - 1) * REC + e] = val;
+                            bnd_out[(size_t)(q + PRE) * REC + e] = val;
                         }
                     }
                 }
 
                 // ---- gather the 27 inputs
-                int rsA = wslot - (P + 2); if (rsA < 0) rsA += RING;  // D = P+2
-                int rsB = wslot - (P + 1); if (rsB < 0) rsB += RING;  // D = P+1
-                int rsC = wslot - P;       if (rsC < 0) rsC += RING;  // D = P
-                int rsD = wslot - (P - 1); if (rsD < 0) rsD += RING;  // D = P-1
+                int rsA, rsB, rsC, rsD;  // ring slots written P+2, P+1, P, P-1 iterations ago
+                if (RP2) {
+                    rsA = (q - (P + 2)) & (RING - 1); rsB = (q - (P + 1)) & (RING - 1);
+                    rsC = (q - P) & (RING - 1);       rsD = (q - (P - 1)) & (RING - 1);
+                } else {
+                    rsA = wslot - (P + 2); if (rsA < 0) rsA += RING;
+                    rsB = wslot - (P + 1); if (rsB < 0) rsB += RING;
+                    rsC = wslot - P;       if (rsC < 0) rsC += RING;
+                    rsD = wslot - (P - 1); if (rsD < 0) rsD += RING;
+                }
                 int inF[9], inH2[9], inH1[9];
                 // long-delay values from the rings (ids: 0..2 Q[11][01,10,11], 3..5 Q[01][..], 6..8 L[11][..], 9..11 L[01][..])
                 inF[8] = ring[baseU0 + rsA * RSLOT + 2 * 32];  // x=1111 Q[11][11]
@@ -300,7 +329,7 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                     inH1[5] = row0 ? b2 : inH1[5];
                 }
                 // origin: M[1111][0,0,0,0] = 0 (pyx:485) enters as the F input of state 1111 (mu1 = mu2 = 0 there)
-                if (i == 0 && j == 0 && a == 0 && bb == S) inF[8] = 0;
+                if (q == q_origin) inF[8] = 0;
 
                 // ---- additive constants per case (affine_score minus its gap-opening part), with the poisons
                 // of the pad-free flavour on exactly the cases whose source cell is outside the band:
@@ -339,7 +368,7 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                 }
 
                 // ---- results at the end cell
-                if (valid && i == n && j == m && a == 0 && bb == S) {
+                if (q == q_end) {
                     int best = M[0] >> TB;
 #pragma unroll
                     for (int t = 1; t < 9; ++t) best = max(best, M[t] >> TB);
@@ -411,20 +440,21 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                 // ---- stage the incoming boundary: virtual row above warp 0, iteration q
                 if (has_in) {
                     cp_async_wait<LA - 1>();
-                    const int rec = q + 2 * RT, nrec = rec + LA;
-                    if (io_fast) {
-                        if (io_thread) {
-                            const int val = (rec >= 0 && rec < nit) ? pb[(q & (PB - 1)) * REC + tid] : NEGP;
-                            smem[st_dst + (io_ring ? wslot : (q & 3)) * io_stride] = val;
-                            if (nrec < nit) cp_async4(pb + ((q + LA) & (PB - 1)) * REC + tid, bnd_in + (size_t)nrec * REC + tid);
-                        }
-                    } else {
+                    if (do_stage) {
+                        int val = lds32(pb_s + (q & (PB - 1)) * (REC * 4));
+                        val = (q < q_rec_lim) ? val : NEGP;
+                        sts32(st_s + (io_ring ? wslot : (q & 3)) * io_stride_b, val);
+                        if (q + LA < q_rec_lim) cp_async4s(pb_s + ((q + LA) & (PB - 1)) * (REC * 4), st_g);
+                    }
+                    st_g += REC;
+                    if (!io_fast) {
+                        const int rec = q + 2 * RT, nrec = rec + LA;
                         for (int e = tid; e < REC; e += blockDim.x) {
                             const int v = e / LPR, cs = e - v * LPR;
                             const int val = (rec >= 0 && rec < nit) ? pb[(q & (PB - 1)) * REC + e] : NEGP;
                             if (v < NV) ring[(0 * RING + wslot) * RSLOT + v * 32 + (R - 1) * LPR + cs] = val;
                             else xs[(0 * 4 + (q & 3)) * NX * LPR + (v - NV) * LPR + cs] = val;
-                            if (nrec < nit) cp_async4(pb + ((q + LA) & (PB - 1)) * REC + e, bnd_in + (size_t)nrec * REC + e);
+                            if (nrec < nit) cp_async4(pb + ((q + LA) & (PB - 1)) * REC + e, bnd_in + (size_t)(nrec + PRE + 1) * REC + e);
                         }
                     }
                     cp_async_commit();
@@ -436,7 +466,7 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                     const int v = e / LPR, cs = e - v * LPR;
                     const int val = (v < NV) ? ring[(G * RING + wslot) * RSLOT + v * 32 + (R - 1) * LPR + cs]
                                              : xs[(G * 4 + ((nit - 1) & 3)) * NX * LPR + (v - NV) * LPR + cs];
-                    bnd_out[(size_t)(nit - 1) * REC + e] = val;
+                    bnd_out[(size_t)(nit + PRE) * REC + e] = val;
                 }
                 __threadfence();
             }

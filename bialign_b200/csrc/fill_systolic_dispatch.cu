@@ -26,7 +26,8 @@ int sys_iters(int S, bool pad, int G, int m) {
     const SysGeo g = sys_geo(S, pad);
     return (m + 1) * g.P + 2 * (G * g.R - 1) + g.LPR + g.RING;
 }
-size_t sys_boundary_ints(int S, bool pad, int G, int mmax) { return (size_t)sys_iters(S, pad, G, mmax) * sys_geo(S, pad).REC; }
+// records -(PRE+1) .. nit-1 (PRE = 4 warm-up iterations of the kernel, one slack record in front)
+size_t sys_boundary_ints(int S, bool pad, int G, int mmax) { return (size_t)(sys_iters(S, pad, G, mmax) + 8) * sys_geo(S, pad).REC; }
 
 // Molecule B is staged with slack on both sides for every lane's position during the pipeline
 // fill (negative columns) and drain (columns beyond m).
