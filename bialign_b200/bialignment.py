@@ -186,7 +186,7 @@ class BiAligner:
     def traceback(self):
         if self._trace is None:
             raise TypeError("'NoneType' object is not subscriptable")  # reference: traceback() before optimize()
-        if self.molA["len"] == 0 and self.molB["len"] == 0 and self._affine:
+        if self.molA["len"] == 0 and self.molB["len"] == 0:
             raise IndexError("string index out of range")  # pyx:555 -> pyx:260 -> pyx:407 on empty strings
         cols = [[(c >> 3) & 1, (c >> 2) & 1, (c >> 1) & 1, c & 1] for c in self._trace.tolist()]
         if self._affine:

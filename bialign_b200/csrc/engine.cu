@@ -347,7 +347,7 @@ int ba_run(ba_engine* e, int want_trace) {
     if (!e) return BA_ERR_INVALID_ARG;
     if (!e->have_scoring) return fail(e, BA_ERR_STATE, "ba_set_scoring first");
     if (!e->have_pairs) return fail(e, BA_ERR_STATE, "ba_load_sequences and ba_load_pairs first");
-    if (e->sc.beta == 0) return fail(e, BA_ERR_INVALID_ARG, "non-affine model (gap_opening_cost == 0) is not available in this build");
+    const bool affine = e->sc.beta != 0;  // pyx:203-205
     CU(cudaSetDevice(e->device));
     const int64_t N = e->n_pairs;
     const int s = e->sc.s;
@@ -370,7 +370,7 @@ int ba_run(ba_engine* e, int want_trace) {
         lm[p] = (int32_t)(e->h_off[e->h_pb[p] + 1] - e->h_off[e->h_pb[p]]);
         nmax = std::max(nmax, ln[p]);
         mmax = std::max(mmax, lm[p]);
-        cs += 9 * band_cells(ln[p], lm[p], s);
+        cs += (affine ? 9 : 1) * band_cells(ln[p], lm[p], s);
     }
     e->stats.cell_states = cs;
     {   // int32 exactness bound of SURVEY 8a-6
@@ -464,8 +464,8 @@ int ba_run(ba_engine* e, int want_trace) {
     for (int w = 0; w < n_waves; ++w) biggest_wave = std::max(biggest_wave, wave_begin[w + 1] - wave_begin[w]);
     // ---- kernel choice: systolic when its exactness conditions hold, else the generic level kernel
     SysPlan plan;
-    if (e->opt_kernel != 0) plan = plan_systolic(e, nmax, mmax, want_trace != 0);
-    if (e->opt_kernel == 1 && !plan.ok)
+    if (e->opt_kernel != 0 && affine) plan = plan_systolic(e, nmax, mmax, want_trace != 0);
+    if (e->opt_kernel == 1 && affine && !plan.ok)
         return fail(e, BA_ERR_SCORE_RANGE, "systolic kernel requested but its packed-integer range conditions do not hold");
     const int kernel = plan.ok ? 1 : 0;
     int max_grid = e->sm_count * 2;
@@ -503,7 +503,7 @@ int ba_run(ba_engine* e, int want_trace) {
         SA.codes = want_trace ? e->d_codes.p : nullptr;
         SA.scores = e->d_scores.p; SA.start_state = e->d_start.p; SA.end_values = e->d_endv.p;
     } else {
-        scratch_stride = generic_scratch_ints(nmax, s);
+        scratch_stride = generic_scratch_ints(nmax, s);  // sized for nine states; the non-affine kernel uses a ninth
         const int grid = (int)std::min<int64_t>(biggest_wave, max_grid);
         cudaError_t ce = e->d_scratch.ensure(scratch_stride * grid);
         if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "fill scratch: " + std::string(cudaGetErrorString(ce)));
@@ -526,15 +526,17 @@ int ba_run(ba_engine* e, int want_trace) {
         if (kernel == 1) {
             SA.pairs = e->d_desc.p + b; SA.npairs = (int)cnt; SA.counter = e->d_counter.p + w;
             CU(launch_fill_systolic(SA, grid, sysG, sys_smem, want_trace != 0, plan.pad, plan.bneg, e->stream));
-        } else {
+        } else if (affine) {
             launch_fill_generic(A, grid, want_trace != 0, e->stream);
+        } else {
+            launch_fill_nonaffine(A, grid, want_trace != 0, e->stream);
         }
         e->stats.kernel_launches++;
         CU(cudaGetLastError());
         CU(cudaEventRecord(ev[1 + 3 * w], e->stream));
         if (want_trace) {
             TraceArgs T{};
-            T.pairs = e->d_desc.p + b; T.npairs = (int)cnt; T.s = s; T.codes = e->d_codes.p; T.fmt = kernel;
+            T.pairs = e->d_desc.p + b; T.npairs = (int)cnt; T.s = s; T.codes = e->d_codes.p; T.fmt = affine ? kernel : 2;
             T.start_state = e->d_start.p; T.trace = e->d_trace.p; T.trace_len = e->d_tlen.p; T.complete = e->d_complete.p;
             launch_traceback(T, e->stream);
             e->stats.kernel_launches++;

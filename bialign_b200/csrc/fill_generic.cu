@@ -118,6 +118,89 @@ __global__ void __launch_bounds__(256) fill_level_kernel(FillArgs A) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Non-affine model (gap_opening_cost == 0): one value per cell, the 13 cases of pyx:233-248 in that
+// order, first case reproducing the maximum wins (pyx:522-528).  Same level wavefront; code word =
+// case index 0..12 in the low nibble (15 = none).
+// ---------------------------------------------------------------------------------------------
+__constant__ int NA_XBITS[13] = {15, 10, 5, 12, 3, 8, 4, 2, 1, 11, 7, 14, 13};
+
+template <bool TRACE>
+__global__ void __launch_bounds__(256) fill_level_nonaffine_kernel(FillArgs A) {
+    __shared__ int s_pair;
+    const int s = A.sc.s, W = 2 * s + 1;
+    const int gamma = A.sc.gamma, Delta = A.sc.delta;
+    for (;;) {
+        if (threadIdx.x == 0) s_pair = atomicAdd(A.counter, 1);
+        __syncthreads();
+        const int pi = s_pair;
+        __syncthreads();
+        if (pi >= A.npairs) return;
+        const PairDesc d = A.pairs[pi];
+        const uint8_t* ra = A.res + d.offA;
+        const uint8_t* rb = A.res + d.offB;
+        const uint8_t* ca = A.cls + d.offA;
+        const uint8_t* cb = A.cls + d.offB;
+        const int n = d.n, m = d.m;
+        const int items = (n + 1) * W * W;
+        int* lv = A.scratch + (size_t)blockIdx.x * A.scratch_stride;
+        uint64_t* codes = TRACE ? A.codes + d.code_off : nullptr;
+        for (int tau = 0; tau <= 2 * (n + m); ++tau) {
+            int* cur = lv + (size_t)(tau % 5) * items;
+            for (int it = threadIdx.x; it < items; it += blockDim.x) {
+                const int bb = it % W, aa = (it / W) % W, i = it / (W * W);
+                const int a = aa - s, b = bb - s;
+                const int twoj = tau - 2 * i - a - b;
+                if (twoj < 0 || (twoj & 1)) continue;
+                const int j = twoj >> 1;
+                const int k = i + a, l = j + b;
+                if (j > m || k < 0 || k > n || l < 0 || l > m) continue;
+                if (tau == 0) {  // np.zeros, pyx:27 / pyx:464-465
+                    cur[it] = 0;
+                    if (TRACE) codes[code_index(m, s, 0, 0, 0, 0)] = 15;
+                    continue;
+                }
+                const int mu1 = (i > 0 && j > 0) ? A.sim[(int)ra[i - 1] * A.sc.nsym + rb[j - 1]] : 0;
+                const int mu2 = (k > 0 && l > 0 && ca[k - 1] == cb[l - 1]) ? A.sc.w : 0;
+                int best = NEG, bid = 15;
+                for (int c = 0; c < 13; ++c) {
+                    const int xb = NA_XBITS[c];
+                    const int x0 = (xb >> 3) & 1, x1 = (xb >> 2) & 1, x2 = (xb >> 1) & 1, x3 = xb & 1;
+                    const int p0 = i - x0, p1 = j - x1, p2 = k - x2, p3 = l - x3;
+                    if (p0 < 0 || p1 < 0 || p2 < 0 || p3 < 0) continue;
+                    const int pa = p2 - p0, pb = p3 - p1;
+                    if (pa > s || pa < -s || pb > s || pb < -s) continue;
+                    int sc;  // pyx:233-248
+                    if (c == 0) sc = mu1 + mu2;
+                    else if (c <= 2) sc = gamma + gamma;
+                    else if (c == 3) sc = mu1 + Delta;
+                    else if (c == 4) sc = mu2 + Delta;
+                    else if (c <= 8) sc = gamma + Delta;
+                    else if (c <= 10) sc = gamma + mu2 + Delta;
+                    else sc = gamma + mu1 + Delta;
+                    const int v = lv[(size_t)((tau - (x0 + x1 + x2 + x3)) % 5) * items + (p0 * W + (pa + s)) * W + (pb + s)] + sc;
+                    if (bid == 15 || v > best) { best = v; bid = c; }
+                }
+                cur[it] = best;
+                if (TRACE) codes[code_index(m, s, i, j, a, b)] = (uint64_t)bid;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const int fin = lv[(size_t)((2 * (n + m)) % 5) * items + (n * W + s) * W + s];
+            A.scores[d.orig] = fin;
+            A.start_state[d.orig] = 0;
+            for (int t = 0; t < 9; ++t) A.end_values[(size_t)d.orig * 9 + t] = fin;
+        }
+        __syncthreads();
+    }
+}
+
+void launch_fill_nonaffine(const FillArgs& A, int grid, bool trace, cudaStream_t st) {
+    if (trace) fill_level_nonaffine_kernel<true><<<grid, 256, 0, st>>>(A);
+    else fill_level_nonaffine_kernel<false><<<grid, 256, 0, st>>>(A);
+}
+
 void launch_fill_generic(const FillArgs& A, int grid, bool trace, cudaStream_t st) {
     if (trace) fill_level_kernel<true><<<grid, 256, 0, st>>>(A);
     else fill_level_kernel<false><<<grid, 256, 0, st>>>(A);

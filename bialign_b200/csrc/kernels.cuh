@@ -51,7 +51,8 @@ struct TraceArgs {
     int npairs;
     int s;
     const uint64_t* codes;
-    int fmt;                  // 0: nibble t = case id (generic kernel); 1: 5-bit tie fields (systolic kernel)
+    int fmt;                  // 0: nibble t = case id (generic kernel); 1: 5-bit tie fields (systolic kernel);
+                              // 2: non-affine model, low nibble = case index 0..12
     const uint8_t* start_state;
     uint8_t* trace;           // slots; columns are written backwards from the end of each slot
     int* trace_len;           // [n_pairs] caller order
@@ -59,6 +60,7 @@ struct TraceArgs {
 };
 
 void launch_fill_generic(const FillArgs& A, int grid, bool trace, cudaStream_t st);
+void launch_fill_nonaffine(const FillArgs& A, int grid, bool trace, cudaStream_t st);
 size_t generic_scratch_ints(int nmax, int s);
 void launch_traceback(const TraceArgs& A, cudaStream_t st);
 

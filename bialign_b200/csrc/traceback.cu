@@ -10,6 +10,8 @@
 
 namespace ba {
 
+__constant__ int NA_XBITS_TB[13] = {15, 10, 5, 12, 3, 8, 4, 2, 1, 11, 7, 14, 13};  // pyx:233-248 order
+
 __global__ void __launch_bounds__(128) traceback_kernel(TraceArgs A) {
     const int pi = blockIdx.x * blockDim.x + threadIdx.x;
     if (pi >= A.npairs) return;
@@ -26,6 +28,15 @@ __global__ void __launch_bounds__(128) traceback_kernel(TraceArgs A) {
         first = false;
         const uint64_t wd = __ldg(codes + code_index(m, s, i, j, k - i, l - j));
         int id;
+        if (A.fmt == 2) {  // non-affine: the walk ends when no case reproduces the value (origin), pyx:521-528
+            const int cidx = (int)(wd & 15);
+            if (cidx > 12) { ok = 1; break; }
+            const int xbn = NA_XBITS_TB[cidx];
+            *--out = (uint8_t)xbn;
+            ++len;
+            i -= (xbn >> 3) & 1; j -= (xbn >> 2) & 1; k -= (xbn >> 1) & 1; l -= xbn & 1;
+            continue;
+        }
         if (A.fmt == 0) {
             id = (int)((wd >> (4 * state)) & 15);
         } else {

@@ -34,14 +34,12 @@ def test_readme_protein_toy_through_dropin():
         "2ffffffffffffdffffffffffffffffffdffffffff2ff"
 
 
-def test_goldens_affine(golden_cases):
-    """Every affine golden case of the unmodified reference: score and trace bit-exact."""
+def test_goldens_all_models(golden_cases):
+    """Every golden case of the unmodified reference (affine and non-affine): score and trace bit-exact."""
     from bialign_b200.batch import trace_hex
 
     groups = {}
     for idx, c in enumerate(golden_cases):
-        if c["params"]["gap_opening_cost"] == 0:
-            continue
         key = tuple(sorted((k, v) for k, v in c["params"].items()))
         groups.setdefault(key, []).append(idx)
     checked = 0
@@ -227,3 +225,39 @@ def test_rna_batch_score_only_vs_oracle():
     for q, (ia, ib) in enumerate(pairs):
         r = oracle.run(seqs[ia], seqs[ib], structs[ia], structs[ib], params, mode="codes")
         assert int(scores[q]) == r["score"], q
+
+
+def test_cli_transcripts_match_reference(capsys):
+    """bin/bialign.py stdout == the reference CLI's stdout (tests/golden/cli_outputs.json), all output modes, -v."""
+    import importlib.util
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bialign_cli", os.path.join(root, "bin", "bialign.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    cases = json.load(open(os.path.join(root, "tests", "golden", "cli_outputs.json")))
+    for c in cases:
+        capsys.readouterr()
+        try:
+            cli.main(c["argv"])
+        except SystemExit:
+            pass
+        out = capsys.readouterr().out
+        assert out == c["stdout"], c["argv"]
+
+
+def test_dropin_nonaffine_and_rna_api():
+    from bialign_b200 import bialignment as ba
+
+    b = ba.BiAligner("GCGGGGGAUAUCCCCAUCG", "GGGGAUAUCCCCAUCG", "...(((.....))).....", ".(((.....)))....", type="RNA",
+                     simmatrix=None, structure_weight=400, gap_opening_cost=0, gap_cost=-200, shift_cost=-250,
+                     max_shift=2, sequence_match_similarity=100, sequence_mismatch_similarity=0, nameA="A", nameB="B")
+    assert b.optimize() == 6300
+    tr = b.traceback()
+    assert all(isinstance(x, tuple) for x in tr)  # non-affine traces are tuples (pyx:526)
+    assert "".join("%x" % (8 * x[0] + 4 * x[1] + 2 * x[2] + x[3]) for x in tr) == "aaffffffffffffaffff"
+    with pytest.raises(KeyError):
+        ba.BiAligner("ACDJ", "ACD", "HHHH", "HHH", type="Protein", simmatrix="BLOSUM62", structure_weight=800,
+                     gap_opening_cost=-150, gap_cost=-50, shift_cost=-150, max_shift=1).optimize()
