@@ -93,6 +93,8 @@ struct ba_engine {
     DevBuf<int> d_scratch;
     DevBuf<int> d_counter;
     DevBuf<int> d_simp, d_tbtab, d_bnd;
+    DevBuf<unsigned long long> d_progress;
+    int opt_long = -1;                 // multi-CTA long-pair mode: -1 auto, 0 off, 1 force
     std::vector<int32_t> h_sim;
     int opt_warps = 4;                 // warps per CTA of the systolic kernel
     int opt_pad = -1;                  // systolic flavour: -1 auto, 0 pad-free, 1 padded
@@ -260,7 +262,7 @@ void ba_engine_destroy(ba_engine* e) {
     e->d_sim.release(); e->d_res.release(); e->d_cls.release(); e->d_desc.release(); e->d_codes.release();
     e->d_scratch.release(); e->d_counter.release(); e->d_scores.release(); e->d_start.release();
     e->d_complete.release(); e->d_trace.release(); e->d_endv.release(); e->d_tlen.release(); e->h_stage.release();
-    e->d_simp.release(); e->d_tbtab.release(); e->d_bnd.release();
+    e->d_simp.release(); e->d_tbtab.release(); e->d_bnd.release(); e->d_progress.release();
     cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -272,6 +274,7 @@ int ba_set_option(ba_engine* e, const char* key, int64_t value) {
     if (!strcmp(key, "code_arena_bytes")) e->opt_code_arena_bytes = value;
     else if (!strcmp(key, "kernel")) e->opt_kernel = (int)value;
     else if (!strcmp(key, "pad")) e->opt_pad = (int)value;
+    else if (!strcmp(key, "long")) e->opt_long = (int)value;
     else if (!strcmp(key, "warps_per_cta")) {
         if (value < 1 || value > 8) return fail(e, BA_ERR_INVALID_ARG, "warps_per_cta must be in 1..8");
         e->opt_warps = (int)value;
@@ -472,7 +475,11 @@ int ba_run(ba_engine* e, int want_trace) {
     size_t scratch_stride = 0, sys_smem = 0;
     int sysG = e->opt_warps;
     SysArgs SA{};
+    bool long_mode = false;
+    int long_grid_max = 0;
     if (kernel == 1) {
+        // the LONG flavour stages one 16-byte vector per thread: a record (<= 180 ints) needs >= 45 threads
+        if (e->opt_long == 1 && sysG < 2) sysG = 2;
         while (sysG > 1 && sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax) > 200 * 1024) --sysG;
         sys_smem = sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax);
         const int occ = sys_occupancy(s, want_trace != 0, plan.pad, plan.bneg, sysG, sys_smem);
@@ -488,7 +495,26 @@ int ba_run(ba_engine* e, int want_trace) {
             CU(e->d_tbtab.ensure(plan.tbtab.size()));
             CU(cudaMemcpyAsync(e->d_tbtab.p, plan.tbtab.data(), plan.tbtab.size() * 4, cudaMemcpyHostToDevice, e->stream));
         }
-        if (multi_pass) {
+        // Few, long pairs: spread the row blocks of each pair over the whole grid (LONG flavour, cooperative launch)
+        const int npass_max = (nmax + rows_pass) / rows_pass;
+        if (plan.bneg && e->opt_long != 0 && npass_max >= 2 && sysG >= 2 &&
+            (e->opt_long == 1 || ((int64_t)N * 2 <= max_grid && npass_max >= 4))) {
+            const int occl = sys_occupancy_long(s, want_trace != 0, plan.pad, sysG, sys_smem);
+            int coop = 0;
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
+            if (occl >= 1 && coop) {
+                long_mode = true;
+                long_grid_max = e->sm_count * occl;
+            } else if (e->opt_long == 1) {
+                return fail(e, BA_ERR_CUDA, "long-pair mode requested but cooperative launch is unavailable");
+            }
+        }
+        if (long_mode) {
+            const int lg = std::min(long_grid_max, npass_max);
+            cudaError_t ce = e->d_bnd.ensure((size_t)lg * 2 * sys_boundary_ints(s, plan.pad, sysG, mmax));
+            if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "boundary streams: " + std::string(cudaGetErrorString(ce)));
+            CU(e->d_progress.ensure((size_t)lg * 2));
+        } else if (multi_pass) {
             cudaError_t ce = e->d_bnd.ensure((size_t)grid * 2 * sys_boundary_ints(s, plan.pad, sysG, mmax));
             if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "boundary streams: " + std::string(cudaGetErrorString(ce)));
         }
@@ -499,6 +525,7 @@ int ba_run(ba_engine* e, int want_trace) {
         SA.k_2g2d = (int)((2 * e->sc.gamma + 2 * e->sc.delta) / plan.g * sh); SA.k_2d = (int)(2 * e->sc.delta / plan.g * sh);
         SA.negp = plan.negp; SA.tb_bits = plan.tb; SA.gscale = plan.g; SA.mmax = mmax;
         SA.boff = sys_boff(s, plan.pad, sysG); SA.bpad = sys_bpad(s, plan.pad, sysG, mmax);
+        SA.progress = e->d_progress.p;
         SA.bnd = e->d_bnd.p; SA.bnd_iters = biters + 8;  // matches sys_boundary_ints: slack records in front
         SA.codes = want_trace ? e->d_codes.p : nullptr;
         SA.scores = e->d_scores.p; SA.start_state = e->d_start.p; SA.end_values = e->d_endv.p;
@@ -523,7 +550,17 @@ int ba_run(ba_engine* e, int want_trace) {
         A.codes = want_trace ? e->d_codes.p : nullptr;
         A.scores = e->d_scores.p; A.start_state = e->d_start.p; A.end_values = e->d_endv.p;
         const int grid = (int)std::min<int64_t>(cnt, max_grid);
-        if (kernel == 1) {
+        if (kernel == 1 && long_mode) {
+            const int rows_pass = sysG * sys_geo(s, plan.pad).R;
+            for (int64_t q = 0; q < cnt; ++q) {  // one cooperative launch per pair
+                const int npass = (e->h_desc[b + q].n + rows_pass) / rows_pass;
+                const int lg = std::min(long_grid_max, npass);
+                CU(cudaMemsetAsync(e->d_progress.p, 0, sizeof(unsigned long long) * 2 * lg, e->stream));
+                SA.pairs = e->d_desc.p + b + q; SA.npairs = 1; SA.counter = e->d_counter.p + w;
+                CU(launch_fill_systolic_long(SA, lg, sysG, sys_smem, want_trace != 0, plan.pad, e->stream));
+                if (q + 1 < cnt) e->stats.kernel_launches++;
+            }
+        } else if (kernel == 1) {
             SA.pairs = e->d_desc.p + b; SA.npairs = (int)cnt; SA.counter = e->d_counter.p + w;
             CU(launch_fill_systolic(SA, grid, sysG, sys_smem, want_trace != 0, plan.pad, plan.bneg, e->stream));
         } else if (affine) {
@@ -566,7 +603,7 @@ int ba_run(ba_engine* e, int want_trace) {
         e->stats.code_bytes = cb;
     }
     e->stats.waves = n_waves;
-    e->stats.kernel_kind = kernel == 0 ? 0 : (plan.pad ? 2 : 1);
+    e->stats.kernel_kind = kernel == 0 ? 0 : (plan.pad ? 2 : 1) + (long_mode ? 2 : 0);
     e->last_fmt = kernel;
     e->ran = true;
     e->ran_trace = want_trace != 0;

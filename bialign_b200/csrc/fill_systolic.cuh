@@ -65,6 +65,17 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16s(unsigned smem_dst, const void* gsrc) {  // L2 only: coherent across SMs
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
@@ -99,7 +110,8 @@ struct Geo {
     static constexpr int NV = 12;                            // ring values per lane per iteration
     static constexpr int NX = 6;                             // short-delay values crossing a warp boundary
     static constexpr int PB = 16;                            // prefetch-buffer depth (iterations), power of two > LA
-    static constexpr int REC = (NV + NX) * LPR;              // ints per boundary record (one iteration of one row)
+    static constexpr int REAL = (NV + NX) * LPR;             // values per boundary record (one iteration of one row)
+    static constexpr int REC = (REAL + 3) & ~3;              // record stride in ints (16-byte multiple)
     static constexpr int RSLOT = NV * 32;
 };
 
@@ -110,11 +122,19 @@ struct Geo {
 //   tb     [P][LPR][12]               tie-break constants per (b, lane column, source state)  (TRACE)
 //   sim    [(nsym+1)][nsym]           similarity table (<< TB), last row zero
 //   resB/clsB  bytes, padded
-template <int S, bool TRACE, bool PAD, bool BNEG>
+//
+// LONG = one long pair spread over the whole grid (cooperative launch): CTA b runs the row blocks
+// ("passes") b, b+NC, b+2NC, ... and the boundary stream of pass p is consumed by pass p+1 on another
+// CTA while it is being produced.  Streams live in 2*NC global buffers (pass p -> buffer
+// p%NC + NC*((p/NC)&1): by the time it is overwritten, at pass p+2NC, pass p+1 has finished because
+// every later pass transitively depends on it).  Progress flags (pass id << 32 | records complete)
+// are published every 16 iterations with release semantics and polled with acquire loads; stream
+// reads are 16-byte cp.async.cg (L2 only), so no stale L1 line can be seen across SMs.
+template <int S, bool TRACE, bool PAD, bool BNEG, bool LONG>
 __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
     using G_ = Geo<S, PAD>;
     constexpr int W = G_::W, P = G_::P, LPR = G_::LPR, R = G_::R, RING = G_::RING, NV = G_::NV, NX = G_::NX, PB = G_::PB;
-    constexpr int RSLOT = G_::RSLOT, REC = G_::REC;
+    constexpr int RSLOT = G_::RSLOT, REC = G_::REC, REAL = G_::REAL;
     constexpr bool RP2 = (RING & (RING - 1)) == 0;  // power-of-two ring: slots are masks of the iteration counter
     extern __shared__ __align__(16) int smem[];
     const int G = blockDim.x >> 5;
@@ -164,12 +184,19 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
     const int xs_in = g * 4 * NX * LPR;                                // xs block feeding this warp's row 0
     const int xs_out = (g + 1) * 4 * NX * LPR;
 
+    bool long_done = false;
     for (;;) {
-        if (tid == 0) s_pair = atomicAdd(A.counter, 1);
-        __syncthreads();
-        const int pi = s_pair;
-        __syncthreads();
-        if (pi >= A.npairs) return;
+        int pi = 0;
+        if (LONG) {
+            if (long_done) return;
+            long_done = true;
+        } else {
+            if (tid == 0) s_pair = atomicAdd(A.counter, 1);
+            __syncthreads();
+            pi = s_pair;
+            __syncthreads();
+            if (pi >= A.npairs) return;
+        }
         const PairDesc d = A.pairs[pi];
         const int n = d.n, m = d.m;
         const uint8_t* ra = A.res + d.offA;
@@ -185,9 +212,10 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
         const int npass = (n + RT) / RT;  // ceil((n+1)/RT)
         const int nit = (m + 1) * P + 2 * (RT - 1) + LPR + RING;
         const size_t bstride = (size_t)A.bnd_iters * REC;  // ints per boundary buffer
-        int* bnd_base = A.bnd + (size_t)blockIdx.x * 2 * bstride;
+        int* bnd_base = A.bnd + (LONG ? (size_t)0 : (size_t)blockIdx.x * 2 * bstride);
+        const int NC = gridDim.x;
 
-        for (int pass = 0; pass < npass; ++pass) {
+        for (int pass = LONG ? (int)blockIdx.x : 0; pass < npass; pass += LONG ? NC : 1) {
             const int i = pass * RT + g * R + r;
             const int k = i + a;
             const bool lane_ok = lane_real && i <= n && k >= 0 && k <= n;
@@ -195,10 +223,16 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
             const int Ak = (lane_ok && k >= 1) ? ca[k - 1] : 254;
             const int* simrow = ssim + Ai * nsym;
             const bool has_in = pass > 0, has_out = pass + 1 < npass;
-            const int* bnd_in = bnd_base + (size_t)((pass + 1) & 1) * bstride;
-            int* bnd_out = bnd_base + (size_t)(pass & 1) * bstride;
+            const int buf_in = LONG ? ((pass - 1 + 2 * NC) % NC) + NC * ((((pass - 1 + 2 * NC) / NC) & 1)) : ((pass + 1) & 1);
+            const int buf_out = LONG ? (pass % NC) + NC * (((pass + 2 * NC) / NC) & 1) : (pass & 1);
+            const int* bnd_in = bnd_base + (size_t)buf_in * bstride;
+            int* bnd_out = bnd_base + (size_t)buf_out * bstride;
+            const unsigned long long* prog_in = LONG ? A.progress + buf_in : nullptr;
+            unsigned long long* prog_out = LONG ? A.progress + buf_out : nullptr;
+            const unsigned long long tag_in = (unsigned long long)pass << 32;         // producer pass id + 1
+            const unsigned long long tag_out = (unsigned long long)(pass + 1) << 32;
             // boundary I/O descriptors: thread e moves record element e (= v*LPR + cs) every iteration
-            const bool io_thread = tid < REC;
+            const bool io_thread = tid < REAL;
             const int io_v = tid / LPR, io_cs = tid - io_v * LPR;
             const bool io_ring = io_v < NV;
             const int io_stride = io_ring ? RSLOT : NX * LPR;
@@ -206,11 +240,25 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                                        : (int)((G + 1) * RING * RSLOT) + (io_v - NV) * LPR + io_cs;
             const int fl_src = io_col + (io_ring ? G * RING * RSLOT : G * 4 * NX * LPR);  // CTA output row
             const int st_dst = io_col;                                                    // ring[0] / xs[0]
-            const bool io_fast = REC <= (int)blockDim.x;
+            const bool io_fast = REAL <= (int)blockDim.x;
             // Boundary streams hold record `rec` at offset (rec + PRE + 1) * REC, so the unconditional flush of
             // "iteration q-1" in the very first iteration lands in a slack record.  Running pointers, shared-memory
             // addresses in bytes: the fast path is ~7 instructions per direction and iteration.
-            const bool do_flush = has_out && io_fast && io_thread, do_stage = has_in && io_fast && io_thread;
+            const bool do_flush = has_out && io_fast && io_thread, do_stage = !LONG && has_in && io_fast && io_thread;
+            // LONG staging: thread e4 < REC/4 moves four consecutive record elements (one 16-byte cp.async.cg)
+            constexpr int NVEC = REC / 4;
+            unsigned lg_dst[4] = {0, 0, 0, 0};
+            int lg_ring = 0, lg_real = 0;
+            if (LONG && tid < NVEC) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = 4 * tid + u, v = e / LPR, cs = e - v * LPR;
+                    const bool rg = v < NV;
+                    lg_ring |= rg ? (1 << u) : 0;
+                    lg_real |= (e < REAL) ? (1 << u) : 0;
+                    lg_dst[u] = smem_u32(smem + (rg ? v * 32 + (R - 1) * LPR + cs : (int)((G + 1) * RING * RSLOT) + (v - NV) * LPR + cs));
+                }
+            }
             int* fl_g = bnd_out + tid;                                                   // record q-1 of iteration q = -PRE
             const int* st_g = bnd_in + (size_t)(2 * RT + LA + 1) * REC + tid;            // record (q + LA + 2RT) of q = -PRE
             const unsigned fl_s = smem_u32(smem + fl_src), st_s = smem_u32(smem + st_dst), pb_s = smem_u32(pb + tid);
@@ -239,9 +287,21 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
             int h2Q1010 = NEGP, h2Q1001 = NEGP, h2Q1011 = NEGP, h3Q1011 = NEGP;
             int h2R11[3] = {NEGP, NEGP, NEGP};
 
-            if (has_in) {  // prime the cp.async pipeline: records for iterations -PRE..LA-PRE-1
+            if (LONG && has_in) {  // wait for the first records of the producer pass, then prime with 16-byte copies
+                if (tid == 0) {
+                    const unsigned long long want = tag_in | (unsigned long long)min(LA + 2 * RT, nit);
+                    while (ld_acquire_u64(prog_in) < want) __nanosleep(100);
+                }
+                __syncthreads();
                 for (int t0 = -PRE; t0 < LA - PRE; ++t0) {
-                    for (int e = tid; e < REC; e += blockDim.x) {
+                    const int rec = t0 + 2 * RT;
+                    if (tid < NVEC && rec < nit)
+                        cp_async16s(smem_u32(pb + (t0 & (PB - 1)) * REC + 4 * tid), bnd_in + (size_t)(rec + PRE + 1) * REC + 4 * tid);
+                    cp_async_commit();
+                }
+            } else if (has_in) {  // prime the cp.async pipeline: records for iterations -PRE..LA-PRE-1
+                for (int t0 = -PRE; t0 < LA - PRE; ++t0) {
+                    for (int e = tid; e < REAL; e += blockDim.x) {
                         const int rec = t0 + 2 * RT;
                         if (rec >= 0 && rec < nit) cp_async4(pb + (t0 & (PB - 1)) * REC + e, bnd_in + (size_t)(rec + PRE + 1) * REC + e);
                     }
@@ -251,6 +311,19 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
             __syncthreads();
 
             for (int q = -PRE; q < nit; ++q) {
+                if (LONG && (q & 15) == 0) {
+                    if (tid == 0) {
+                        if (has_out && q > 0) {  // records 0..q-2 were stored before the last barrier
+                            __threadfence();
+                            st_release_u64(prog_out, tag_out | (unsigned long long)(q - 1));
+                        }
+                        if (has_in) {  // the next 16 iterations prefetch records up to q + 15 + LA + 2RT
+                            const unsigned long long want = tag_in | (unsigned long long)min(q + 16 + LA + 2 * RT, nit);
+                            while (ld_acquire_u64(prog_in) < want) __nanosleep(100);
+                        }
+                    }
+                    __syncthreads();
+                }
                 // ---- advance position
                 ++bb;
                 if (bb == P) { bb = 0; ++j; }
@@ -269,7 +342,7 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                     if (do_flush) *fl_g = lds32(fl_s + (io_ring ? ps : ((q - 1) & 3)) * io_stride_b);
                     fl_g += REC;
                     if (has_out && !io_fast && q > -PRE) {
-                        for (int e = tid; e < REC; e += blockDim.x) {
+                        for (int e = tid; e < REAL; e += blockDim.x) {
                             const int v = e / LPR, cs = e - v * LPR;
                             const int val = (v < NV) ? ring[(G * RING + ps) * RSLOT + v * 32 + (R - 1) * LPR + cs]
                                                      : xs[(G * 4 + ((q - 1) & 3)) * NX * LPR + (v - NV) * LPR + cs];
@@ -438,7 +511,22 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                 }
 
                 // ---- stage the incoming boundary: virtual row above warp 0, iteration q
-                if (has_in) {
+                if (LONG && has_in) {
+                    cp_async_wait<LA - 1>();
+                    if (tid < NVEC) {
+                        int4 v4 = make_int4(NEGP, NEGP, NEGP, NEGP);
+                        if (q < q_rec_lim) v4 = *reinterpret_cast<const int4*>(pb + (q & (PB - 1)) * REC + 4 * tid);
+                        const int vals[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if ((lg_real >> u) & 1)
+                                sts32(lg_dst[u] + (((lg_ring >> u) & 1) ? wslot * (RSLOT * 4) : (q & 3) * (NX * LPR * 4)), vals[u]);
+                        if (q + LA < q_rec_lim)
+                            cp_async16s(smem_u32(pb + ((q + LA) & (PB - 1)) * REC + 4 * tid),
+                                        bnd_in + (size_t)(q + LA + 2 * RT + PRE + 1) * REC + 4 * tid);
+                    }
+                    cp_async_commit();
+                } else if (has_in) {
                     cp_async_wait<LA - 1>();
                     if (do_stage) {
                         int val = lds32(pb_s + (q & (PB - 1)) * (REC * 4));
@@ -449,7 +537,7 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                     st_g += REC;
                     if (!io_fast) {
                         const int rec = q + 2 * RT, nrec = rec + LA;
-                        for (int e = tid; e < REC; e += blockDim.x) {
+                        for (int e = tid; e < REAL; e += blockDim.x) {
                             const int v = e / LPR, cs = e - v * LPR;
                             const int val = (rec >= 0 && rec < nit) ? pb[(q & (PB - 1)) * REC + e] : NEGP;
                             if (v < NV) ring[(0 * RING + wslot) * RSLOT + v * 32 + (R - 1) * LPR + cs] = val;
@@ -462,13 +550,20 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                 __syncthreads();
             }  // iterations
             if (has_out) {  // last iteration's record, then make the stream visible to the next pass
-                for (int e = tid; e < REC; e += blockDim.x) {
+                for (int e = tid; e < REAL; e += blockDim.x) {
                     const int v = e / LPR, cs = e - v * LPR;
                     const int val = (v < NV) ? ring[(G * RING + wslot) * RSLOT + v * 32 + (R - 1) * LPR + cs]
                                              : xs[(G * 4 + ((nit - 1) & 3)) * NX * LPR + (v - NV) * LPR + cs];
                     bnd_out[(size_t)(nit + PRE) * REC + e] = val;
                 }
                 __threadfence();
+                if (LONG) {
+                    __syncthreads();
+                    if (tid == 0) {
+                        __threadfence();
+                        st_release_u64(prog_out, tag_out | (unsigned long long)nit);
+                    }
+                }
             }
             if (has_in) cp_async_wait<0>();
             if (!has_out && has_in) {
@@ -493,16 +588,35 @@ size_t smem_bytes_t(int G, int nsym, int bpad) {
 
 template <int S, bool TRACE, bool PAD, bool BNEG>
 cudaError_t launch_t(const SysArgs& A, int grid, int G, size_t smem, cudaStream_t st) {
-    auto kern = fill_systolic_kernel<S, TRACE, PAD, BNEG>;
+    auto kern = fill_systolic_kernel<S, TRACE, PAD, BNEG, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, G * 32, smem, st>>>(A);
     return cudaGetLastError();
 }
 
+// LONG flavour: cooperative launch (all CTAs must be co-resident: they wait on one another)
+template <int S, bool TRACE, bool PAD>
+cudaError_t launch_long_t(const SysArgs& A, int grid, int G, size_t smem, cudaStream_t st) {
+    auto kern = fill_systolic_kernel<S, TRACE, PAD, true, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    SysArgs a = A;
+    void* params[] = {&a};
+    return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(G * 32), params, smem, st);
+}
+template <int S, bool TRACE, bool PAD>
+int occ_long_t(int G, size_t smem) {
+    auto kern = fill_systolic_kernel<S, TRACE, PAD, true, true>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, G * 32, smem);
+    return nb;
+}
+
 template <int S, bool TRACE, bool PAD, bool BNEG>
 int occ_t(int G, size_t smem) {
-    auto kern = fill_systolic_kernel<S, TRACE, PAD, BNEG>;
+    auto kern = fill_systolic_kernel<S, TRACE, PAD, BNEG, false>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, G * 32, smem);
@@ -516,6 +630,16 @@ cudaError_t launch_s(const SysArgs& A, int grid, int G, size_t smem, bool trace,
     if (!pad) return trace ? launch_t<S, true, false, true>(A, grid, G, smem, st) : launch_t<S, false, false, true>(A, grid, G, smem, st);
     if (bneg) return trace ? launch_t<S, true, true, true>(A, grid, G, smem, st) : launch_t<S, false, true, true>(A, grid, G, smem, st);
     return trace ? launch_t<S, true, true, false>(A, grid, G, smem, st) : launch_t<S, false, true, false>(A, grid, G, smem, st);
+}
+template <int S>
+cudaError_t launch_long_s(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, cudaStream_t st) {
+    if (pad) return trace ? launch_long_t<S, true, true>(A, grid, G, smem, st) : launch_long_t<S, false, true>(A, grid, G, smem, st);
+    return trace ? launch_long_t<S, true, false>(A, grid, G, smem, st) : launch_long_t<S, false, false>(A, grid, G, smem, st);
+}
+template <int S>
+int occ_long_s(bool trace, bool pad, int G, size_t smem) {
+    if (pad) return trace ? occ_long_t<S, true, true>(G, smem) : occ_long_t<S, false, true>(G, smem);
+    return trace ? occ_long_t<S, true, false>(G, smem) : occ_long_t<S, false, false>(G, smem);
 }
 template <int S>
 int occ_s(bool trace, bool pad, bool bneg, int G, size_t smem) {

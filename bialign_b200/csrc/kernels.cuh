@@ -38,6 +38,7 @@ struct SysArgs {
     const PairDesc* pairs;
     int npairs;
     int* counter;
+    unsigned long long* progress;  // LONG flavour: one progress flag per boundary stream (2 * grid)
     int* bnd;                 // per CTA: two boundary streams of bnd_iters records
     int bnd_iters;
     uint64_t* codes;
@@ -73,5 +74,7 @@ int sys_occupancy(int S, bool trace, bool pad, bool bneg, int G, size_t smem);
 int sys_boff(int S, bool pad, int G);
 int sys_bpad(int S, bool pad, int G, int mmax);
 cudaError_t launch_fill_systolic(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, bool bneg, cudaStream_t st);
+int sys_occupancy_long(int S, bool trace, bool pad, int G, size_t smem);
+cudaError_t launch_fill_systolic_long(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, cudaStream_t st);
 
 }  // namespace ba

@@ -7,7 +7,7 @@ import oracle
 from test_gpu_parity import _random_protein_batch, _decode_codes
 from bialign_b200.batch import BatchAligner, trace_hex
 
-def main(s, seed, npairs, lo, hi, warps=4, kernel=1, extra=None):
+def main(s, seed, npairs, lo, hi, warps=4, kernel=1, pad=-1, long=-1, extra=None):
     rng = np.random.default_rng(seed)
     params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150, gap_cost=-50,
                   shift_cost=-150, max_shift=s)
@@ -15,6 +15,7 @@ def main(s, seed, npairs, lo, hi, warps=4, kernel=1, extra=None):
     seqs, structs, pairs = _random_protein_batch(rng, npairs, lo, hi)
     al = BatchAligner(**params)
     al.engine.set_option("kernel", kernel); al.engine.set_option("warps_per_cta", warps)
+    al.engine.set_option("pad", pad); al.engine.set_option("long", long)
     scores, cols, offsets, complete = al.align(seqs, structs, pairs, want_trace=True)
     kind = al.engine.stats()["kernel_kind"]
     W = 2 * s + 1

@@ -144,6 +144,7 @@ def _unselect(engine):
     engine.set_option("kernel", -1)
     engine.set_option("pad", -1)
     engine.set_option("warps_per_cta", 4)
+    engine.set_option("long", -1)
 
 
 @pytest.mark.parametrize("kernel", [0, 1, 2])
@@ -261,3 +262,45 @@ def test_dropin_nonaffine_and_rna_api():
     with pytest.raises(KeyError):
         ba.BiAligner("ACDJ", "ACD", "HHHH", "HHH", type="Protein", simmatrix="BLOSUM62", structure_weight=800,
                      gap_opening_cost=-150, gap_cost=-50, shift_cost=-150, max_shift=1).optimize()
+
+
+@pytest.mark.parametrize("pad", [0, 1])
+@pytest.mark.parametrize("warps", [1, 4])
+def test_long_pair_mode_multi_cta(warps, pad):
+    """Row blocks of one pair spread over several CTAs (cooperative launch, flag-synchronised boundary streams)."""
+    rng = np.random.default_rng(900 + warps + 10 * pad)
+    for s in (1, 2, 3):
+        params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150,
+                      gap_cost=-50, shift_cost=-150, max_shift=s)
+        seqs, structs, pairs = _random_protein_batch(rng, 3, 90, 260)
+        al = _aligner(params)
+        _select(al.engine, 1 + pad)
+        al.engine.set_option("warps_per_cta", warps)
+        al.engine.set_option("long", 1)
+        try:
+            _check_batch(al, seqs, structs, pairs, params, table_pairs=3)
+            assert al.engine.stats()["kernel_kind"] == 3 + pad
+        finally:
+            _unselect(al.engine)
+
+
+def test_long_pair_auto_mode_many_passes():
+    """One 1500 x 1400 pair, max_shift 1: auto-selected long mode, dozens of passes over dozens of CTAs."""
+    rng = np.random.default_rng(1234)
+    params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150, gap_cost=-50,
+                  shift_cost=-150, max_shift=1)
+    aa = "ARNDCQEGHILKMFPSTWYV"
+    a = "".join(aa[i] for i in rng.integers(0, 20, 1500))
+    b = list(a[:1400])
+    for q in range(0, 1400, 7):
+        b[q] = aa[rng.integers(0, 20)]
+    b = "".join(b[:700] + b[650:])[:1400]
+    sa = "".join("HEC"[i] for i in rng.integers(0, 3, 1500))
+    sb = sa[3:1403]
+    al = _aligner(params)
+    from bialign_b200.batch import trace_hex
+    scores, cols, offsets, complete = al.align([a, b], [sa, sb], [(0, 1)], want_trace=True)
+    assert al.engine.stats()["kernel_kind"] in (3, 4)
+    r = oracle.run(a, b, sa, sb, params, mode="codes")
+    assert int(scores[0]) == r["score"] and trace_hex(cols, offsets, 0) == r["trace"] and bool(complete[0])
+    assert (al.align([a, b], [sa, sb], [(0, 1)], want_trace=False) == scores).all()
