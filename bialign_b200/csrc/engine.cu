@@ -9,6 +9,8 @@
 //   trace       one slot of 2(n+m)+2 bytes per pair, columns written backwards by the traceback
 //   scores/start_state/end_values/trace_len/complete   per pair, caller order
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <numeric>
@@ -107,6 +109,8 @@ struct ba_engine {
     bool have_tlen = false;
 
     int64_t opt_code_arena_bytes = 0;  // 0 = auto
+    int64_t arena_from_option = 0;     // option value the current arena was sized with
+    bool arena_is_budget = false;      // current arena = the full memory budget (not just "all pairs fit")
     int opt_kernel = -1;               // -1 auto
     ba_stats stats{};
 };
@@ -213,7 +217,7 @@ SysPlan plan_systolic(const ba_engine* e, int nmax, int mmax, bool trace) {
                     const int T0 = (c - S) + hb0(s01) - hb0(s23), T1 = (bb - S) + hb1(s01) - hb1(s23);
                     const int k1 = std::abs(T1), k0 = std::abs(T0) + k1;
                     const int rank = (int)(std::lower_bound(keys.begin(), keys.end(), std::make_pair(k0, k1)) - keys.begin());
-                    pl.tbtab[((size_t)bb * LPR + c) * 12 + src] = ((NK - 1 - rank) << 5) | (18 - src);
+                    pl.tbtab[((size_t)bb * LPR + c) * 12 + src] = ((NK - 1 - rank) << 5) | (27 - src);
                 }
     }
     pl.ok = true;
@@ -354,6 +358,15 @@ int ba_run(ba_engine* e, int want_trace) {
     CU(cudaSetDevice(e->device));
     const int64_t N = e->n_pairs;
     const int s = e->sc.s;
+    const bool timing = getenv("BA_TIMING") != nullptr;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto t_start = tnow();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto t = tnow();
+        fprintf(stderr, "[ba_run] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_start).count());
+        t_start = t;
+    };
     e->ran = false;
     e->have_tlen = false;
     e->stats = ba_stats{};
@@ -382,6 +395,7 @@ int ba_run(ba_engine* e, int want_trace) {
         if ((int64_t)(nmax + mmax + 2) * col >= ((int64_t)1 << 30))
             return fail(e, BA_ERR_SCORE_RANGE, "score bound exceeds int32 range (needs the reference's int64 tables)");
     }
+    lap("lengths + range check");
     std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
         return (int64_t)(ln[x] + 1) * (lm[x] + 1) > (int64_t)(ln[y] + 1) * (lm[y] + 1);
     });
@@ -398,6 +412,7 @@ int ba_run(ba_engine* e, int want_trace) {
             trace_total += (e->h_slot_cap[p] + 15) & ~15;
         }
 
+    lap("sort + slots");
     // code arena
     size_t arena_words = 0;
     std::vector<int64_t> wave_begin;  // indices into sorted order
@@ -408,14 +423,23 @@ int ba_run(ba_engine* e, int want_trace) {
             total_words += wds;
             max_words = std::max(max_words, wds);
         }
-        int64_t budget_bytes = e->opt_code_arena_bytes;
-        if (budget_bytes <= 0) {
-            size_t fr = 0, tot = 0;
-            CU(cudaMemGetInfo(&fr, &tot));
-            budget_bytes = (int64_t)(fr + e->d_codes.cap * 8) / 2;
+        // The arena is sticky: once allocated it is reused as long as the largest pair fits (a 90 GB
+        // cudaFree + cudaMalloc costs tens of milliseconds and free memory drifts from run to run).
+        if ((int64_t)e->d_codes.cap >= max_words && (e->opt_code_arena_bytes <= 0 || e->arena_from_option == e->opt_code_arena_bytes) &&
+            ((int64_t)e->d_codes.cap >= total_words || e->arena_is_budget)) {
+            arena_words = (size_t)std::min<int64_t>((int64_t)e->d_codes.cap, total_words);
+        } else {
+            int64_t budget_bytes = e->opt_code_arena_bytes;
+            if (budget_bytes <= 0) {
+                size_t fr = 0, tot = 0;
+                CU(cudaMemGetInfo(&fr, &tot));
+                budget_bytes = (int64_t)(fr + e->d_codes.cap * 8) / 2;
+            }
+            int64_t budget_words = std::max<int64_t>(budget_bytes / 8, max_words);
+            arena_words = (size_t)std::min(budget_words, total_words);
+            e->arena_is_budget = budget_words <= total_words;
+            e->arena_from_option = e->opt_code_arena_bytes;
         }
-        int64_t budget_words = std::max<int64_t>(budget_bytes / 8, max_words);
-        arena_words = (size_t)std::min(budget_words, total_words);
         cudaError_t ce = e->d_codes.ensure(arena_words);
         if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "traceback-code arena: " + std::string(cudaGetErrorString(ce)));
     }
@@ -446,6 +470,7 @@ int ba_run(ba_engine* e, int want_trace) {
         wave_begin.push_back(N);
     }
     const int n_waves = (int)wave_begin.size() - 1;
+    lap("arena + waves");
 
     // ---- buffers
     CU(e->d_desc.ensure((size_t)N));
@@ -463,6 +488,7 @@ int ba_run(ba_engine* e, int want_trace) {
         e->ran_trace = want_trace != 0;
         return BA_OK;
     }
+    lap("result buffers");
     int64_t biggest_wave = 0;
     for (int w = 0; w < n_waves; ++w) biggest_wave = std::max(biggest_wave, wave_begin[w + 1] - wave_begin[w]);
     // ---- kernel choice: systolic when its exactness conditions hold, else the generic level kernel
@@ -498,7 +524,7 @@ int ba_run(ba_engine* e, int want_trace) {
         // Few, long pairs: spread the row blocks of each pair over the whole grid (LONG flavour, cooperative launch)
         const int npass_max = (nmax + rows_pass) / rows_pass;
         if (plan.bneg && e->opt_long != 0 && npass_max >= 2 && sysG >= 2 &&
-            (e->opt_long == 1 || ((int64_t)N * 2 <= max_grid && npass_max >= 4))) {
+            (e->opt_long == 1 || (N <= 4 && npass_max >= 8))) {
             const int occl = sys_occupancy_long(s, want_trace != 0, plan.pad, sysG, sys_smem);
             int coop = 0;
             cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
@@ -535,6 +561,7 @@ int ba_run(ba_engine* e, int want_trace) {
         cudaError_t ce = e->d_scratch.ensure(scratch_stride * grid);
         if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "fill scratch: " + std::string(cudaGetErrorString(ce)));
     }
+    lap("kernel plan + scratch");
     CU(cudaMemcpyAsync(e->d_desc.p, e->h_desc.data(), sizeof(PairDesc) * N, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemsetAsync(e->d_counter.p, 0, sizeof(int) * n_waves, e->stream));
 
@@ -582,7 +609,9 @@ int ba_run(ba_engine* e, int want_trace) {
         CU(cudaEventRecord(ev[2 + 3 * w], e->stream));
         CU(cudaEventRecord(ev[3 + 3 * w], e->stream));
     }
+    lap("launches");
     CU(cudaStreamSynchronize(e->stream));
+    lap("device");
     {
         float ms = 0;
         for (int w = 0; w < n_waves; ++w) {

@@ -35,7 +35,7 @@
 //
 // Traceback codes.  With TRACE the integers carry the tie-break of pyx:555-564 in their low bits:
 // value << TB | (inverted rank of the tie key (|T0|+|T1|, |T1|) of (cell, source state)) << 5 |
-// id field, so plain integer max implements (value desc, key asc, case id asc) exactly.  The id
+// id field (27 - source state), so plain integer max implements (value desc, key asc, case id asc) exactly.  The id
 // field of the winner (5 bits per state, 45 bits per cell) is streamed to HBM, one 8-byte word per
 // cell, each lane writing its own contiguous stream.
 #pragma once
@@ -420,22 +420,24 @@ __global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
                 kF[6] = mu1 + kGD + pU1;           // x=1101
                 kF[7] = mu1 + kGD + pB1;           // x=1110
                 kF[8] = mu1 + mu2;                 // x=1111
+                // half-column cases also re-base the id field of the winner they carry (TRACE): a full-column
+                // source has field 27 - src (19..27); -10 maps the (t01, h) sources of x=(0,0,t2,t3) to 9..17 and
+                // -19 the (h, t23) sources of x=(t0,t1,0,0) to 0..8, so on equal tie keys the three groups keep the
+                // reference's case order (ids 0-8 < 9-11 < 12-14) and the source stays decodable.
+                constexpr int ADJ2 = TRACE ? -10 : 0, ADJ1 = TRACE ? -19 : 0;
                 int kh2[3], kh1[3];
-                kh2[0] = kGD + pB0;                // x=0001
-                kh2[1] = kGD + pW;                 // x=0010
-                kh2[2] = mu2 + k2D + pW + pB0;     // x=0011
-                kh1[0] = kGD + pB1;                // x=0100
-                kh1[1] = kGD + pU1;                // x=1000
-                kh1[2] = mu1 + k2D + pU1 + pB1;    // x=1100
+                kh2[0] = kGD + ADJ2 + pB0;             // x=0001
+                kh2[1] = kGD + ADJ2 + pW;              // x=0010
+                kh2[2] = mu2 + k2D + ADJ2 + pW + pB0;  // x=0011
+                kh1[0] = kGD + ADJ1 + pB1;             // x=0100
+                kh1[1] = kGD + ADJ1 + pU1;             // x=1000
+                kh1[2] = mu1 + k2D + ADJ1 + pU1 + pB1; // x=1100
                 int M[9];
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
                     const int t01 = t / 3, t23 = t % 3;
-                    // tie-break id-field adjustments (TRACE): H2 -> 9 - r23, H1 -> 6 - 3*r01 (see engine.cu)
-                    const int c2 = kh2[t23] + (TRACE ? (-9 + 3 * t01) : 0);
-                    const int c1 = kh1[t01] + (TRACE ? (-12 + t23) : 0);
-                    const int v1 = addmax(inH1[t], c1, NEGP);  // floor: nothing ever drops below "minus infinity"
-                    const int v = addmax(inH2[t], c2, v1);
+                    const int v1 = addmax(inH1[t], kh1[t01], NEGP);  // floor: nothing ever drops below "minus infinity"
+                    const int v = addmax(inH2[t], kh2[t23], v1);
                     M[t] = addmax(inF[t], kF[t], v);
                     M[t] = valid ? M[t] : NEGP;
                 }

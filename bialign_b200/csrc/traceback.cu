@@ -40,15 +40,23 @@ __global__ void __launch_bounds__(128) traceback_kernel(TraceArgs A) {
         if (A.fmt == 0) {
             id = (int)((wd >> (4 * state)) & 15);
         } else {
-            // systolic format: fields 0..5 in the low word, 6..8 in the high word, 5 bits each.  The field
-            // is the id part of the winner's tie-break: 10..18 -> full column, source 18-f (ids 0-8);
-            // 7..9 -> half column x=(0,0,t2,t3), id f+2 (9-11); 0,3,6 -> x=(t0,t1,0,0), id 12+f/3.
+            // systolic format: fields 0..5 in the low word, 6..8 in the high word, 5 bits each.  The field is the
+            // id part of the winner's tie-break: a source state src carries 27 - src;
+            //   19..27        full column, case id = source = 27 - f                     (ids 0-8)
+            //    9..17        x=(0,0,t2,t3), source (t01, h): f = 17 - 3*t01 - rank(h)   (ids 9-11, h = 11,10,01)
+            //    0..8         x=(t0,t1,0,0), source (h, t23): f = 8 - 3*rank(h) - t23    (ids 12-14)
             const unsigned half = state < 6 ? (unsigned)wd : (unsigned)(wd >> 32);
             const int f = (int)((half >> (5 * (state < 6 ? state : state - 6))) & 31);
-            if (f >= 10 && f <= 18) id = 18 - f;
-            else if (f >= 7 && f <= 9) id = f + 2;
-            else if (f == 0 || f == 3 || f == 6) id = 12 + f / 3;
-            else id = 15;
+            const int t01 = state / 3, t23 = state % 3;
+            id = 15;
+            if (f >= 19 && f <= 27) id = 27 - f;
+            else if (f >= 9 && f <= 17) {
+                const int rk = 17 - 3 * t01 - f;
+                if (rk >= 0 && rk <= 2) id = 9 + (2 - rk);
+            } else if (f <= 8) {
+                const int num = 8 - t23 - f;
+                if (num >= 0 && num <= 6 && num % 3 == 0) id = 12 + (2 - num / 3);
+            }
         }
         if (id == 15) break;  // no case reproduced the value (pyx:570-571)
         int xb, src;

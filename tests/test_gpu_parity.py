@@ -91,12 +91,15 @@ def _decode_codes(words, kind):
             sh = 5 * t if t < 6 else 32 + 5 * (t - 6)
             f = ((w >> np.uint64(sh)) & np.uint64(31)).astype(np.int64)
             ids = np.full(f.shape, 15, dtype=np.int64)
-            full = (f >= 10) & (f <= 18)
-            ids[full] = 18 - f[full]
-            h2 = (f >= 7) & (f <= 9)
-            ids[h2] = f[h2] + 2
-            h1 = (f == 0) | (f == 3) | (f == 6)
-            ids[h1] = 12 + f[h1] // 3
+            t01, t23 = t // 3, t % 3
+            full = (f >= 19) & (f <= 27)
+            ids[full] = 27 - f[full]
+            rk = 17 - 3 * t01 - f
+            h2 = (f >= 9) & (f <= 17) & (rk >= 0) & (rk <= 2)
+            ids[h2] = 9 + (2 - rk[h2])
+            num = 8 - t23 - f
+            h1 = (f <= 8) & (num >= 0) & (num <= 6) & (num % 3 == 0)
+            ids[h1] = 12 + (2 - num[h1] // 3)
             out[:, t] = ids
     return out
 
