@@ -175,8 +175,14 @@ SysPlan plan_systolic(const ba_engine* e, int nmax, int mmax, bool trace) {
     const int64_t c1p = pos({smax, sc.gamma, gb}), c1n = pos({-smin, -(int64_t)sc.gamma, -gb});
     const int64_t c2p = pos({sc.w, sc.gamma, gb}), c2n = pos({-(int64_t)sc.w, -(int64_t)sc.gamma, -gb});
     const int64_t dp = pos({sc.delta}), dn = pos({-(int64_t)sc.delta});
-    const int64_t len = (int64_t)nmax + mmax + 2;
-    const int64_t Fp = len * (c1p + c2p + 2 * dp) / g + 2, Fn = len * (c1n + c2n + 2 * dn) / g + 2;
+    // Every finite value lies in [-Fn, Fp]: a path has at most n+m half-columns per alignment and 2(n+m)
+    // shift units; only min(n,m) of the half-columns of an alignment can be matches.
+    const int64_t len = (int64_t)nmax + mmax + 2, mlen = std::min(nmax, mmax) + 1;
+    const int64_t g1p = pos({(int64_t)sc.gamma, gb}), m1p = pos({smax}), m2p = pos({(int64_t)sc.w});
+    const int64_t Fp = (mlen * (std::max(m1p, g1p) + std::max(m2p, g1p)) + (len - mlen) * 2 * g1p + len * 2 * dp) / g + 2;
+    const int64_t Fn = len * (c1n + c2n + 2 * dn) / g + 2;
+    const int64_t colabs = (c1p + c2p + c1n + c2n + 2 * dp + 2 * dn + 2 * std::llabs((long long)sc.beta)) / g + 64;  // one column + tie adjustments
+    (void)c1p; (void)c2p;
     int kb = 0;
     while ((1 << kb) < (S + 2) * (S + 2)) ++kb;
     pl.tb = trace ? kb + 5 : 0;
@@ -185,8 +191,8 @@ SysPlan plan_systolic(const ba_engine* e, int nmax, int mmax, bool trace) {
     pl.bneg = sc.beta < 0;
     // pad-free flavour: band-edge cases carry a poison of NEGP and values are floored at NEGP, so the most
     // negative intermediate is (floored source) + two poisons + constants  >=  3*negv - Fn
-    const int64_t negv_nopad = -(Fn + Fp + 64);
-    const bool nopad_ok = pl.bneg && (-3 * negv_nopad + Fn + 64 < lim);
+    const int64_t negv_nopad = -(Fn + Fp + colabs);
+    const bool nopad_ok = pl.bneg && (-3 * negv_nopad + 2 * colabs < lim);
     const bool pad_ok = (2 * Fn + Fp + 64 < lim);
     if (e->opt_pad == 0 && !nopad_ok) return pl;
     if (e->opt_pad == 1 && !pad_ok) return pl;
