@@ -96,6 +96,9 @@ __device__ __forceinline__ void open3(int i0, int i1, int i2, int beta, int& o0,
     }
 }
 
+#ifndef BA_SYS_MAXNREG
+#define BA_SYS_MAXNREG 168  // 3 CTAs of 128 threads per SM: 65536 / 384 = 170
+#endif
 constexpr int LA = 8;   // cp.async look-ahead (iterations) of the boundary staging
 constexpr int PRE = 4;  // iterations run before position 0: the virtual row above row 0 is 2 iterations ahead,
                         // so its first records must be staged before lane (0,0) reaches its first cell
@@ -131,7 +134,7 @@ struct Geo {
 // are published every 16 iterations with release semantics and polled with acquire loads; stream
 // reads are 16-byte cp.async.cg (L2 only), so no stale L1 line can be seen across SMs.
 template <int S, bool TRACE, bool PAD, bool BNEG, bool LONG>
-__global__ void __launch_bounds__(256) fill_systolic_kernel(SysArgs A) {
+__global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
     using G_ = Geo<S, PAD>;
     constexpr int W = G_::W, P = G_::P, LPR = G_::LPR, R = G_::R, RING = G_::RING, NV = G_::NV, NX = G_::NX, PB = G_::PB;
     constexpr int RSLOT = G_::RSLOT, REC = G_::REC, REAL = G_::REAL;
