@@ -24,7 +24,10 @@ __global__ void __launch_bounds__(128) traceback_kernel(TraceArgs A) {
     int len = 0, ok = 0;
     bool first = true;  // the reference's very first termination test never fires (pyx:551, tuple vs list)
     while (len < d.trace_cap) {
-        if (!first && (i | j | k | l) == 0 && state == 8) { ok = 1; break; }
+        if ((i | j | k | l) == 0) {  // at the origin no case passes the guard (pyx:133-141): the walk ends here
+            ok = (!first && state == 8) || A.fmt == 2;
+            break;
+        }
         first = false;
         const uint64_t wd = __ldg(codes + code_index(m, s, i, j, k - i, l - j));
         int id;

@@ -307,3 +307,50 @@ def test_long_pair_auto_mode_many_passes():
     r = oracle.run(a, b, sa, sb, params, mode="codes")
     assert int(scores[0]) == r["score"] and trace_hex(cols, offsets, 0) == r["trace"] and bool(complete[0])
     assert (al.align([a, b], [sa, sb], [(0, 1)], want_trace=False) == scores).all()
+
+
+@pytest.mark.parametrize("kernel", [0, 1, 2])
+def test_edge_cases_empty_and_tiny_sequences(kernel):
+    """Empty molecules (the batch API defines them by the recurrence; the reference class raises IndexError),
+    length-1 molecules, and very unequal lengths."""
+    params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150, gap_cost=-50,
+                  shift_cost=-150, max_shift=2)
+    seqs = ["", "A", "AC", "ACDEFGHIKLMNPQRSTVWY" * 4, "W", ""]
+    structs = ["", "H", "HE", "HHHHHEEEEECCCCCHHHHH" * 4, "C", ""]
+    pairs = [(0, 5), (0, 1), (1, 0), (1, 4), (1, 1), (2, 3), (3, 2), (3, 3), (0, 3), (3, 0)]
+    al = _aligner(params)
+    _select(al.engine, kernel)
+    try:
+        from bialign_b200.batch import trace_hex
+
+        scores, cols, offsets, complete = al.align(seqs, structs, pairs, want_trace=True)
+        for q, (ia, ib) in enumerate(pairs):
+            r = oracle.run(seqs[ia], seqs[ib], structs[ia], structs[ib], params, mode="codes")
+            assert int(scores[q]) == r["score"], (q, pairs[q])
+            assert trace_hex(cols, offsets, q) == r["trace"], (q, pairs[q])
+            assert bool(complete[q]) == r["complete"], (q, pairs[q])
+        assert (al.align(seqs, structs, pairs, want_trace=False) == scores).all()
+        empty = al.align(seqs, structs, [], want_trace=True)
+        assert len(empty[0]) == 0 and empty[2].tolist() == [0]
+    finally:
+        _unselect(al.engine)
+
+
+def test_error_codes_range_and_alphabet():
+    from bialign_b200 import _capi
+    from bialign_b200.batch import BatchAligner
+
+    big = BatchAligner(type="Protein", simmatrix="BLOSUM62", structure_weight=1 << 27, gap_opening_cost=-150, gap_cost=-50,
+                       shift_cost=-150, max_shift=1)
+    with pytest.raises(_capi.BialignError) as ei:
+        big.align(["ACD" * 20, "ACD" * 20], ["HHH" * 20, "HHH" * 20], [(0, 1)])
+    assert ei.value.code == _capi.BA_ERR_SCORE_RANGE
+    ok = BatchAligner(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150, gap_cost=-50,
+                      shift_cost=-150, max_shift=1)
+    res = np.array([0, 1, 200, 3], dtype=np.uint8)  # 200 >= nsym (24): the reference would raise KeyError (pyx:407)
+    with pytest.raises(_capi.BialignError) as ei:
+        ok.align_encoded(res, np.zeros(4, np.uint8), np.array([0, 2, 4], np.int64), np.array([0], np.int32), np.array([1], np.int32))
+    assert ei.value.code == _capi.BA_ERR_ALPHABET
+    with pytest.raises(_capi.BialignError) as ei:  # pair index outside the sequence table
+        ok.align_encoded(res[:2], np.zeros(2, np.uint8), np.array([0, 1, 2], np.int64), np.array([0], np.int32), np.array([7], np.int32))
+    assert ei.value.code == _capi.BA_ERR_INVALID_ARG
