@@ -227,7 +227,7 @@ def main():
         torch.cuda.synchronize()
 
     from bialign_b200 import _capi
-    from bialign_b200.batch import BatchAligner, lpt_shards, pair_cost
+    from bialign_b200.batch import BatchAligner, compact_shard, lpt_shards, pair_cost
 
     os.environ["BIALIGN_DEVICE"] = str(local_rank)
     al = BatchAligner(device=local_rank, **params)
@@ -235,9 +235,11 @@ def main():
         al.engine.set_option("warps_per_cta", args.warps)
     lens = np.diff(off)
     mine = lpt_shards(pair_cost(lens[pa], lens[pb], MAX_SHIFT), world)[rank]
-    my_pa, my_pb = pa[mine], pb[mine]
-    my_cs = int(cell_states_of(off, my_pa, my_pb, MAX_SHIFT).sum())
     total_cs = int(cell_states_of(off, pa, pb, MAX_SHIFT).sum())
+    # this rank's share of the sequence table and pair list (what it uploads every end-to-end step)
+    res, cls, off, my_pa, my_pb = compact_shard(res, cls, off, pa[mine], pb[mine])
+    lens = np.diff(off)
+    my_cs = int(cell_states_of(off, my_pa, my_pb, MAX_SHIFT).sum())
 
     eng = al.engine
     al.configure()
@@ -267,7 +269,8 @@ def main():
     h2d = res.nbytes + cls.nbytes + off.nbytes + my_pa.nbytes + my_pb.nbytes
     d2h = 0
     scores = np.empty(len(my_pa), dtype=np.int64)
-    eng.align_batch(res, cls, off, my_pa, my_pb, want_trace=True, scores_out=scores)  # warm
+    eng.align_batch(res, cls, off, my_pa, my_pb, want_trace=True, scores_out=scores)  # warm (first-use allocations)
+    eng.fetch_traces()
     barrier()
     t1 = time.perf_counter()
     for _ in range(args.steps):
@@ -342,7 +345,7 @@ def main():
            "gpu_launches": int(launches_all), "kernel_kind": st["kernel_kind"], "waves_per_step": st["waves"],
            "roofline": roofline}
     if n_gpus == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(res, cls, off, pa, pb, params)
+        out["cpu_baseline"] = cpu_baseline(res, cls, off, my_pa, my_pb, params)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

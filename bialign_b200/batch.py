@@ -125,12 +125,26 @@ class BatchAligner:
         lens = np.diff(off)
         costs = pair_cost(lens[np.asarray(pair_a)], lens[np.asarray(pair_b)], self.max_shift)
         mine = lpt_shards(costs, world_size)[rank]
-        out = self.align_encoded(res, cls, off, np.asarray(pair_a)[mine], np.asarray(pair_b)[mine], want_trace)
+        sres, scls, soff, spa, spb = compact_shard(res, cls, off, np.asarray(pair_a)[mine], np.asarray(pair_b)[mine])
+        out = self.align_encoded(sres, scls, soff, spa, spb, want_trace)
         return (mine, out)
 
 
 def trace_hex(cols, offsets, p):
     return "".join("%x" % c for c in cols[offsets[p]:offsets[p + 1]])
+
+
+def compact_shard(res, cls, off, pair_a, pair_b):
+    """Sequence table restricted to the sequences a shard's pairs use (so a rank uploads only its share).
+    Returns (res, cls, off, pair_a, pair_b) with re-numbered sequence indices."""
+    pair_a = np.asarray(pair_a, dtype=np.int64)
+    pair_b = np.asarray(pair_b, dtype=np.int64)
+    used, inv = np.unique(np.concatenate([pair_a, pair_b]), return_inverse=True)
+    lens = (off[used + 1] - off[used]).astype(np.int64)
+    new_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    idx = np.arange(int(new_off[-1])) - np.repeat(new_off[:-1], lens) + np.repeat(off[used], lens)
+    return (np.ascontiguousarray(res[idx]), np.ascontiguousarray(cls[idx]), new_off,
+            inv[:len(pair_a)].astype(np.int32), inv[len(pair_a):].astype(np.int32))
 
 
 def gather_scores(mine, scores, n_total, device=None):

@@ -170,3 +170,31 @@ def test_cfssp_reader_on_synthetic_report(tmp_path):
     f = tmp_path / "x.cfssp"
     f.write_text(txt)
     assert ba.read_molecule_from_file(str(f), "Protein") == ["MVQIPAK", "EEHHCCC"]
+
+
+def test_compact_shard_keeps_sequences():
+    from bialign_b200 import workloads
+    from bialign_b200.batch import compact_shard
+
+    res, cls, off, pa, pb = workloads.protein_pairs(50, lo=5, hi=20, seed=1)
+    mine = np.array([3, 7, 8, 20, 49])
+    r2, c2, o2, a2, b2 = compact_shard(res, cls, off, pa[mine], pb[mine])
+    assert len(r2) == len(c2) == o2[-1] < len(res)
+    for q, p in enumerate(mine):
+        assert (r2[o2[a2[q]]:o2[a2[q] + 1]] == res[off[pa[p]]:off[pa[p] + 1]]).all()
+        assert (c2[o2[b2[q]]:o2[b2[q] + 1]] == cls[off[pb[p]]:off[pb[p] + 1]]).all()
+
+
+def test_workload_generators_are_deterministic_and_well_formed():
+    from bialign_b200 import encoding, workloads
+
+    r1 = workloads.protein_pairs(20, seed=3)
+    r2 = workloads.protein_pairs(20, seed=3)
+    assert all((x == y).all() for x, y in zip(r1, r2))
+    lens = np.diff(r1[2])
+    assert lens.min() >= 200 and lens.max() <= 500 and set(bytes(r1[1]).decode()) <= set("HEC")
+    res, cls, off, pa, pb = workloads.rna_pairs(8, seed=4)
+    for q in range(16):
+        seq, st = workloads.decode_rna(res, cls, off, q)
+        assert len(seq) == 120 and st.count("(") == st.count(")")
+        assert (encoding.rna_structure_classes(st) == cls[off[q]:off[q + 1]]).all()
