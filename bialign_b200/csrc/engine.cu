@@ -223,7 +223,7 @@ SysPlan plan_systolic(const ba_engine* e, int nmax, int mmax, bool trace) {
                     const int T0 = (c - S) + hb0(s01) - hb0(s23), T1 = (bb - S) + hb1(s01) - hb1(s23);
                     const int k1 = std::abs(T1), k0 = std::abs(T0) + k1;
                     const int rank = (int)(std::lower_bound(keys.begin(), keys.end(), std::make_pair(k0, k1)) - keys.begin());
-                    pl.tbtab[((size_t)bb * LPR + c) * 12 + src] = ((NK - 1 - rank) << 5) | (27 - src);
+                    pl.tbtab[(size_t)src * P * LPR + (size_t)bb * LPR + c] = ((NK - 1 - rank) << 5) | (27 - src);
                 }
     }
     pl.ok = true;

@@ -122,7 +122,7 @@ struct Geo {
 //   ring   [(G+1)][RING][NV][32]      ring[0] = staging ring of the virtual warp above warp 0
 //   xs     [(G+1)][4][NX][LPR]        short-delay values of the row above each warp; xs[G] = CTA output
 //   pb     [PB][REC]                  cp.async landing zone for the incoming boundary stream
-//   tb     [P][LPR][12]               tie-break constants per (b, lane column, source state)  (TRACE)
+//   tb     [9][P][LPR] (+pad)         tie-break constants per (source state, b, lane column)  (TRACE)
 //   sim    [(nsym+1)][nsym]           similarity table (<< TB), last row zero
 //   resB/clsB  bytes, padded
 //
@@ -468,12 +468,12 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                                         ((M[4] & 31) << 20) | ((M[5] & 31) << 25);
                     const unsigned hi = (M[6] & 31) | ((M[7] & 31) << 5) | ((M[8] & 31) << 10);
                     if (valid) *reinterpret_cast<uint2*>(code_ptr + (long long)j * W + bb) = make_uint2(lo, hi);
-                    const int4* tp = reinterpret_cast<const int4*>(tbtab + (bb * LPR + c) * 12);
-                    const int4 ta = tp[0], tbv = tp[1], tc = tp[2];
+                    // table layout [source state][b][lane column]: for one source state the lanes of a warp read
+                    // (at most P*LPR <= 32) consecutive words -> no bank conflicts
+                    const int* tp = tbtab + bb * LPR + c;
                     const int msk = ~((1 << TB) - 1);
-                    M[0] = (M[0] & msk) | ta.x; M[1] = (M[1] & msk) | ta.y; M[2] = (M[2] & msk) | ta.z;
-                    M[3] = (M[3] & msk) | ta.w; M[4] = (M[4] & msk) | tbv.x; M[5] = (M[5] & msk) | tbv.y;
-                    M[6] = (M[6] & msk) | tbv.z; M[7] = (M[7] & msk) | tbv.w; M[8] = (M[8] & msk) | tc.x;
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) M[t] = (M[t] & msk) | tp[t * (P * LPR)];
                 }
 
                 // ---- publish: R (second alignment decided), L (first decided), Q (both)
