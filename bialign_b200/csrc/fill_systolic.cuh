@@ -139,6 +139,7 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
     constexpr int W = G_::W, P = G_::P, LPR = G_::LPR, R = G_::R, RING = G_::RING, NV = G_::NV, NX = G_::NX, PB = G_::PB;
     constexpr int RSLOT = G_::RSLOT, REC = G_::REC, REAL = G_::REAL;
     constexpr bool RP2 = (RING & (RING - 1)) == 0;  // power-of-two ring: slots are masks of the iteration counter
+    constexpr bool PF = (P - 1) >= 2;               // ring inputs can be fetched one iteration ahead
     extern __shared__ __align__(16) int smem[];
     const int G = blockDim.x >> 5;
     const int RT = G * R;  // rows per pass
@@ -289,6 +290,7 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                 for (int y = 0; y < 3; ++y) hR[x][y] = NEGP;
             int h2Q1010 = NEGP, h2Q1001 = NEGP, h2Q1011 = NEGP, h3Q1011 = NEGP;
             int h2R11[3] = {NEGP, NEGP, NEGP};
+            int pfF[6] = {NEGP, NEGP, NEGP, NEGP, NEGP, NEGP}, pfH[6] = {NEGP, NEGP, NEGP, NEGP, NEGP, NEGP};
 
             if (LONG && has_in) {  // wait for the first records of the producer pass, then prime with 16-byte copies
                 if (tid == 0) {
@@ -355,28 +357,36 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                 }
 
                 // ---- gather the 27 inputs
-                int rsA, rsB, rsC, rsD;  // ring slots written P+2, P+1, P, P-1 iterations ago
-                if (RP2) {
-                    rsA = (q - (P + 2)) & (RING - 1); rsB = (q - (P + 1)) & (RING - 1);
-                    rsC = (q - P) & (RING - 1);       rsD = (q - (P - 1)) & (RING - 1);
-                } else {
-                    rsA = wslot - (P + 2); if (rsA < 0) rsA += RING;
-                    rsB = wslot - (P + 1); if (rsB < 0) rsB += RING;
-                    rsC = wslot - P;       if (rsC < 0) rsC += RING;
-                    rsD = wslot - (P - 1); if (rsD < 0) rsD += RING;
-                }
                 int inF[9], inH2[9], inH1[9];
-                // long-delay values from the rings (ids: 0..2 Q[11][01,10,11], 3..5 Q[01][..], 6..8 L[11][..], 9..11 L[01][..])
-                inF[8] = ring[baseU0 + rsA * RSLOT + 2 * 32];  // x=1111 Q[11][11]
-                inF[7] = ring[baseU0 + rsB * RSLOT + 1 * 32];  // x=1110 Q[11][10]
-                inF[6] = ring[baseU1 + rsB * RSLOT + 0 * 32];  // x=1101 Q[11][01]
-                inF[2] = ring[baseW + rsB * RSLOT + 5 * 32];   // x=0111 Q[01][11]
-                inF[1] = ring[baseW + rsC * RSLOT + 4 * 32];   // x=0110 Q[01][10]
-                inF[0] = ring[baseS + rsC * RSLOT + 3 * 32];   // x=0101 Q[01][01]
+                // long-delay values from the rings (ids: 0..2 Q[11][01,10,11], 3..5 Q[01][..], 6..8 L[11][..], 9..11 L[01][..]).
+                // They are at least P-1 iterations old, so (when P-1 >= 2) they were fetched during the previous
+                // iteration: the loads overlap that iteration's tail and the barrier instead of stalling this one.
+                if (PF) {
 #pragma unroll
-                for (int y = 0; y < 3; ++y) {
-                    inH1[6 + y] = ring[baseU1 + rsC * RSLOT + (6 + y) * 32];  // x=1100 L[11][y]
-                    inH1[y] = ring[baseS + rsD * RSLOT + (9 + y) * 32];       // x=0100 L[01][y]
+                    for (int y = 0; y < 3; ++y) { inH1[6 + y] = pfH[y]; inH1[y] = pfH[3 + y]; }
+                    inF[8] = pfF[0]; inF[7] = pfF[1]; inF[6] = pfF[2]; inF[2] = pfF[3]; inF[1] = pfF[4]; inF[0] = pfF[5];
+                } else {
+                    int rsA, rsB, rsC, rsD;  // ring slots written P+2, P+1, P, P-1 iterations ago
+                    if (RP2) {
+                        rsA = (q - (P + 2)) & (RING - 1); rsB = (q - (P + 1)) & (RING - 1);
+                        rsC = (q - P) & (RING - 1);       rsD = (q - (P - 1)) & (RING - 1);
+                    } else {
+                        rsA = wslot - (P + 2); if (rsA < 0) rsA += RING;
+                        rsB = wslot - (P + 1); if (rsB < 0) rsB += RING;
+                        rsC = wslot - P;       if (rsC < 0) rsC += RING;
+                        rsD = wslot - (P - 1); if (rsD < 0) rsD += RING;
+                    }
+                    inF[8] = ring[baseU0 + rsA * RSLOT + 2 * 32];  // x=1111 Q[11][11]
+                    inF[7] = ring[baseU0 + rsB * RSLOT + 1 * 32];  // x=1110 Q[11][10]
+                    inF[6] = ring[baseU1 + rsB * RSLOT + 0 * 32];  // x=1101 Q[11][01]
+                    inF[2] = ring[baseW + rsB * RSLOT + 5 * 32];   // x=0111 Q[01][11]
+                    inF[1] = ring[baseW + rsC * RSLOT + 4 * 32];   // x=0110 Q[01][10]
+                    inF[0] = ring[baseS + rsC * RSLOT + 3 * 32];   // x=0101 Q[01][01]
+#pragma unroll
+                    for (int y = 0; y < 3; ++y) {
+                        inH1[6 + y] = ring[baseU1 + rsC * RSLOT + (6 + y) * 32];  // x=1100 L[11][y]
+                        inH1[y] = ring[baseS + rsD * RSLOT + (9 + y) * 32];       // x=0100 L[01][y]
+                    }
                 }
                 // short-delay values by shuffle
                 inF[5] = __shfl_up_sync(0xffffffffu, h3Q1011, LPR);      // x=1011 D=3
@@ -485,6 +495,32 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                 }
 #pragma unroll
                 for (int y = 0; y < 3; ++y) open3<BNEG>(Rv[0][y], Rv[1][y], Rv[2][y], beta, Qv[0][y], Qv[1][y], Qv[2][y]);
+
+                // prefetch the ring inputs of the next iteration (slots written >= 2 iterations before it)
+                if (PF) {
+                    int rsA, rsB, rsC, rsD;
+                    if (RP2) {
+                        rsA = (q + 1 - (P + 2)) & (RING - 1); rsB = (q + 1 - (P + 1)) & (RING - 1);
+                        rsC = (q + 1 - P) & (RING - 1);       rsD = (q + 1 - (P - 1)) & (RING - 1);
+                    } else {
+                        const int ns = (wslot + 1 == RING) ? 0 : wslot + 1;
+                        rsA = ns - (P + 2); if (rsA < 0) rsA += RING;
+                        rsB = ns - (P + 1); if (rsB < 0) rsB += RING;
+                        rsC = ns - P;       if (rsC < 0) rsC += RING;
+                        rsD = ns - (P - 1); if (rsD < 0) rsD += RING;
+                    }
+                    pfF[0] = ring[baseU0 + rsA * RSLOT + 2 * 32];  // x=1111 Q[11][11]
+                    pfF[1] = ring[baseU0 + rsB * RSLOT + 1 * 32];  // x=1110 Q[11][10]
+                    pfF[2] = ring[baseU1 + rsB * RSLOT + 0 * 32];  // x=1101 Q[11][01]
+                    pfF[3] = ring[baseW + rsB * RSLOT + 5 * 32];   // x=0111 Q[01][11]
+                    pfF[4] = ring[baseW + rsC * RSLOT + 4 * 32];   // x=0110 Q[01][10]
+                    pfF[5] = ring[baseS + rsC * RSLOT + 3 * 32];   // x=0101 Q[01][01]
+#pragma unroll
+                    for (int y = 0; y < 3; ++y) {
+                        pfH[y] = ring[baseU1 + rsC * RSLOT + (6 + y) * 32];     // x=1100 L[11][y]
+                        pfH[3 + y] = ring[baseS + rsD * RSLOT + (9 + y) * 32];  // x=0100 L[01][y]
+                    }
+                }
 
                 // ring: long-delay values
                 int* wr = ring + own_ring + wslot * RSLOT + lane;
