@@ -20,7 +20,7 @@ class BaStats(ctypes.Structure):
     _fields_ = [("pairs", ctypes.c_int64), ("cell_states", ctypes.c_int64), ("kernel_launches", ctypes.c_int64),
                 ("waves", ctypes.c_int64), ("fill_ms", ctypes.c_double), ("traceback_ms", ctypes.c_double),
                 ("total_ms", ctypes.c_double), ("code_bytes", ctypes.c_int64), ("kernel_kind", ctypes.c_int32),
-                ("device", ctypes.c_int32)]
+                ("device", ctypes.c_int32), ("warps_per_cta", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class BialignError(RuntimeError):

@@ -98,7 +98,7 @@ struct ba_engine {
     DevBuf<unsigned long long> d_progress;
     int opt_long = -1;                 // multi-CTA long-pair mode: -1 auto, 0 off, 1 force
     std::vector<int32_t> h_sim;
-    int opt_warps = 4;                 // warps per CTA of the systolic kernel
+    int opt_warps = 0;                 // warps per CTA of the systolic kernel (0 = chosen per batch)
     int opt_pad = -1;                  // systolic flavour: -1 auto, 0 pad-free, 1 padded
     int last_fmt = 0;
     DevBuf<long long> d_scores;
@@ -286,7 +286,7 @@ int ba_set_option(ba_engine* e, const char* key, int64_t value) {
     else if (!strcmp(key, "pad")) e->opt_pad = (int)value;
     else if (!strcmp(key, "long")) e->opt_long = (int)value;
     else if (!strcmp(key, "warps_per_cta")) {
-        if (value < 1 || value > 8) return fail(e, BA_ERR_INVALID_ARG, "warps_per_cta must be in 1..8");
+        if (value < 0 || value > 8) return fail(e, BA_ERR_INVALID_ARG, "warps_per_cta must be in 0..8 (0 = auto)");
         e->opt_warps = (int)value;
     }
     else return fail(e, BA_ERR_INVALID_ARG, std::string("unknown option ") + key);
@@ -510,6 +510,31 @@ int ba_run(ba_engine* e, int want_trace) {
     bool long_mode = false;
     int long_grid_max = 0;
     if (kernel == 1) {
+        if (sysG == 0) {
+            // Pick the CTA width that minimises the estimated warp-iterations per resident warp:
+            // a pair costs passes(G) * iterations(G) on G warps; an SM runs occ(G) CTAs, and more than ~12
+            // resident warps do not add throughput (the ALU pipe is saturated).  Short pairs want a CTA that
+            // covers all rows in one pass; long ones want few warps per CTA and several CTAs per SM.
+            const SysGeo geo = sys_geo(s, plan.pad);
+            double best = 0;
+            for (int G = 2; G <= 8; ++G) {
+                const size_t sm = sys_smem_bytes(s, plan.pad, G, e->sc.nsym, mmax);
+                if (sm > 220 * 1024) continue;
+                const int occ = sys_occupancy(s, want_trace != 0, plan.pad, plan.bneg, G, sm);
+                if (occ < 1) continue;
+                const double eff = std::min(occ * G, 12);
+                double cost = 0;
+                const int64_t stride = std::max<int64_t>(1, N / 4096);  // sample large batches
+                for (int64_t p = 0; p < N; p += stride) {
+                    const int rows = G * geo.R;
+                    const double passes = (ln[p] + rows) / rows;
+                    cost += passes * (double)sys_iters(s, plan.pad, G, lm[p]) * G;
+                }
+                cost /= eff;
+                if (sysG == 0 || cost < best * 0.97) { best = cost; sysG = G; }  // prefer the narrower CTA on near-ties
+            }
+            if (sysG == 0) sysG = 2;
+        }
         // the LONG flavour stages one 16-byte vector per thread: a record (<= 180 ints) needs >= 45 threads
         if (e->opt_long == 1 && sysG < 2) sysG = 2;
         while (sysG > 1 && sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax) > 200 * 1024) --sysG;
@@ -639,6 +664,7 @@ int ba_run(ba_engine* e, int want_trace) {
     }
     e->stats.waves = n_waves;
     e->stats.kernel_kind = kernel == 0 ? 0 : (plan.pad ? 2 : 1) + (long_mode ? 2 : 0);
+    e->stats.warps_per_cta = kernel == 0 ? 0 : sysG;
     e->last_fmt = kernel;
     e->ran = true;
     e->ran_trace = want_trace != 0;

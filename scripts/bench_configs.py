@@ -31,7 +31,7 @@ def run(name, al, res, cls, off, pa, pb, want_trace, reps=3):
     out = dict(config=name, pairs=int(len(pa)), want_trace=want_trace, cell_states=best["cell_states"],
                fill_ms=best["fill_ms"], traceback_ms=best["traceback_ms"], total_ms=best["total_ms"], wall_ms=best["wall_ms"],
                gcups_fill=best["cell_states"] / best["fill_ms"] / 1e6, gcups_total=best["cell_states"] / best["wall_ms"] / 1e6,
-               kernel_kind=best["kernel_kind"], waves=best["waves"], code_GB=best["code_bytes"] / 1e9)
+               kernel_kind=best["kernel_kind"], warps=best["warps_per_cta"], waves=best["waves"], code_GB=best["code_bytes"] / 1e9)
     print(json.dumps(out), flush=True)
     return out
 

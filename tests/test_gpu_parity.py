@@ -146,7 +146,7 @@ def _select(engine, kind):
 def _unselect(engine):
     engine.set_option("kernel", -1)
     engine.set_option("pad", -1)
-    engine.set_option("warps_per_cta", 4)
+    engine.set_option("warps_per_cta", 0)
     engine.set_option("long", -1)
 
 
