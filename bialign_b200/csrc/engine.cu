@@ -97,6 +97,7 @@ struct ba_engine {
     DevBuf<int> d_simp, d_tbtab, d_bnd;
     DevBuf<unsigned long long> d_progress;
     int opt_long = -1;                 // multi-CTA long-pair mode: -1 auto, 0 off, 1 force
+    int opt_p16 = -1;                  // 16-bit pair mode for score-only batches: -1 auto, 0 off, 1 force
     std::vector<int32_t> h_sim;
     int opt_warps = 0;                 // warps per CTA of the systolic kernel (0 = chosen per batch)
     int opt_pad = -1;                  // systolic flavour: -1 auto, 0 pad-free, 1 padded
@@ -161,8 +162,9 @@ int64_t gcd64(int64_t a, int64_t b) {
 // Exactness conditions of the packed 32-bit domain (DESIGN.md "tie-break packing"): every finite value
 // lies in [-Fn, Fp], "minus infinity" values in [negp - Fn, negp + Fp]; the two ranges must not meet
 // and nothing may leave the (32 - tb)-bit field.
-SysPlan plan_systolic(const ba_engine* e, int nmax, int mmax, bool trace) {
+SysPlan plan_systolic(const ba_engine* e, int nmax, int mmax, bool trace, bool bits16 = false) {
     SysPlan pl;
+    if (bits16 && trace) return pl;
     const Scoring& sc = e->sc;
     const int S = sc.s, nsym = sc.nsym;
     if (nsym > 64) return pl;
@@ -186,7 +188,7 @@ SysPlan plan_systolic(const ba_engine* e, int nmax, int mmax, bool trace) {
     int kb = 0;
     while ((1 << kb) < (S + 2) * (S + 2)) ++kb;
     pl.tb = trace ? kb + 5 : 0;
-    const int vb = 32 - pl.tb;
+    const int vb = (bits16 ? 16 : 32) - pl.tb;
     const int64_t lim = (int64_t)1 << (vb - 1);
     pl.bneg = sc.beta < 0;
     // pad-free flavour: band-edge cases carry a poison of NEGP and values are floored at NEGP, so the most
@@ -194,9 +196,12 @@ SysPlan plan_systolic(const ba_engine* e, int nmax, int mmax, bool trace) {
     const int64_t negv_nopad = -(Fn + Fp + colabs);
     const bool nopad_ok = pl.bneg && (-3 * negv_nopad + 2 * colabs < lim);
     const bool pad_ok = (2 * Fn + Fp + 64 < lim);
+    if (bits16) {  // 16-bit pair mode exists for the pad-free flavour only, and the table entries must fit too
+        if (!nopad_ok || (smax - smin) / g >= lim / 2) return pl;
+    }
     if (e->opt_pad == 0 && !nopad_ok) return pl;
     if (e->opt_pad == 1 && !pad_ok) return pl;
-    pl.pad = (e->opt_pad == 1) || (e->opt_pad < 0 && !nopad_ok);
+    pl.pad = !bits16 && ((e->opt_pad == 1) || (e->opt_pad < 0 && !nopad_ok));
     if (pl.pad && !pad_ok) return pl;
     int64_t negv = negv_nopad;
     if (pl.pad) {
@@ -285,6 +290,7 @@ int ba_set_option(ba_engine* e, const char* key, int64_t value) {
     else if (!strcmp(key, "kernel")) e->opt_kernel = (int)value;
     else if (!strcmp(key, "pad")) e->opt_pad = (int)value;
     else if (!strcmp(key, "long")) e->opt_long = (int)value;
+    else if (!strcmp(key, "p16")) e->opt_p16 = (int)value;
     else if (!strcmp(key, "warps_per_cta")) {
         if (value < 0 || value > 8) return fail(e, BA_ERR_INVALID_ARG, "warps_per_cta must be in 0..8 (0 = auto)");
         e->opt_warps = (int)value;
@@ -499,7 +505,14 @@ int ba_run(ba_engine* e, int want_trace) {
     for (int w = 0; w < n_waves; ++w) biggest_wave = std::max(biggest_wave, wave_begin[w + 1] - wave_begin[w]);
     // ---- kernel choice: systolic when its exactness conditions hold, else the generic level kernel
     SysPlan plan;
-    if (e->opt_kernel != 0 && affine) plan = plan_systolic(e, nmax, mmax, want_trace != 0);
+    bool p16 = false;
+    if (e->opt_kernel != 0 && affine && !want_trace && e->opt_p16 != 0 && e->opt_pad != 1 && N >= 2) {
+        plan = plan_systolic(e, nmax, mmax, false, true);  // do the scores provably fit 16 bits?
+        p16 = plan.ok;
+    }
+    if (e->opt_p16 == 1 && !p16 && !want_trace && affine && N >= 2)
+        return fail(e, BA_ERR_SCORE_RANGE, "16-bit pair mode requested but the score range does not fit");
+    if (!p16 && e->opt_kernel != 0 && affine) plan = plan_systolic(e, nmax, mmax, want_trace != 0);
     if (e->opt_kernel == 1 && affine && !plan.ok)
         return fail(e, BA_ERR_SCORE_RANGE, "systolic kernel requested but its packed-integer range conditions do not hold");
     const int kernel = plan.ok ? 1 : 0;
@@ -518,9 +531,9 @@ int ba_run(ba_engine* e, int want_trace) {
             const SysGeo geo = sys_geo(s, plan.pad);
             double best = 0;
             for (int G = 2; G <= 8; ++G) {
-                const size_t sm = sys_smem_bytes(s, plan.pad, G, e->sc.nsym, mmax);
+                const size_t sm = sys_smem_bytes(s, plan.pad, G, e->sc.nsym, mmax, p16);
                 if (sm > 220 * 1024) continue;
-                const int occ = sys_occupancy(s, want_trace != 0, plan.pad, plan.bneg, G, sm);
+                const int occ = p16 ? sys_occupancy_p16(s, G, sm) : sys_occupancy(s, want_trace != 0, plan.pad, plan.bneg, G, sm);
                 if (occ < 1) continue;
                 const double eff = std::min(occ * G, 12);
                 double cost = 0;
@@ -537,9 +550,9 @@ int ba_run(ba_engine* e, int want_trace) {
         }
         // the LONG flavour stages one 16-byte vector per thread: a record (<= 180 ints) needs >= 45 threads
         if (e->opt_long == 1 && sysG < 2) sysG = 2;
-        while (sysG > 1 && sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax) > 200 * 1024) --sysG;
-        sys_smem = sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax);
-        const int occ = sys_occupancy(s, want_trace != 0, plan.pad, plan.bneg, sysG, sys_smem);
+        while (sysG > 1 && sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax, p16) > 200 * 1024) --sysG;
+        sys_smem = sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax, p16);
+        const int occ = p16 ? sys_occupancy_p16(s, sysG, sys_smem) : sys_occupancy(s, want_trace != 0, plan.pad, plan.bneg, sysG, sys_smem);
         if (occ < 1) return fail(e, BA_ERR_CUDA, "systolic kernel does not fit on an SM (shared memory " + std::to_string(sys_smem) + ")");
         max_grid = e->sm_count * occ;
         const int grid = (int)std::min<int64_t>(biggest_wave, max_grid);
@@ -554,7 +567,7 @@ int ba_run(ba_engine* e, int want_trace) {
         }
         // Few, long pairs: spread the row blocks of each pair over the whole grid (LONG flavour, cooperative launch)
         const int npass_max = (nmax + rows_pass) / rows_pass;
-        if (plan.bneg && e->opt_long != 0 && npass_max >= 2 && sysG >= 2 &&
+        if (!p16 && plan.bneg && e->opt_long != 0 && npass_max >= 2 && sysG >= 2 &&
             (e->opt_long == 1 || (N <= 4 && npass_max >= 8))) {
             const int occl = sys_occupancy_long(s, want_trace != 0, plan.pad, sysG, sys_smem);
             int coop = 0;
@@ -593,7 +606,13 @@ int ba_run(ba_engine* e, int want_trace) {
         if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "fill scratch: " + std::string(cudaGetErrorString(ce)));
     }
     lap("kernel plan + scratch");
-    CU(cudaMemcpyAsync(e->d_desc.p, e->h_desc.data(), sizeof(PairDesc) * N, cudaMemcpyHostToDevice, e->stream));
+    if (p16 && (N & 1)) {  // odd batch: the last work item computes its only pair in both halves
+        PairDesc extra = e->h_desc[N - 1];
+        extra.orig = -1;
+        e->h_desc.push_back(extra);
+        CU(e->d_desc.ensure((size_t)N + 1));
+    }
+    CU(cudaMemcpyAsync(e->d_desc.p, e->h_desc.data(), sizeof(PairDesc) * e->h_desc.size(), cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemsetAsync(e->d_counter.p, 0, sizeof(int) * n_waves, e->stream));
 
     std::vector<cudaEvent_t> ev((size_t)n_waves * 3 + 1);
@@ -618,6 +637,9 @@ int ba_run(ba_engine* e, int want_trace) {
                 CU(launch_fill_systolic_long(SA, lg, sysG, sys_smem, want_trace != 0, plan.pad, e->stream));
                 if (q + 1 < cnt) e->stats.kernel_launches++;
             }
+        } else if (kernel == 1 && p16) {  // two pairs per work item (score only: a single wave)
+            SA.pairs = e->d_desc.p; SA.npairs = (int)((N + 1) / 2); SA.counter = e->d_counter.p + w;
+            CU(launch_fill_systolic_p16(SA, (int)std::min<int64_t>((N + 1) / 2, max_grid), sysG, sys_smem, e->stream));
         } else if (kernel == 1) {
             SA.pairs = e->d_desc.p + b; SA.npairs = (int)cnt; SA.counter = e->d_counter.p + w;
             CU(launch_fill_systolic(SA, grid, sysG, sys_smem, want_trace != 0, plan.pad, plan.bneg, e->stream));
@@ -663,7 +685,7 @@ int ba_run(ba_engine* e, int want_trace) {
         e->stats.code_bytes = cb;
     }
     e->stats.waves = n_waves;
-    e->stats.kernel_kind = kernel == 0 ? 0 : (plan.pad ? 2 : 1) + (long_mode ? 2 : 0);
+    e->stats.kernel_kind = kernel == 0 ? 0 : (p16 ? 5 : (plan.pad ? 2 : 1) + (long_mode ? 2 : 0));
     e->stats.warps_per_cta = kernel == 0 ? 0 : sysG;
     e->last_fmt = kernel;
     e->ran = true;

@@ -49,6 +49,22 @@ __device__ __forceinline__ int vmax(int a, int b) { return max(a, b); }
 __device__ __forceinline__ int vmax3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 __device__ __forceinline__ int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); }  // max(a+b, c)
 
+// 16-bit pair mode (P16): every int holds two independent signed 16-bit values, one per pair of a two-pair work
+// item; the DPX SIMD forms do per-halfword add/max in one instruction.  Plain integer adds are not allowed on
+// packed values (carries would cross the halves), hence vadd2 = max(a + b, -32768) per half.
+__device__ __forceinline__ int pack2(int x) { return (x & 0xffff) | (x << 16); }
+__device__ __forceinline__ int vadd2(int a, int b) { return (int)__viaddmax_s16x2((unsigned)a, (unsigned)b, 0x80008000u); }
+template <bool P16>
+__device__ __forceinline__ int xadd(int a, int b) { return P16 ? vadd2(a, b) : a + b; }
+template <bool P16>
+__device__ __forceinline__ int xaddmax(int a, int b, int c) {
+    return P16 ? (int)__viaddmax_s16x2((unsigned)a, (unsigned)b, (unsigned)c) : __viaddmax_s32(a, b, c);
+}
+template <bool P16>
+__device__ __forceinline__ int xmax3(int a, int b, int c) {
+    return P16 ? (int)__vimax3_s16x2((unsigned)a, (unsigned)b, (unsigned)c) : __vimax3_s32(a, b, c);
+}
+
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ int lds32(unsigned addr) {
     int v;
@@ -84,12 +100,12 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //   x = 11 (match half): best of all three sources (mu is added at the target)
 //   x = gap half g     : max(in[g], beta + max(other two))                       (pyx:108-115)
 // With beta < 0 the own source may join the inner max (beta + in[g] < in[g] never wins).
-template <bool BNEG>
+template <bool BNEG, bool P16 = false>
 __device__ __forceinline__ void open3(int i0, int i1, int i2, int beta, int& o0, int& o1, int& o2) {
-    o2 = vmax3(i0, i1, i2);
+    o2 = xmax3<P16>(i0, i1, i2);
     if (BNEG) {
-        o0 = addmax(o2, beta, i0);
-        o1 = addmax(o2, beta, i1);
+        o0 = xaddmax<P16>(o2, beta, i0);
+        o1 = xaddmax<P16>(o2, beta, i1);
     } else {
         o0 = addmax(vmax(i1, i2), beta, i0);
         o1 = addmax(vmax(i0, i2), beta, i1);
@@ -133,8 +149,12 @@ struct Geo {
 // every later pass transitively depends on it).  Progress flags (pass id << 32 | records complete)
 // are published every 16 iterations with release semantics and polled with acquire loads; stream
 // reads are 16-byte cp.async.cg (L2 only), so no stale L1 line can be seen across SMs.
-template <int S, bool TRACE, bool PAD, bool BNEG, bool LONG>
+//
+// P16 = two pairs per work item in packed 16-bit halves (score only, pad-free, beta < 0): twice the pairs per
+// instruction for batches whose scores provably fit 16 bits (short RNA-like pairs, BASELINE config 4).
+template <int S, bool TRACE, bool PAD, bool BNEG, bool LONG, bool P16 = false>
 __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
+    static_assert(!P16 || (!TRACE && !PAD && BNEG && !LONG), "16-bit pair mode: score only, pad-free, beta < 0, batch mode");
     using G_ = Geo<S, PAD>;
     constexpr int W = G_::W, P = G_::P, LPR = G_::LPR, R = G_::R, RING = G_::RING, NV = G_::NV, NX = G_::NX, PB = G_::PB;
     constexpr int RSLOT = G_::RSLOT, REC = G_::REC, REAL = G_::REAL;
@@ -152,6 +172,8 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
     uint8_t* sresB = reinterpret_cast<uint8_t*>(ssim + (nsym + 1) * nsym);
     const int bpad = A.bpad, boff = A.boff;
     uint8_t* sclsB = sresB + bpad;
+    uint8_t* sresB_hi = sclsB + bpad;   // P16 only: molecule B of the second pair
+    uint8_t* sclsB_hi = sresB_hi + bpad;
     __shared__ int s_pair;
 
     const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
@@ -161,8 +183,9 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
     const int sigma = 2 * (g * R + r) + c;
     const bool row0 = (r == 0);
     const int TB = TRACE ? A.tb_bits : 0;
-    const int NEGP = A.negp;
-    const int beta = A.beta_p, kGD = A.k_gd, k2G = A.k_2g, k2G2D = A.k_2g2d, k2D = A.k_2d;
+    const int NEGP = P16 ? pack2(A.negp) : A.negp;
+    const int beta = P16 ? pack2(A.beta_p) : A.beta_p, kGD = P16 ? pack2(A.k_gd) : A.k_gd, k2G = P16 ? pack2(A.k_2g) : A.k_2g;
+    const int k2G2D = P16 ? pack2(A.k_2g2d) : A.k_2g2d, k2D = P16 ? pack2(A.k_2d) : A.k_2d;
     // band-edge poisons of the pad-free flavour (lane constants): sources at a+1 (x0=1,x2=0) do not exist for
     // the last column, sources at a-1 (x0=0,x2=1) do not exist for the first one
     const int pU1 = (!PAD && c == W - 1) ? NEGP : 0;
@@ -201,15 +224,28 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
             __syncthreads();
             if (pi >= A.npairs) return;
         }
-        const PairDesc d = A.pairs[pi];
-        const int n = d.n, m = d.m;
+        PairDesc d, dh;  // dh: second pair of a P16 work item (dh.orig < 0: none, the first pair is computed twice)
+        if (P16) {
+            d = A.pairs[2 * pi];
+            dh = A.pairs[2 * pi + 1];
+        } else {
+            d = A.pairs[pi];
+            dh = d;
+        }
+        const int n = P16 ? max(d.n, dh.n) : d.n, m = P16 ? max(d.m, dh.m) : d.m;
         const uint8_t* ra = A.res + d.offA;
         const uint8_t* ca = A.cls + d.offA;
+        const uint8_t* ra_hi = A.res + dh.offA;
+        const uint8_t* ca_hi = A.cls + dh.offA;
         // stage molecule B (bytes); 1-based position l -> sclsB[l + boff]; 255 (B) / 254 (A) never match
         for (int q = tid; q < bpad; q += blockDim.x) {
             const int l = q - boff;
-            sresB[q] = (l >= 1 && l <= m) ? A.res[d.offB + l - 1] : 0;
-            sclsB[q] = (l >= 1 && l <= m) ? A.cls[d.offB + l - 1] : 255;
+            sresB[q] = (l >= 1 && l <= d.m) ? A.res[d.offB + l - 1] : 0;
+            sclsB[q] = (l >= 1 && l <= d.m) ? A.cls[d.offB + l - 1] : 255;
+            if (P16) {
+                sresB_hi[q] = (l >= 1 && l <= dh.m) ? A.res[dh.offB + l - 1] : 0;
+                sclsB_hi[q] = (l >= 1 && l <= dh.m) ? A.cls[dh.offB + l - 1] : 255;
+            }
         }
         __syncthreads();
 
@@ -222,10 +258,14 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
         for (int pass = LONG ? (int)blockIdx.x : 0; pass < npass; pass += LONG ? NC : 1) {
             const int i = pass * RT + g * R + r;
             const int k = i + a;
-            const bool lane_ok = lane_real && i <= n && k >= 0 && k <= n;
+            const bool lane_ok = lane_real && i <= d.n && k >= 0 && k <= d.n;
             const int Ai = (lane_ok && i >= 1) ? ra[i - 1] : nsym;  // zero row for i = 0
             const int Ak = (lane_ok && k >= 1) ? ca[k - 1] : 254;
             const int* simrow = ssim + Ai * nsym;
+            const bool lane_ok_hi = P16 && lane_real && i <= dh.n && k >= 0 && k <= dh.n;
+            const int Ak_hi = (lane_ok_hi && k >= 1) ? ca_hi[k - 1] : 254;
+            const int* simrow_hi = ssim + ((lane_ok_hi && i >= 1) ? ra_hi[i - 1] : nsym) * nsym;
+            const int wlo = A.w_p & 0xffff, whi = A.w_p << 16;
             const bool has_in = pass > 0, has_out = pass + 1 < npass;
             const int buf_in = LONG ? ((pass - 1 + 2 * NC) % NC) + NC * ((((pass - 1 + 2 * NC) / NC) & 1)) : ((pass + 1) & 1);
             const int buf_out = LONG ? (pass % NC) + NC * (((pass + 2 * NC) / NC) & 1) : (pass & 1);
@@ -270,7 +310,12 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
             const int q_rec_lim = nit - 2 * RT;                                          // records beyond are "minus infinity"
             // iteration at which this lane sits on the origin / on the end cell (INT_MIN: never)
             const int q_origin = (i == 0 && a == 0) ? S + sigma : (int)0x80000000;
-            const int q_end = (lane_ok && i == n && a == 0) ? m * P + S + sigma : (int)0x80000000;
+            const int q_end = (lane_ok && i == d.n && a == 0) ? d.m * P + S + sigma : (int)0x80000000;
+            const int q_end_hi = (lane_ok_hi && i == dh.n && a == 0 && dh.orig >= 0) ? dh.m * P + S + sigma : (int)0x80000000;
+            // P16 lane constants: additive constants with the lane's band-edge poisons folded in (SIMD adds)
+            const int c16_a1 = P16 ? vadd2(k2G2D, pW) : 0, c16_a3 = P16 ? vadd2(k2G2D, pU1) : 0;
+            const int c16_a2 = P16 ? vadd2(kGD, pW) : 0, c16_a6 = P16 ? vadd2(kGD, pU1) : 0;
+            const int c16_h22 = P16 ? vadd2(k2D, pW) : 0, c16_h12 = P16 ? vadd2(k2D, pU1) : 0;
             uint64_t* code_ptr = nullptr;
             if (TRACE && lane_ok) code_ptr = A.codes + d.code_off + ((long long)i * W + c) * (long long)(m + 1) * W;
 
@@ -334,12 +379,25 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                 if (bb == P) { bb = 0; ++j; }
                 wslot = RP2 ? (q & (RING - 1)) : ((wslot + 1 == RING) ? 0 : wslot + 1);
                 const int l = j + bb - S;
-                const bool valid = lane_ok && (bb < W) && ((unsigned)j <= (unsigned)m) && ((unsigned)l <= (unsigned)m);
+                const bool valid = lane_ok && (bb < W) && ((unsigned)j <= (unsigned)d.m) && ((unsigned)l <= (unsigned)d.m);
+                int vmask = 0, nmask = 0;  // P16: per-half validity
+                if (P16) {
+                    const bool valid_hi = lane_ok_hi && (bb < W) && ((unsigned)j <= (unsigned)dh.m) && ((unsigned)l <= (unsigned)dh.m);
+                    vmask = (valid ? 0x0000ffff : 0) | (valid_hi ? (int)0xffff0000 : 0);
+                    nmask = NEGP & ~vmask;
+                }
 
                 // ---- similarity inputs of the target cell (mu1 changes once per column)
                 const int cB = sclsB[l + boff];
-                if (bb == 0) mu1 = simrow[sresB[j + boff]];
-                const int mu2 = (cB == Ak) ? A.w_p : 0;
+                int mu2;
+                if (P16) {
+                    const int cBh = sclsB_hi[l + boff];
+                    if (bb == 0) mu1 = (simrow[sresB[j + boff]] & 0xffff) | (simrow_hi[sresB_hi[j + boff]] << 16);
+                    mu2 = ((cB == Ak) ? wlo : 0) | ((cBh == Ak_hi) ? whi : 0);
+                } else {
+                    if (bb == 0) mu1 = simrow[sresB[j + boff]];
+                    mu2 = (cB == Ak) ? A.w_p : 0;
+                }
 
                 // ---- flush the CTA's last row of iteration q-1 to the outgoing boundary stream
                 {
@@ -423,53 +481,84 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                 //   pB0: x1=0,x3=1 at b = -S          pB1: x1=1,x3=0 at b = +S
                 const int pB0 = (!PAD && bb == 0) ? NEGP : 0;
                 const int pB1 = (!PAD && bb == W - 1) ? NEGP : 0;
-                int kF[9];
-                kF[0] = k2G;                       // x=0101
-                kF[1] = k2G2D + pW + pB1;          // x=0110
-                kF[2] = mu2 + kGD + pW;            // x=0111
-                kF[3] = k2G2D + pU1 + pB0;         // x=1001
-                kF[4] = k2G;                       // x=1010
-                kF[5] = mu2 + kGD + pB0;           // x=1011
-                kF[6] = mu1 + kGD + pU1;           // x=1101
-                kF[7] = mu1 + kGD + pB1;           // x=1110
-                kF[8] = mu1 + mu2;                 // x=1111
-                // half-column cases also re-base the id field of the winner they carry (TRACE): a full-column
-                // source has field 27 - src (19..27); -10 maps the (t01, h) sources of x=(0,0,t2,t3) to 9..17 and
-                // -19 the (h, t23) sources of x=(t0,t1,0,0) to 0..8, so on equal tie keys the three groups keep the
-                // reference's case order (ids 0-8 < 9-11 < 12-14) and the source stays decodable.
+                int kF[9], kh2[3], kh1[3];
                 constexpr int ADJ2 = TRACE ? -10 : 0, ADJ1 = TRACE ? -19 : 0;
-                int kh2[3], kh1[3];
-                kh2[0] = kGD + ADJ2 + pB0;             // x=0001
-                kh2[1] = kGD + ADJ2 + pW;              // x=0010
-                kh2[2] = mu2 + k2D + ADJ2 + pW + pB0;  // x=0011
-                kh1[0] = kGD + ADJ1 + pB1;             // x=0100
-                kh1[1] = kGD + ADJ1 + pU1;             // x=1000
-                kh1[2] = mu1 + k2D + ADJ1 + pU1 + pB1; // x=1100
+                if (P16) {
+                    const int t0 = vadd2(kGD, pB0), t1 = vadd2(kGD, pB1);
+                    kF[0] = k2G;                         // x=0101
+                    kF[1] = vadd2(c16_a1, pB1);          // x=0110
+                    kF[2] = vadd2(mu2, c16_a2);          // x=0111
+                    kF[3] = vadd2(c16_a3, pB0);          // x=1001
+                    kF[4] = k2G;                         // x=1010
+                    kF[5] = vadd2(mu2, t0);              // x=1011
+                    kF[6] = vadd2(mu1, c16_a6);          // x=1101
+                    kF[7] = vadd2(mu1, t1);              // x=1110
+                    kF[8] = vadd2(mu1, mu2);             // x=1111
+                    kh2[0] = t0;                         // x=0001
+                    kh2[1] = c16_a2;                     // x=0010
+                    kh2[2] = vadd2(mu2, vadd2(c16_h22, pB0));  // x=0011
+                    kh1[0] = t1;                         // x=0100
+                    kh1[1] = c16_a6;                     // x=1000
+                    kh1[2] = vadd2(mu1, vadd2(c16_h12, pB1));  // x=1100
+                } else {
+                    kF[0] = k2G;                       // x=0101
+                    kF[1] = k2G2D + pW + pB1;          // x=0110
+                    kF[2] = mu2 + kGD + pW;            // x=0111
+                    kF[3] = k2G2D + pU1 + pB0;         // x=1001
+                    kF[4] = k2G;                       // x=1010
+                    kF[5] = mu2 + kGD + pB0;           // x=1011
+                    kF[6] = mu1 + kGD + pU1;           // x=1101
+                    kF[7] = mu1 + kGD + pB1;           // x=1110
+                    kF[8] = mu1 + mu2;                 // x=1111
+                    // half-column cases also re-base the id field of the winner they carry (TRACE): a full-column
+                    // source has field 27 - src (19..27); -10 maps the (t01, h) sources of x=(0,0,t2,t3) to 9..17 and
+                    // -19 the (h, t23) sources of x=(t0,t1,0,0) to 0..8, so on equal tie keys the three groups keep the
+                    // reference's case order (ids 0-8 < 9-11 < 12-14) and the source stays decodable.
+                    kh2[0] = kGD + ADJ2 + pB0;             // x=0001
+                    kh2[1] = kGD + ADJ2 + pW;              // x=0010
+                    kh2[2] = mu2 + k2D + ADJ2 + pW + pB0;  // x=0011
+                    kh1[0] = kGD + ADJ1 + pB1;             // x=0100
+                    kh1[1] = kGD + ADJ1 + pU1;             // x=1000
+                    kh1[2] = mu1 + k2D + ADJ1 + pU1 + pB1; // x=1100
+                }
                 int M[9];
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
                     const int t01 = t / 3, t23 = t % 3;
-                    const int v1 = addmax(inH1[t], kh1[t01], NEGP);  // floor: nothing ever drops below "minus infinity"
-                    const int v = addmax(inH2[t], kh2[t23], v1);
-                    M[t] = addmax(inF[t], kF[t], v);
-                    M[t] = valid ? M[t] : NEGP;
+                    const int v1 = xaddmax<P16>(inH1[t], kh1[t01], NEGP);  // floor: nothing ever drops below "minus infinity"
+                    const int v = xaddmax<P16>(inH2[t], kh2[t23], v1);
+                    M[t] = xaddmax<P16>(inF[t], kF[t], v);
+                    M[t] = P16 ? ((M[t] & vmask) | nmask) : (valid ? M[t] : NEGP);
                 }
 
                 // ---- results at the end cell
                 if (q == q_end) {
-                    int best = M[0] >> TB;
+                    int Mv[9];  // plain values of the nine states (low half in 16-bit pair mode)
 #pragma unroll
-                    for (int t = 1; t < 9; ++t) best = max(best, M[t] >> TB);
+                    for (int t = 0; t < 9; ++t) Mv[t] = P16 ? (int)(short)(M[t] & 0xffff) : (M[t] >> TB);
+                    int best = Mv[0];
+#pragma unroll
+                    for (int t = 1; t < 9; ++t) best = max(best, Mv[t]);
                     int st = 0, bsh = 99;
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
                         const int t01 = t / 3, t23 = t % 3;
                         const int sh = (hb0(t01) != hb0(t23)) + (hb1(t01) != hb1(t23));
-                        if ((M[t] >> TB) == best && sh < bsh) { bsh = sh; st = t; }
-                        A.end_values[(size_t)d.orig * 9 + t] = (M[t] >> TB) * A.gscale;
+                        if (Mv[t] == best && sh < bsh) { bsh = sh; st = t; }
+                        A.end_values[(size_t)d.orig * 9 + t] = Mv[t] * A.gscale;
                     }
                     A.scores[d.orig] = (long long)best * A.gscale;
                     A.start_state[d.orig] = (uint8_t)st;
+                }
+
+                if (P16 && q == q_end_hi) {  // the second pair of the work item ends at its own cell
+                    int best = M[0] >> 16;
+#pragma unroll
+                    for (int t = 1; t < 9; ++t) best = max(best, M[t] >> 16);
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) A.end_values[(size_t)dh.orig * 9 + t] = (M[t] >> 16) * A.gscale;
+                    A.scores[dh.orig] = (long long)best * A.gscale;
+                    A.start_state[dh.orig] = 0;
                 }
 
                 // ---- traceback code word + re-arm the tie-break bits for the role as a source
@@ -490,11 +579,11 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                 int Rv[3][3], Lv[3][3], Qv[3][3];
 #pragma unroll
                 for (int x = 0; x < 3; ++x) {
-                    open3<BNEG>(M[3 * x + 0], M[3 * x + 1], M[3 * x + 2], beta, Rv[x][0], Rv[x][1], Rv[x][2]);  // over s23, s01 = x
-                    open3<BNEG>(M[0 + x], M[3 + x], M[6 + x], beta, Lv[0][x], Lv[1][x], Lv[2][x]);              // over s01, s23 = x
+                    open3<BNEG, P16>(M[3 * x + 0], M[3 * x + 1], M[3 * x + 2], beta, Rv[x][0], Rv[x][1], Rv[x][2]);  // over s23, s01 = x
+                    open3<BNEG, P16>(M[0 + x], M[3 + x], M[6 + x], beta, Lv[0][x], Lv[1][x], Lv[2][x]);              // over s01, s23 = x
                 }
 #pragma unroll
-                for (int y = 0; y < 3; ++y) open3<BNEG>(Rv[0][y], Rv[1][y], Rv[2][y], beta, Qv[0][y], Qv[1][y], Qv[2][y]);
+                for (int y = 0; y < 3; ++y) open3<BNEG, P16>(Rv[0][y], Rv[1][y], Rv[2][y], beta, Qv[0][y], Qv[1][y], Qv[2][y]);
 
                 // prefetch the ring inputs of the next iteration (slots written >= 2 iterations before it)
                 if (PF) {
@@ -619,11 +708,11 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
 
 // ---- host-side geometry helpers (mirrored by engine.cu through kernels.cuh)
 template <int S, bool PAD>
-size_t smem_bytes_t(int G, int nsym, int bpad) {
+size_t smem_bytes_t(int G, int nsym, int bpad, bool p16 = false) {
     using G_ = Geo<S, PAD>;
     size_t ints = (size_t)(G + 1) * G_::RING * G_::RSLOT + (size_t)(G + 1) * 4 * G_::NX * G_::LPR + (size_t)G_::PB * G_::REC +
                   (size_t)G_::P * G_::LPR * 12 + (size_t)(nsym + 1) * nsym;
-    size_t bytes = ints * 4 + 2 * (size_t)bpad;
+    size_t bytes = ints * 4 + (p16 ? 4 : 2) * (size_t)bpad;  // molecule B residues + classes (of both pairs in 16-bit pair mode)
     return (bytes + 15) & ~(size_t)15;
 }
 
@@ -634,6 +723,24 @@ cudaError_t launch_t(const SysArgs& A, int grid, int G, size_t smem, cudaStream_
     if (e != cudaSuccess) return e;
     kern<<<grid, G * 32, smem, st>>>(A);
     return cudaGetLastError();
+}
+
+// 16-bit pair mode: two pairs per work item (score only, pad-free, beta < 0)
+template <int S>
+cudaError_t launch_p16_t(const SysArgs& A, int grid, int G, size_t smem, cudaStream_t st) {
+    auto kern = fill_systolic_kernel<S, false, false, true, false, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, G * 32, smem, st>>>(A);
+    return cudaGetLastError();
+}
+template <int S>
+int occ_p16_t(int G, size_t smem) {
+    auto kern = fill_systolic_kernel<S, false, false, true, false, true>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, G * 32, smem);
+    return nb;
 }
 
 // LONG flavour: cooperative launch (all CTAs must be co-resident: they wait on one another)

@@ -9,7 +9,9 @@ namespace ba {
     int sys_occupancy_s##s(bool, bool, bool, int, size_t);                                                              \
     cudaError_t launch_fill_systolic_long_s##s(const SysArgs&, int, int, size_t, bool, bool, cudaStream_t);             \
     int sys_occupancy_long_s##s(bool, bool, int, size_t);                                                              \
-    size_t sys_smem_bytes_s##s(bool, int, int, int);
+    size_t sys_smem_bytes_s##s(bool, int, int, int, bool);                                                              \
+    cudaError_t launch_fill_systolic_p16_s##s(const SysArgs&, int, int, size_t, cudaStream_t);                          \
+    int sys_occupancy_p16_s##s(int, size_t);
 DECL(0) DECL(1) DECL(2) DECL(3) DECL(4)
 #undef DECL
 
@@ -42,15 +44,36 @@ int sys_bpad(int S, bool pad, int G, int mmax) {
     return sys_boff(S, pad, G) + mmax + (2 * G * g.R + 4 * g.P + 16) / g.P + S + 8;
 }
 
-size_t sys_smem_bytes(int S, bool pad, int G, int nsym, int mmax) {
+size_t sys_smem_bytes(int S, bool pad, int G, int nsym, int mmax, bool p16) {
     const int bpad = sys_bpad(S, pad, G, mmax);
     switch (S) {
-        case 0: return sys_smem_bytes_s0(pad, G, nsym, bpad);
-        case 1: return sys_smem_bytes_s1(pad, G, nsym, bpad);
-        case 2: return sys_smem_bytes_s2(pad, G, nsym, bpad);
-        case 3: return sys_smem_bytes_s3(pad, G, nsym, bpad);
-        default: return sys_smem_bytes_s4(pad, G, nsym, bpad);
+        case 0: return sys_smem_bytes_s0(pad, G, nsym, bpad, p16);
+        case 1: return sys_smem_bytes_s1(pad, G, nsym, bpad, p16);
+        case 2: return sys_smem_bytes_s2(pad, G, nsym, bpad, p16);
+        case 3: return sys_smem_bytes_s3(pad, G, nsym, bpad, p16);
+        default: return sys_smem_bytes_s4(pad, G, nsym, bpad, p16);
     }
+}
+
+int sys_occupancy_p16(int S, int G, size_t smem) {
+    switch (S) {
+        case 0: return sys_occupancy_p16_s0(G, smem);
+        case 1: return sys_occupancy_p16_s1(G, smem);
+        case 2: return sys_occupancy_p16_s2(G, smem);
+        case 3: return sys_occupancy_p16_s3(G, smem);
+        default: return sys_occupancy_p16_s4(G, smem);
+    }
+}
+
+cudaError_t launch_fill_systolic_p16(const SysArgs& A, int grid, int G, size_t smem, cudaStream_t st) {
+    switch (A.sc.s) {
+        case 0: return launch_fill_systolic_p16_s0(A, grid, G, smem, st);
+        case 1: return launch_fill_systolic_p16_s1(A, grid, G, smem, st);
+        case 2: return launch_fill_systolic_p16_s2(A, grid, G, smem, st);
+        case 3: return launch_fill_systolic_p16_s3(A, grid, G, smem, st);
+        case 4: return launch_fill_systolic_p16_s4(A, grid, G, smem, st);
+    }
+    return cudaErrorInvalidValue;
 }
 
 int sys_occupancy(int S, bool trace, bool pad, bool bneg, int G, size_t smem) {

@@ -67,7 +67,9 @@ void launch_traceback(const TraceArgs& A, cudaStream_t st);
 
 struct SysGeo { int W, LPR, P, R, RING, REC; };
 SysGeo sys_geo(int S, bool pad);
-size_t sys_smem_bytes(int S, bool pad, int G, int nsym, int mmax);
+size_t sys_smem_bytes(int S, bool pad, int G, int nsym, int mmax, bool p16 = false);
+int sys_occupancy_p16(int S, int G, size_t smem);
+cudaError_t launch_fill_systolic_p16(const SysArgs& A, int grid, int G, size_t smem, cudaStream_t st);
 int sys_iters(int S, bool pad, int G, int m);
 size_t sys_boundary_ints(int S, bool pad, int G, int mmax);
 int sys_occupancy(int S, bool trace, bool pad, bool bneg, int G, size_t smem);

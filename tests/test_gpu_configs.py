@@ -73,6 +73,7 @@ def test_config3_slice_properties_and_subsample():
     scores, cols, offsets, complete = al.align_encoded(res, cls, off, pa, pb, want_trace=True)
     assert complete.all() and al.engine.stats()["kernel_kind"] == 1
     assert (al.align_encoded(res, cls, off, pa, pb, want_trace=False) == scores).all()
+    assert al.engine.stats()["kernel_kind"] == 1  # 200-500 aa with BLOSUM62: does not fit the 16-bit pair mode
     assert _rescore_all(res, cls, off, pa, pb, params, scores, cols, offsets, workloads.decode_protein, step=5) == 0
     for p in (0, 1, 777, 1234, 1998, 1999):
         a, sa = workloads.decode_protein(res, cls, off, int(pa[p]))
@@ -92,6 +93,12 @@ def test_config4_rna_slice_score_only():
     al.table = __import__("bialign_b200.encoding", fromlist=["x"]).match_table(100, 0, nsym=4)
     scores = al.align_encoded(res, cls, off, pa, pb, want_trace=False)
     assert al.engine.stats()["cell_states"] == 20000 * 3229209  # 3 229 209 cell-states per pair
+    assert al.engine.stats()["kernel_kind"] == 5  # config 4 runs two pairs per lane in packed 16-bit halves
+    al.engine.set_option("p16", 0)
+    try:
+        assert (al.align_encoded(res, cls, off, pa, pb, want_trace=False) == scores).all()  # 32-bit kernel agrees
+    finally:
+        al.engine.set_option("p16", -1)
     for p in list(range(0, 20000, 667)) + [19999]:
         a, sa = workloads.decode_rna(res, cls, off, int(pa[p]))
         b, sb = workloads.decode_rna(res, cls, off, int(pb[p]))

@@ -132,9 +132,10 @@ def _check_batch(al, seqs, structs, pairs, params, table_pairs=0):
             reach = np.stack([((oc[valid] >> np.uint64(36 + t)) & np.uint64(1)).astype(bool) for t in range(9)], axis=1)
             reach &= want != 15
             assert (want[reach] == got[reach]).all(), q
-    # score-only run (no tie-break bits, no code stores) must give the same scores
+    # score-only run (no tie-break bits, no code stores; 16-bit pair mode when the range fits) must give the same scores
     s2 = al.align(seqs, structs, pairs, want_trace=False)
     assert (s2 == scores).all()
+    return kind
 
 
 def _select(engine, kind):
@@ -148,6 +149,7 @@ def _unselect(engine):
     engine.set_option("pad", -1)
     engine.set_option("warps_per_cta", 0)
     engine.set_option("long", -1)
+    engine.set_option("p16", -1)
 
 
 @pytest.mark.parametrize("kernel", [0, 1, 2])
@@ -161,8 +163,7 @@ def test_random_batch_vs_oracle(s, kernel):
     al = _aligner(params)
     _select(al.engine, kernel)
     try:
-        _check_batch(al, seqs, structs, pairs, params, table_pairs=24)
-        assert al.engine.stats()["kernel_kind"] == kernel
+        assert _check_batch(al, seqs, structs, pairs, params, table_pairs=24) == kernel
     finally:
         _unselect(al.engine)
 
@@ -181,8 +182,7 @@ def test_systolic_multipass_and_cta_shapes(warps, pad):
         _select(al.engine, 1 + pad)
         al.engine.set_option("warps_per_cta", warps)
         try:
-            _check_batch(al, seqs, structs, pairs, params, table_pairs=2)
-            assert al.engine.stats()["kernel_kind"] == 1 + pad
+            assert _check_batch(al, seqs, structs, pairs, params, table_pairs=2) == 1 + pad
         finally:
             _unselect(al.engine)
 
@@ -197,8 +197,7 @@ def test_positive_gap_opening_and_tie_storms():
         params.update(var)
         seqs, structs, pairs = _random_protein_batch(rng, 8, 1, 60)
         al = _aligner(params)
-        _check_batch(al, seqs, structs, pairs, params, table_pairs=8)
-        assert al.engine.stats()["kernel_kind"] in (1, 2)
+        assert _check_batch(al, seqs, structs, pairs, params, table_pairs=8) in (1, 2)
 
 
 def test_rna_batch_score_only_vs_oracle():
@@ -281,8 +280,7 @@ def test_long_pair_mode_multi_cta(warps, pad):
         al.engine.set_option("warps_per_cta", warps)
         al.engine.set_option("long", 1)
         try:
-            _check_batch(al, seqs, structs, pairs, params, table_pairs=3)
-            assert al.engine.stats()["kernel_kind"] == 3 + pad
+            assert _check_batch(al, seqs, structs, pairs, params, table_pairs=3) == 3 + pad
         finally:
             _unselect(al.engine)
 
@@ -354,3 +352,58 @@ def test_error_codes_range_and_alphabet():
     with pytest.raises(_capi.BialignError) as ei:  # pair index outside the sequence table
         ok.align_encoded(res[:2], np.zeros(2, np.uint8), np.array([0, 1, 2], np.int64), np.array([0], np.int32), np.array([7], np.int32))
     assert ei.value.code == _capi.BA_ERR_INVALID_ARG
+
+
+@pytest.mark.parametrize("s", [0, 1, 2, 3, 4])
+def test_score_only_16bit_pair_mode(s):
+    """Two pairs per lane in packed 16-bit halves (score-only batches whose range provably fits): ragged
+    partners, odd batch size, multi-pass, RNA and protein scoring -- against the oracle and the 32-bit kernel."""
+    rng = np.random.default_rng(1600 + s)
+    cases = [dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150, gap_cost=-50,
+                  shift_cost=-150, max_shift=s),
+             dict(type="RNA", simmatrix=None, structure_weight=400, gap_opening_cost=-200, gap_cost=-50, shift_cost=-150,
+                  max_shift=s, sequence_match_similarity=100, sequence_mismatch_similarity=0)]
+    for params in cases:
+        if params["type"] == "Protein":
+            seqs, structs, pairs = _random_protein_batch(rng, 13, 1, 90)
+        else:
+            seqs, structs, pairs = [], [], []
+            for q in range(13):
+                for _ in range(2):
+                    L = int(rng.integers(1, 130))
+                    seqs.append("".join("ACGU"[i] for i in rng.integers(0, 4, L)))
+                    structs.append("".join(".()"[i] if False else "." for i in range(L)))
+                pairs.append((2 * q, 2 * q + 1))
+            # simple balanced structures
+            structs = [("(" * (len(x) // 3) + "." * (len(x) - 2 * (len(x) // 3)) + ")" * (len(x) // 3)) for x in seqs]
+        al = _aligner(params)
+        try:
+            al.engine.set_option("p16", 1)
+            s16 = al.align(seqs, structs, pairs, want_trace=False)
+            assert al.engine.stats()["kernel_kind"] == 5
+            al.engine.set_option("p16", 0)
+            s32 = al.align(seqs, structs, pairs, want_trace=False)
+            assert al.engine.stats()["kernel_kind"] in (1, 2)
+        finally:
+            _unselect(al.engine)
+        assert (s16 == s32).all()
+        for q, (ia, ib) in enumerate(pairs):
+            assert int(s16[q]) == oracle.run(seqs[ia], seqs[ib], structs[ia], structs[ib], params, mode="codes")["score"], q
+
+
+def test_16bit_pair_mode_refused_when_range_does_not_fit():
+    from bialign_b200 import _capi
+    from bialign_b200 import workloads
+    from bialign_b200.batch import BatchAligner
+
+    res, cls, off, pa, pb = workloads.protein_pairs(4, seed=3)  # length 200-500 with BLOSUM62 x100: needs > 16 bits
+    al = BatchAligner(max_shift=2, **workloads.PROTEIN_PARAMS)
+    try:
+        al.engine.set_option("p16", 1)
+        with pytest.raises(_capi.BialignError) as ei:
+            al.align_encoded(res, cls, off, pa, pb, want_trace=False)
+        assert ei.value.code == _capi.BA_ERR_SCORE_RANGE
+    finally:
+        _unselect(al.engine)
+    al.align_encoded(res, cls, off, pa, pb, want_trace=False)
+    assert al.engine.stats()["kernel_kind"] in (1, 3)  # auto: falls back to a 32-bit kernel
