@@ -198,3 +198,22 @@ def test_workload_generators_are_deterministic_and_well_formed():
         seq, st = workloads.decode_rna(res, cls, off, q)
         assert len(seq) == 120 and st.count("(") == st.count(")")
         assert (encoding.rna_structure_classes(st) == cls[off[q]:off[q + 1]]).all()
+
+
+def test_header_is_valid_c_and_links(tmp_path):
+    """include/bialign_b200.h is plain C (no C++/CUDA types); a C client compiles and links against the library."""
+    import subprocess
+
+    from bialign_b200 import _capi
+
+    src = tmp_path / "client.c"
+    src.write_text('#include "bialign_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { ba_engine* e = 0; int rc = ba_engine_create(0, &e);\n'
+                   '  printf("%s rc=%d %s\\n", ba_version(), rc, rc ? ba_last_error(0) : "ok");\n'
+                   '  if (!rc) { ba_engine_destroy(e); }\n  return 0; }\n')
+    exe = tmp_path / "client"
+    libdir = os.path.dirname(_capi.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-l:libbialign_b200.so", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "bialign_b200" in out.stdout
