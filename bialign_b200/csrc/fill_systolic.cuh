@@ -210,6 +210,7 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
     const int baseS = own_ring + lane;                                 // self
     const int xs_in = g * 4 * NX * LPR;                                // xs block feeding this warp's row 0
     const int xs_out = (g + 1) * 4 * NX * LPR;
+    int* const xs_scratch = tbtab + 9 * P * LPR + c;  // 3*P*LPR >= 6*LPR spare ints behind the [9][P][LPR] table
 
     bool long_done = false;
     for (;;) {
@@ -620,8 +621,9 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                     wr[(6 + y) * 32] = Lv[2][y];
                     wr[(9 + y) * 32] = Lv[0][y];
                 }
-                if (r == R - 1) {  // short-delay values for the warp below / the next pass
-                    int* xo = xs + xs_out + (q & 3) * NX * LPR + c;
+                {   // short-delay values for the warp below / the next pass: only the last row's matter; the other
+                    // rows store into a scratch strip (the unused tail of the tie-break table) -- no divergent branch
+                    int* xo = (r == R - 1) ? xs + xs_out + (q & 3) * NX * LPR + c : xs_scratch;
 #pragma unroll
                     for (int y = 0; y < 3; ++y) {
                         xo[y * LPR] = Qv[1][y];
