@@ -159,7 +159,7 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
     constexpr int W = G_::W, P = G_::P, LPR = G_::LPR, R = G_::R, RING = G_::RING, NV = G_::NV, NX = G_::NX, PB = G_::PB;
     constexpr int RSLOT = G_::RSLOT, REC = G_::REC, REAL = G_::REAL;
     constexpr bool RP2 = (RING & (RING - 1)) == 0;  // power-of-two ring: slots are masks of the iteration counter
-    constexpr bool PF = (P - 1) >= 2;               // ring inputs can be fetched one iteration ahead
+    constexpr bool PF = LONG && (P - 1) >= 2;       // ring inputs fetched one iteration ahead (pays off in the long-pair pipeline only)
     extern __shared__ __align__(16) int smem[];
     const int G = blockDim.x >> 5;
     const int RT = G * R;  // rows per pass
