@@ -96,6 +96,7 @@ struct ba_engine {
     DevBuf<int> d_counter;
     DevBuf<int> d_simp, d_tbtab, d_bnd;
     DevBuf<unsigned long long> d_progress;
+    DevBuf<uint64_t> d_code_dump;
     int opt_long = -1;                 // multi-CTA long-pair mode: -1 auto, 0 off, 1 force
     int opt_p16 = -1;                  // 16-bit pair mode for score-only batches: -1 auto, 0 off, 1 force
     std::vector<int32_t> h_sim;
@@ -277,7 +278,7 @@ void ba_engine_destroy(ba_engine* e) {
     e->d_sim.release(); e->d_res.release(); e->d_cls.release(); e->d_desc.release(); e->d_codes.release();
     e->d_scratch.release(); e->d_counter.release(); e->d_scores.release(); e->d_start.release();
     e->d_complete.release(); e->d_trace.release(); e->d_endv.release(); e->d_tlen.release(); e->h_stage.release();
-    e->d_simp.release(); e->d_tbtab.release(); e->d_bnd.release(); e->d_progress.release();
+    e->d_simp.release(); e->d_tbtab.release(); e->d_bnd.release(); e->d_progress.release(); e->d_code_dump.release();
     cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -530,7 +531,7 @@ int ba_run(ba_engine* e, int want_trace) {
             // covers all rows in one pass; long ones want few warps per CTA and several CTAs per SM.
             const SysGeo geo = sys_geo(s, plan.pad);
             double best = 0;
-            for (int G = 2; G <= 8; ++G) {
+            for (int G = std::max(2, (18 * geo.LPR + 31) / 32); G <= 8; ++G) {
                 const size_t sm = sys_smem_bytes(s, plan.pad, G, e->sc.nsym, mmax, p16);
                 if (sm > 220 * 1024) continue;
                 const int occ = p16 ? sys_occupancy_p16(s, G, sm) : sys_occupancy(s, want_trace != 0, plan.pad, plan.bneg, G, sm);
@@ -548,8 +549,8 @@ int ba_run(ba_engine* e, int want_trace) {
             }
             if (sysG == 0) sysG = 2;
         }
-        // the LONG flavour stages one 16-byte vector per thread: a record (<= 180 ints) needs >= 45 threads
-        if (e->opt_long == 1 && sysG < 2) sysG = 2;
+        // one boundary-record element per thread: a CTA needs at least 18 * LPR threads
+        sysG = std::max(sysG, (18 * sys_geo(s, plan.pad).LPR + 31) / 32);
         while (sysG > 1 && sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax, p16) > 200 * 1024) --sysG;
         sys_smem = sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax, p16);
         const int occ = p16 ? sys_occupancy_p16(s, sysG, sys_smem) : sys_occupancy(s, want_trace != 0, plan.pad, plan.bneg, sysG, sys_smem);
@@ -598,6 +599,8 @@ int ba_run(ba_engine* e, int want_trace) {
         SA.progress = e->d_progress.p;
         SA.bnd = e->d_bnd.p; SA.bnd_iters = biters + 8;  // matches sys_boundary_ints: slack records in front
         SA.codes = want_trace ? e->d_codes.p : nullptr;
+        if (want_trace) CU(e->d_code_dump.ensure((size_t)(mmax + 2) * (2 * s + 1) + 8));
+        SA.code_dump = e->d_code_dump.p;
         SA.scores = e->d_scores.p; SA.start_state = e->d_start.p; SA.end_values = e->d_endv.p;
     } else {
         scratch_stride = generic_scratch_ints(nmax, s);  // sized for nine states; the non-affine kernel uses a ninth

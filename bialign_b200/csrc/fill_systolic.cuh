@@ -285,11 +285,11 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                                        : (int)((G + 1) * RING * RSLOT) + (io_v - NV) * LPR + io_cs;
             const int fl_src = io_col + (io_ring ? G * RING * RSLOT : G * 4 * NX * LPR);  // CTA output row
             const int st_dst = io_col;                                                    // ring[0] / xs[0]
-            const bool io_fast = REAL <= (int)blockDim.x;
+            // (the engine guarantees blockDim.x >= REAL, see engine.cu: one record element per thread)
             // Boundary streams hold record `rec` at offset (rec + PRE + 1) * REC, so the unconditional flush of
             // "iteration q-1" in the very first iteration lands in a slack record.  Running pointers, shared-memory
             // addresses in bytes: the fast path is ~7 instructions per direction and iteration.
-            const bool do_flush = has_out && io_fast && io_thread, do_stage = !LONG && has_in && io_fast && io_thread;
+            const bool do_flush = has_out && io_thread, do_stage = !LONG && has_in && io_thread;
             // LONG staging: thread e4 < REC/4 moves four consecutive record elements (one 16-byte cp.async.cg)
             constexpr int NVEC = REC / 4;
             unsigned lg_dst[4] = {0, 0, 0, 0};
@@ -317,8 +317,10 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
             const int c16_a1 = P16 ? vadd2(k2G2D, pW) : 0, c16_a3 = P16 ? vadd2(k2G2D, pU1) : 0;
             const int c16_a2 = P16 ? vadd2(kGD, pW) : 0, c16_a6 = P16 ? vadd2(kGD, pU1) : 0;
             const int c16_h22 = P16 ? vadd2(k2D, pW) : 0, c16_h12 = P16 ? vadd2(k2D, pU1) : 0;
+            // dead lanes (rows beyond n, band offsets outside [0,n]) stream their code words into a dump strip,
+            // so the store needs no lane test: only "is column j inside the pair"
             uint64_t* code_ptr = nullptr;
-            if (TRACE && lane_ok) code_ptr = A.codes + d.code_off + ((long long)i * W + c) * (long long)(m + 1) * W;
+            if (TRACE) code_ptr = lane_ok ? A.codes + d.code_off + ((long long)i * W + c) * (long long)(m + 1) * W : A.code_dump;
 
             // position of this lane one iteration before the first one (q = -PRE)
             int pos = -PRE - 1 - sigma;
@@ -405,14 +407,6 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                     const int ps = RP2 ? ((q - 1) & (RING - 1)) : ((wslot == 0) ? RING - 1 : wslot - 1);
                     if (do_flush) *fl_g = lds32(fl_s + (io_ring ? ps : ((q - 1) & 3)) * io_stride_b);
                     fl_g += REC;
-                    if (has_out && !io_fast && q > -PRE) {
-                        for (int e = tid; e < REAL; e += blockDim.x) {
-                            const int v = e / LPR, cs = e - v * LPR;
-                            const int val = (v < NV) ? ring[(G * RING + ps) * RSLOT + v * 32 + (R - 1) * LPR + cs]
-                                                     : xs[(G * 4 + ((q - 1) & 3)) * NX * LPR + (v - NV) * LPR + cs];
-                            bnd_out[(size_t)(q + PRE) * REC + e] = val;
-                        }
-                    }
                 }
 
                 // ---- gather the 27 inputs
@@ -567,7 +561,10 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                     const unsigned lo = (M[0] & 31) | ((M[1] & 31) << 5) | ((M[2] & 31) << 10) | ((M[3] & 31) << 15) |
                                         ((M[4] & 31) << 20) | ((M[5] & 31) << 25);
                     const unsigned hi = (M[6] & 31) | ((M[7] & 31) << 5) | ((M[8] & 31) << 10);
-                    if (valid) *reinterpret_cast<uint2*>(code_ptr + (long long)j * W + bb) = make_uint2(lo, hi);
+                    // cells of a valid column always lie inside this lane's code row (those with l outside the pair
+                    // are unused slots); pad cells (P > W) would spill into the next column and are skipped
+                    if ((unsigned)j <= (unsigned)m && (P == W || bb < W))
+                        *reinterpret_cast<uint2*>(code_ptr + j * W + bb) = make_uint2(lo, hi);
                     // table layout [source state][b][lane column]: for one source state the lanes of a warp read
                     // (at most P*LPR <= 32) consecutive words -> no bank conflicts
                     const int* tp = tbtab + bb * LPR + c;
@@ -667,16 +664,6 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                         if (q + LA < q_rec_lim) cp_async4s(pb_s + ((q + LA) & (PB - 1)) * (REC * 4), st_g);
                     }
                     st_g += REC;
-                    if (!io_fast) {
-                        const int rec = q + 2 * RT, nrec = rec + LA;
-                        for (int e = tid; e < REAL; e += blockDim.x) {
-                            const int v = e / LPR, cs = e - v * LPR;
-                            const int val = (rec >= 0 && rec < nit) ? pb[(q & (PB - 1)) * REC + e] : NEGP;
-                            if (v < NV) ring[(0 * RING + wslot) * RSLOT + v * 32 + (R - 1) * LPR + cs] = val;
-                            else xs[(0 * 4 + (q & 3)) * NX * LPR + (v - NV) * LPR + cs] = val;
-                            if (nrec < nit) cp_async4(pb + ((q + LA) & (PB - 1)) * REC + e, bnd_in + (size_t)(nrec + PRE + 1) * REC + e);
-                        }
-                    }
                     cp_async_commit();
                 }
                 __syncthreads();

@@ -42,6 +42,7 @@ struct SysArgs {
     int* bnd;                 // per CTA: two boundary streams of bnd_iters records
     int bnd_iters;
     uint64_t* codes;
+    uint64_t* code_dump;      // (mmax+1)*(2s+1) words: where lanes outside the pair stream their code words
     long long* scores;
     uint8_t* start_state;
     int* end_values;
