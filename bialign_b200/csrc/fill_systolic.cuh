@@ -71,6 +71,12 @@ __device__ __forceinline__ int lds32(unsigned addr) {
     asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
+template <int OFF>
+__device__ __forceinline__ int lds32o(unsigned addr) {  // [addr + OFF]: the offset folds into the LDS immediate
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1+%2];\n" : "=r"(v) : "r"(addr), "n"(OFF) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sts32(unsigned addr, int v) { asm volatile("st.shared.s32 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void cp_async4s(unsigned smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
@@ -208,6 +214,8 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
     const int lsrcW = (lane == 0) ? 31 : lane - 1;
     const int baseW = own_ring + lsrcW;                                // x0=0,x2=1
     const int baseS = own_ring + lane;                                 // self
+    // the same as shared-memory byte addresses: slot * RSLOT * 4 is then the only per-iteration address arithmetic
+    const unsigned rU0 = smem_u32(ring + baseU0), rU1 = smem_u32(ring + baseU1), rW = smem_u32(ring + baseW), rS = smem_u32(ring + baseS);
     const int xs_in = g * 4 * NX * LPR;                                // xs block feeding this warp's row 0
     const int xs_out = (g + 1) * 4 * NX * LPR;
     int* const xs_scratch = tbtab + 9 * P * LPR + c;  // 3*P*LPR >= 6*LPR spare ints behind the [9][P][LPR] table
@@ -429,17 +437,15 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                         rsC = wslot - P;       if (rsC < 0) rsC += RING;
                         rsD = wslot - (P - 1); if (rsD < 0) rsD += RING;
                     }
-                    inF[8] = ring[baseU0 + rsA * RSLOT + 2 * 32];  // x=1111 Q[11][11]
-                    inF[7] = ring[baseU0 + rsB * RSLOT + 1 * 32];  // x=1110 Q[11][10]
-                    inF[6] = ring[baseU1 + rsB * RSLOT + 0 * 32];  // x=1101 Q[11][01]
-                    inF[2] = ring[baseW + rsB * RSLOT + 5 * 32];   // x=0111 Q[01][11]
-                    inF[1] = ring[baseW + rsC * RSLOT + 4 * 32];   // x=0110 Q[01][10]
-                    inF[0] = ring[baseS + rsC * RSLOT + 3 * 32];   // x=0101 Q[01][01]
-#pragma unroll
-                    for (int y = 0; y < 3; ++y) {
-                        inH1[6 + y] = ring[baseU1 + rsC * RSLOT + (6 + y) * 32];  // x=1100 L[11][y]
-                        inH1[y] = ring[baseS + rsD * RSLOT + (9 + y) * 32];       // x=0100 L[01][y]
-                    }
+                    inF[8] = lds32o<(2) * 128>(rU0 + rsA * (RSLOT * 4));  // x=1111 Q[11][11]
+                    inF[7] = lds32o<(1) * 128>(rU0 + rsB * (RSLOT * 4));  // x=1110 Q[11][10]
+                    inF[6] = lds32o<(0) * 128>(rU1 + rsB * (RSLOT * 4));  // x=1101 Q[11][01]
+                    inF[2] = lds32o<(5) * 128>(rW + rsB * (RSLOT * 4));   // x=0111 Q[01][11]
+                    inF[1] = lds32o<(4) * 128>(rW + rsC * (RSLOT * 4));   // x=0110 Q[01][10]
+                    inF[0] = lds32o<(3) * 128>(rS + rsC * (RSLOT * 4));   // x=0101 Q[01][01]
+                    const unsigned aU1C = rU1 + rsC * (RSLOT * 4), aSD = rS + rsD * (RSLOT * 4);
+                    inH1[6] = lds32o<6 * 128>(aU1C); inH1[7] = lds32o<7 * 128>(aU1C); inH1[8] = lds32o<8 * 128>(aU1C);  // x=1100 L[11][*]
+                    inH1[0] = lds32o<9 * 128>(aSD); inH1[1] = lds32o<10 * 128>(aSD); inH1[2] = lds32o<11 * 128>(aSD);   // x=0100 L[01][*]
                 }
                 // short-delay values by shuffle
                 inF[5] = __shfl_up_sync(0xffffffffu, h3Q1011, LPR);      // x=1011 D=3
@@ -596,17 +602,15 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                         rsC = ns - P;       if (rsC < 0) rsC += RING;
                         rsD = ns - (P - 1); if (rsD < 0) rsD += RING;
                     }
-                    pfF[0] = ring[baseU0 + rsA * RSLOT + 2 * 32];  // x=1111 Q[11][11]
-                    pfF[1] = ring[baseU0 + rsB * RSLOT + 1 * 32];  // x=1110 Q[11][10]
-                    pfF[2] = ring[baseU1 + rsB * RSLOT + 0 * 32];  // x=1101 Q[11][01]
-                    pfF[3] = ring[baseW + rsB * RSLOT + 5 * 32];   // x=0111 Q[01][11]
-                    pfF[4] = ring[baseW + rsC * RSLOT + 4 * 32];   // x=0110 Q[01][10]
-                    pfF[5] = ring[baseS + rsC * RSLOT + 3 * 32];   // x=0101 Q[01][01]
-#pragma unroll
-                    for (int y = 0; y < 3; ++y) {
-                        pfH[y] = ring[baseU1 + rsC * RSLOT + (6 + y) * 32];     // x=1100 L[11][y]
-                        pfH[3 + y] = ring[baseS + rsD * RSLOT + (9 + y) * 32];  // x=0100 L[01][y]
-                    }
+                    pfF[0] = lds32o<(2) * 128>(rU0 + rsA * (RSLOT * 4));  // x=1111 Q[11][11]
+                    pfF[1] = lds32o<(1) * 128>(rU0 + rsB * (RSLOT * 4));  // x=1110 Q[11][10]
+                    pfF[2] = lds32o<(0) * 128>(rU1 + rsB * (RSLOT * 4));  // x=1101 Q[11][01]
+                    pfF[3] = lds32o<(5) * 128>(rW + rsB * (RSLOT * 4));   // x=0111 Q[01][11]
+                    pfF[4] = lds32o<(4) * 128>(rW + rsC * (RSLOT * 4));   // x=0110 Q[01][10]
+                    pfF[5] = lds32o<(3) * 128>(rS + rsC * (RSLOT * 4));   // x=0101 Q[01][01]
+                    const unsigned aU1C = rU1 + rsC * (RSLOT * 4), aSD = rS + rsD * (RSLOT * 4);
+                    pfH[0] = lds32o<6 * 128>(aU1C); pfH[1] = lds32o<7 * 128>(aU1C); pfH[2] = lds32o<8 * 128>(aU1C);   // x=1100 L[11][*]
+                    pfH[3] = lds32o<9 * 128>(aSD); pfH[4] = lds32o<10 * 128>(aSD); pfH[5] = lds32o<11 * 128>(aSD);    // x=0100 L[01][*]
                 }
 
                 // ring: long-delay values
