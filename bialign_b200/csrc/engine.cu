@@ -599,7 +599,8 @@ int ba_run(ba_engine* e, int want_trace) {
         SA.progress = e->d_progress.p;
         SA.bnd = e->d_bnd.p; SA.bnd_iters = biters + 8;  // matches sys_boundary_ints: slack records in front
         SA.codes = want_trace ? e->d_codes.p : nullptr;
-        if (want_trace) CU(e->d_code_dump.ensure((size_t)(mmax + 2) * (2 * s + 1) + 8));
+        SA.code_dump_stride = (size_t)(mmax + 2) * (2 * s + 1) + 8;
+        if (want_trace) CU(e->d_code_dump.ensure(SA.code_dump_stride * (size_t)std::max({max_grid, long_grid_max, 1})));
         SA.code_dump = e->d_code_dump.p;
         SA.scores = e->d_scores.p; SA.start_state = e->d_start.p; SA.end_values = e->d_endv.p;
     } else {

@@ -328,7 +328,8 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
             // dead lanes (rows beyond n, band offsets outside [0,n]) stream their code words into a dump strip,
             // so the store needs no lane test: only "is column j inside the pair"
             uint64_t* code_ptr = nullptr;
-            if (TRACE) code_ptr = lane_ok ? A.codes + d.code_off + ((long long)i * W + c) * (long long)(m + 1) * W : A.code_dump;
+            if (TRACE) code_ptr = lane_ok ? A.codes + d.code_off + ((long long)i * W + c) * (long long)(m + 1) * W
+                                           : A.code_dump + (size_t)blockIdx.x * A.code_dump_stride;  // one strip per CTA
 
             // position of this lane one iteration before the first one (q = -PRE)
             int pos = -PRE - 1 - sigma;

@@ -42,7 +42,8 @@ struct SysArgs {
     int* bnd;                 // per CTA: two boundary streams of bnd_iters records
     int bnd_iters;
     uint64_t* codes;
-    uint64_t* code_dump;      // (mmax+1)*(2s+1) words: where lanes outside the pair stream their code words
+    uint64_t* code_dump;      // per CTA a strip of (mmax+2)*(2s+1) words: where lanes outside the pair stream
+    size_t code_dump_stride;  //   their code words (shared strips would serialise in L2)
     long long* scores;
     uint8_t* start_state;
     int* end_values;
