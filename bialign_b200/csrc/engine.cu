@@ -168,7 +168,7 @@ SysPlan plan_systolic(const ba_engine* e, int nmax, int mmax, bool trace, bool b
     if (bits16 && trace) return pl;
     const Scoring& sc = e->sc;
     const int S = sc.s, nsym = sc.nsym;
-    if (nsym > 64) return pl;
+    if (nsym > 64 || S > BA_SYSTOLIC_MAX_SHIFT) return pl;
     int64_t g = gcd64(gcd64(sc.w, sc.beta), gcd64(sc.gamma, sc.delta));
     int64_t smax = 0, smin = 0;
     for (int32_t v : e->h_sim) { g = gcd64(g, v); smax = std::max<int64_t>(smax, v); smin = std::min<int64_t>(smin, v); }
@@ -306,6 +306,8 @@ int ba_set_scoring(ba_engine* e, const int32_t* sim, int nsym, int structure_wei
     if (!sim || nsym <= 0 || nsym > 256) return fail(e, BA_ERR_INVALID_ARG, "sim is NULL or nsym not in 1..256");
     if (max_shift < 0 || max_shift > BA_MAX_SHIFT)
         return fail(e, BA_ERR_INVALID_ARG, "max_shift must be in 0.." + std::to_string(BA_MAX_SHIFT));
+    // (the systolic kernels are instantiated for max_shift <= BA_SYSTOLIC_MAX_SHIFT; larger bands run on the
+    // general level kernel)
     CU(cudaSetDevice(e->device));
     e->sc = Scoring{structure_weight, gap_opening_cost, gap_cost, shift_cost, max_shift, nsym};
     e->h_sim.assign(sim, sim + (size_t)nsym * nsym);
@@ -619,8 +621,13 @@ int ba_run(ba_engine* e, int want_trace) {
     CU(cudaMemcpyAsync(e->d_desc.p, e->h_desc.data(), sizeof(PairDesc) * e->h_desc.size(), cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemsetAsync(e->d_counter.p, 0, sizeof(int) * n_waves, e->stream));
 
-    std::vector<cudaEvent_t> ev((size_t)n_waves * 3 + 1);
-    for (auto& x : ev) CU(cudaEventCreate(&x));
+    struct EventSet {  // destroyed on every exit path (the CU macro returns early on errors)
+        std::vector<cudaEvent_t> v;
+        ~EventSet() { for (auto x : v) if (x) cudaEventDestroy(x); }
+        cudaEvent_t& operator[](size_t i) { return v[i]; }
+    } ev;
+    ev.v.assign((size_t)n_waves * 3 + 1, nullptr);
+    for (auto& x : ev.v) CU(cudaEventCreate(&x));
     CU(cudaEventRecord(ev[0], e->stream));
     for (int w = 0; w < n_waves; ++w) {
         const int64_t b = wave_begin[w], cnt = wave_begin[w + 1] - b;
@@ -681,7 +688,6 @@ int ba_run(ba_engine* e, int want_trace) {
         CU(cudaEventElapsedTime(&ms, ev[0], ev[3 * n_waves]));
         e->stats.total_ms = ms;
     }
-    for (auto& x : ev) cudaEventDestroy(x);
     if (want_trace) {
         for (int64_t q = wave_begin[n_waves - 1]; q < N; ++q) e->h_last_code_off[e->h_desc[q].orig] = e->h_desc[q].code_off;
         int64_t cb = 0;

@@ -44,7 +44,8 @@ extern "C" {
 #define BA_API
 #endif
 
-#define BA_MAX_SHIFT 4 /* band half-width supported by the device kernels */
+#define BA_MAX_SHIFT 16         /* largest band half-width accepted (general level kernel)          */
+#define BA_SYSTOLIC_MAX_SHIFT 4 /* the fast systolic kernels are instantiated for max_shift 0..4    */
 
 typedef struct ba_engine ba_engine;
 

@@ -407,3 +407,36 @@ def test_16bit_pair_mode_refused_when_range_does_not_fit():
         _unselect(al.engine)
     al.align_encoded(res, cls, off, pa, pb, want_trace=False)
     assert al.engine.stats()["kernel_kind"] in (1, 3)  # auto: falls back to a 32-bit kernel
+
+
+def test_wide_band_and_large_alphabet_fall_back_to_the_general_kernel():
+    """max_shift 5 (beyond the systolic instantiations) and a 256-symbol similarity table (raw bytes, too large
+    for the shared-memory copy of the fast kernel) run on the general level kernel -- still on the GPU, still exact."""
+    from bialign_b200 import _capi
+    from bialign_b200.batch import trace_hex
+
+    rng = np.random.default_rng(55)
+    params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150, gap_cost=-50,
+                  shift_cost=-150, max_shift=5)
+    seqs, structs, pairs = _random_protein_batch(rng, 4, 3, 24)
+    al = _aligner(params)
+    scores, cols, offsets, complete = al.align(seqs, structs, pairs, want_trace=True)
+    assert al.engine.stats()["kernel_kind"] == 0
+    for q, (ia, ib) in enumerate(pairs):
+        r = oracle.run(seqs[ia], seqs[ib], structs[ia], structs[ib], params, mode="codes")
+        assert int(scores[q]) == r["score"] and trace_hex(cols, offsets, q) == r["trace"], q
+    # raw-byte residues with the oracle's own 256 x 256 table, straight through the C ABI wrapper
+    params["max_shift"] = 2
+    eng = _capi.get_engine()
+    eng.set_scoring(oracle.blosum62_table(), 800, -150, -50, -150, 2)
+    res = np.concatenate([oracle.encode(x, y, False)[0] for x, y in zip(seqs, structs)])
+    cls = np.concatenate([oracle.encode(x, y, False)[1] for x, y in zip(seqs, structs)])
+    off = np.concatenate([[0], np.cumsum([len(x) for x in seqs])]).astype(np.int64)
+    pa = np.array([p[0] for p in pairs], dtype=np.int32)
+    pb = np.array([p[1] for p in pairs], dtype=np.int32)
+    sc = eng.align_batch(res, cls, off, pa, pb, want_trace=True)
+    assert eng.stats()["kernel_kind"] == 0
+    cols, offsets, complete = eng.fetch_traces()
+    for q, (ia, ib) in enumerate(pairs):
+        r = oracle.run(seqs[ia], seqs[ib], structs[ia], structs[ib], params, mode="codes")
+        assert int(sc[q]) == r["score"] and trace_hex(cols, offsets, q) == r["trace"], q
