@@ -122,6 +122,9 @@ __device__ __forceinline__ void open3(int i0, int i1, int i2, int beta, int& o0,
 #define BA_SYS_MAXNREG 168  // 3 CTAs of 128 threads per SM: 65536 / 384 = 170
 #endif
 constexpr int LA = 8;   // cp.async look-ahead (iterations) of the boundary staging
+constexpr int LQ = 32;   // long-pair mode: progress flags are published / polled every LQ iterations (power of two);
+                        // measured on the 8192 x 8192 pair: 4 -> 158 ms (the extra barrier and the spinning thread dominate),
+                        // 16 -> 86 ms, 32 -> 84 ms, 64 -> 84 ms
 constexpr int PRE = 4;  // iterations run before position 0: the virtual row above row 0 is 2 iterations ahead,
                         // so its first records must be staged before lane (0,0) reaches its first cell
 
@@ -153,7 +156,7 @@ struct Geo {
 // CTA while it is being produced.  Streams live in 2*NC global buffers (pass p -> buffer
 // p%NC + NC*((p/NC)&1): by the time it is overwritten, at pass p+2NC, pass p+1 has finished because
 // every later pass transitively depends on it).  Progress flags (pass id << 32 | records complete)
-// are published every 16 iterations with release semantics and polled with acquire loads; stream
+// are published every LQ iterations with release semantics and polled with acquire loads; stream
 // reads are 16-byte cp.async.cg (L2 only), so no stale L1 line can be seen across SMs.
 //
 // P16 = two pairs per work item in packed 16-bit halves (score only, pad-free, beta < 0): twice the pairs per
@@ -373,14 +376,14 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
             __syncthreads();
 
             for (int q = -PRE; q < nit; ++q) {
-                if (LONG && (q & 15) == 0) {
+                if (LONG && (q & (LQ - 1)) == 0) {
                     if (tid == 0) {
                         if (has_out && q > 0) {  // records 0..q-2 were stored before the last barrier
                             __threadfence();
                             st_release_u64(prog_out, tag_out | (unsigned long long)(q - 1));
                         }
-                        if (has_in) {  // the next 16 iterations prefetch records up to q + 15 + LA + 2RT
-                            const unsigned long long want = tag_in | (unsigned long long)min(q + 16 + LA + 2 * RT, nit);
+                        if (has_in) {  // the next LQ iterations prefetch records up to q + LQ - 1 + LA + 2RT
+                            const unsigned long long want = tag_in | (unsigned long long)min(q + LQ + LA + 2 * RT, nit);
                             while (ld_acquire_u64(prog_in) < want) __nanosleep(100);
                         }
                     }
