@@ -440,3 +440,29 @@ def test_wide_band_and_large_alphabet_fall_back_to_the_general_kernel():
     for q, (ia, ib) in enumerate(pairs):
         r = oracle.run(seqs[ia], seqs[ib], structs[ia], structs[ib], params, mode="codes")
         assert int(sc[q]) == r["score"] and trace_hex(cols, offsets, q) == r["trace"], q
+
+
+@pytest.mark.parametrize("variant", [{"shift_cost": 0}, {"structure_weight": 0, "gap_cost": 0}, {"shift_cost": 0, "gap_cost": 0, "gap_opening_cost": -1}])
+def test_tie_storms_at_multipass_sizes(variant):
+    """Tie-breaking exactness where it is hardest: parameter sets that make most cases tie, on pairs long enough for
+    a dozen passes through the boundary streams; scores, traces and every reachable code vs the oracle."""
+    rng = np.random.default_rng(31337)
+    params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150, gap_cost=-50,
+                  shift_cost=-150, max_shift=2)
+    params.update(variant)
+    seqs, structs, pairs = _random_protein_batch(rng, 3, 150, 260)
+    # make the second molecule of each pair a noisy copy of the first: long runs of equally good alternatives
+    for q in range(3):
+        a = seqs[2 * q]
+        b = list(a[: len(seqs[2 * q + 1])].ljust(len(seqs[2 * q + 1]), "A"))
+        for p in range(0, len(b), 9):
+            b[p] = "ARNDCQEGHILKMFPSTWYV"[rng.integers(0, 20)]
+        seqs[2 * q + 1] = "".join(b)
+        structs[2 * q + 1] = (structs[2 * q][3:] + "HHH")[: len(b)].ljust(len(b), "C")
+    al = _aligner(params)
+    assert _check_batch(al, seqs, structs, pairs, params, table_pairs=3) in (3, 4)  # three long-ish pairs: long-pair mode
+    al.engine.set_option("long", 0)
+    try:
+        assert _check_batch(al, seqs, structs, pairs, params, table_pairs=3) in (1, 2)  # CTA-per-pair mode
+    finally:
+        _unselect(al.engine)
