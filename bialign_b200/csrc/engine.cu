@@ -163,9 +163,9 @@ int64_t gcd64(int64_t a, int64_t b) {
 // Exactness conditions of the packed 32-bit domain (DESIGN.md "tie-break packing"): every finite value
 // lies in [-Fn, Fp], "minus infinity" values in [negp - Fn, negp + Fp]; the two ranges must not meet
 // and nothing may leave the (32 - tb)-bit field.
-SysPlan plan_systolic(const ba_engine* e, int nmax, int mmax, bool trace, bool bits16 = false) {
+SysPlan plan_systolic(const ba_engine* e, int nmax, int mmax, bool trace, bool bits16 = false, bool nonaffine = false) {
     SysPlan pl;
-    if (bits16 && trace) return pl;
+    if (bits16 && (trace || nonaffine)) return pl;
     const Scoring& sc = e->sc;
     const int S = sc.s, nsym = sc.nsym;
     if (nsym > 64 || S > BA_SYSTOLIC_MAX_SHIFT) return pl;
@@ -188,10 +188,10 @@ SysPlan plan_systolic(const ba_engine* e, int nmax, int mmax, bool trace, bool b
     (void)c1p; (void)c2p;
     int kb = 0;
     while ((1 << kb) < (S + 2) * (S + 2)) ++kb;
-    pl.tb = trace ? kb + 5 : 0;
+    pl.tb = trace ? (nonaffine ? 4 : kb + 5) : 0;  // non-affine: 15 - case index of pyx:233-248
     const int vb = (bits16 ? 16 : 32) - pl.tb;
     const int64_t lim = (int64_t)1 << (vb - 1);
-    pl.bneg = sc.beta < 0;
+    pl.bneg = sc.beta < 0 || nonaffine;  // beta == 0: the beta <= 0 shortcut of open() is exact, no opening term at all
     // pad-free flavour: band-edge cases carry a poison of NEGP and values are floored at NEGP, so the most
     // negative intermediate is (floored source) + two poisons + constants  >=  3*negv - Fn
     const int64_t negv_nopad = -(Fn + Fp + colabs);
@@ -213,7 +213,7 @@ SysPlan plan_systolic(const ba_engine* e, int nmax, int mmax, bool trace, bool b
     pl.negp = (int)(negv * ((int64_t)1 << pl.tb));
     pl.sim_p.resize((size_t)nsym * nsym);
     for (size_t q = 0; q < pl.sim_p.size(); ++q) pl.sim_p[q] = (int)((e->h_sim[q] / g) * ((int64_t)1 << pl.tb));
-    if (trace) {
+    if (trace && !nonaffine) {
         // rank of the tie key (k0,k1) = (|T0|+|T1|, |T1|), T = band offset of the cell + (s0-s2, s1-s3): pyx:541-545
         const SysGeo geo = sys_geo(S, pl.pad);
         const int LPR = geo.LPR, P = geo.P, NK = (S + 2) * (S + 2);
@@ -515,8 +515,8 @@ int ba_run(ba_engine* e, int want_trace) {
     }
     if (e->opt_p16 == 1 && !p16 && !want_trace && affine && N >= 2)
         return fail(e, BA_ERR_SCORE_RANGE, "16-bit pair mode requested but the score range does not fit");
-    if (!p16 && e->opt_kernel != 0 && affine) plan = plan_systolic(e, nmax, mmax, want_trace != 0);
-    if (e->opt_kernel == 1 && affine && !plan.ok)
+    if (!p16 && e->opt_kernel != 0) plan = plan_systolic(e, nmax, mmax, want_trace != 0, false, !affine);
+    if (e->opt_kernel == 1 && !plan.ok)
         return fail(e, BA_ERR_SCORE_RANGE, "systolic kernel requested but its packed-integer range conditions do not hold");
     const int kernel = plan.ok ? 1 : 0;
     int max_grid = e->sm_count * 2;
@@ -536,7 +536,9 @@ int ba_run(ba_engine* e, int want_trace) {
             for (int G = std::max(2, (18 * geo.LPR + 31) / 32); G <= 8; ++G) {
                 const size_t sm = sys_smem_bytes(s, plan.pad, G, e->sc.nsym, mmax, p16);
                 if (sm > 220 * 1024) continue;
-                const int occ = p16 ? sys_occupancy_p16(s, G, sm) : sys_occupancy(s, want_trace != 0, plan.pad, plan.bneg, G, sm);
+                const int occ = p16 ? sys_occupancy_p16(s, G, sm)
+                                    : !affine ? sys_occupancy_na(s, want_trace != 0, plan.pad, G, sm)
+                                              : sys_occupancy(s, want_trace != 0, plan.pad, plan.bneg, G, sm);
                 if (occ < 1) continue;
                 const double eff = std::min(occ * G, 12);
                 double cost = 0;
@@ -555,7 +557,9 @@ int ba_run(ba_engine* e, int want_trace) {
         sysG = std::max(sysG, (18 * sys_geo(s, plan.pad).LPR + 31) / 32);
         while (sysG > 1 && sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax, p16) > 200 * 1024) --sysG;
         sys_smem = sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax, p16);
-        const int occ = p16 ? sys_occupancy_p16(s, sysG, sys_smem) : sys_occupancy(s, want_trace != 0, plan.pad, plan.bneg, sysG, sys_smem);
+        const int occ = p16 ? sys_occupancy_p16(s, sysG, sys_smem)
+                            : !affine ? sys_occupancy_na(s, want_trace != 0, plan.pad, sysG, sys_smem)
+                                      : sys_occupancy(s, want_trace != 0, plan.pad, plan.bneg, sysG, sys_smem);
         if (occ < 1) return fail(e, BA_ERR_CUDA, "systolic kernel does not fit on an SM (shared memory " + std::to_string(sys_smem) + ")");
         max_grid = e->sm_count * occ;
         const int grid = (int)std::min<int64_t>(biggest_wave, max_grid);
@@ -570,7 +574,7 @@ int ba_run(ba_engine* e, int want_trace) {
         }
         // Few, long pairs: spread the row blocks of each pair over the whole grid (LONG flavour, cooperative launch)
         const int npass_max = (nmax + rows_pass) / rows_pass;
-        if (!p16 && plan.bneg && e->opt_long != 0 && npass_max >= 2 && sysG >= 2 &&
+        if (!p16 && affine && plan.bneg && e->opt_long != 0 && npass_max >= 2 && sysG >= 2 &&
             (e->opt_long == 1 || (N <= 4 && npass_max >= 8))) {
             const int occl = sys_occupancy_long(s, want_trace != 0, plan.pad, sysG, sys_smem);
             int coop = 0;
@@ -596,6 +600,7 @@ int ba_run(ba_engine* e, int want_trace) {
         SA.w_p = (int)(e->sc.w / plan.g * sh); SA.beta_p = (int)(e->sc.beta / plan.g * sh);
         SA.k_gd = (int)((e->sc.gamma + e->sc.delta) / plan.g * sh); SA.k_2g = (int)(2 * e->sc.gamma / plan.g * sh);
         SA.k_2g2d = (int)((2 * e->sc.gamma + 2 * e->sc.delta) / plan.g * sh); SA.k_2d = (int)(2 * e->sc.delta / plan.g * sh);
+        SA.k_d = (int)(e->sc.delta / plan.g * sh);
         SA.negp = plan.negp; SA.tb_bits = plan.tb; SA.gscale = plan.g; SA.mmax = mmax;
         SA.boff = sys_boff(s, plan.pad, sysG); SA.bpad = sys_bpad(s, plan.pad, sysG, mmax);
         SA.progress = e->d_progress.p;
@@ -651,6 +656,9 @@ int ba_run(ba_engine* e, int want_trace) {
         } else if (kernel == 1 && p16) {  // two pairs per work item (score only: a single wave)
             SA.pairs = e->d_desc.p; SA.npairs = (int)((N + 1) / 2); SA.counter = e->d_counter.p + w;
             CU(launch_fill_systolic_p16(SA, (int)std::min<int64_t>((N + 1) / 2, max_grid), sysG, sys_smem, e->stream));
+        } else if (kernel == 1 && !affine) {
+            SA.pairs = e->d_desc.p + b; SA.npairs = (int)cnt; SA.counter = e->d_counter.p + w;
+            CU(launch_fill_systolic_na(SA, grid, sysG, sys_smem, want_trace != 0, plan.pad, e->stream));
         } else if (kernel == 1) {
             SA.pairs = e->d_desc.p + b; SA.npairs = (int)cnt; SA.counter = e->d_counter.p + w;
             CU(launch_fill_systolic(SA, grid, sysG, sys_smem, want_trace != 0, plan.pad, plan.bneg, e->stream));
@@ -695,7 +703,7 @@ int ba_run(ba_engine* e, int want_trace) {
         e->stats.code_bytes = cb;
     }
     e->stats.waves = n_waves;
-    e->stats.kernel_kind = kernel == 0 ? 0 : (p16 ? 5 : (plan.pad ? 2 : 1) + (long_mode ? 2 : 0));
+    e->stats.kernel_kind = kernel == 0 ? 0 : (p16 ? 5 : !affine ? (plan.pad ? 7 : 6) : (plan.pad ? 2 : 1) + (long_mode ? 2 : 0));
     e->stats.warps_per_cta = kernel == 0 ? 0 : sysG;
     e->last_fmt = kernel;
     e->ran = true;

@@ -161,9 +161,17 @@ struct Geo {
 //
 // P16 = two pairs per work item in packed 16-bit halves (score only, pad-free, beta < 0): twice the pairs per
 // instruction for batches whose scores provably fit 16 bits (short RNA-like pairs, BASELINE config 4).
-template <int S, bool TRACE, bool PAD, bool BNEG, bool LONG, bool P16 = false>
+//
+// NA = the non-affine model (gap_opening_cost == 0, pyx:225-252, 443-471, 513-531) on the same machinery: with beta = 0
+// the nine "states" only remember the type of the last column, the best of them is the reference's single value
+// M[i,j,k,l].  Three constants differ from the affine score (half-match columns 1100 / 0011 cost Delta, not 2 Delta;
+// the double-shift columns 0110 / 1001 do not exist, pyx:250-252), and the tie-break is "first case in the order of
+// pyx:233-248": with TRACE the low 4 bits carry 15 - case index, attached at the target through the additive constants;
+// the code word of a cell is the case index of its best state (what the traceback of pyx:521-528 would pick).
+template <int S, bool TRACE, bool PAD, bool BNEG, bool LONG, bool P16 = false, bool NA = false>
 __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
     static_assert(!P16 || (!TRACE && !PAD && BNEG && !LONG), "16-bit pair mode: score only, pad-free, beta < 0, batch mode");
+    static_assert(!NA || (BNEG && !LONG && !P16), "non-affine flavour: batch mode, 32-bit");
     using G_ = Geo<S, PAD>;
     constexpr int W = G_::W, P = G_::P, LPR = G_::LPR, R = G_::R, RING = G_::RING, NV = G_::NV, NX = G_::NX, PB = G_::PB;
     constexpr int RSLOT = G_::RSLOT, REC = G_::REC, REAL = G_::REAL;
@@ -202,7 +210,7 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
 
     // ---- one-time shared-memory initialisation: everything "minus infinity"
     for (int q = tid; q < (int)((G + 1) * RING * RSLOT + (G + 1) * 4 * NX * LPR + PB * REC); q += blockDim.x) smem[q] = NEGP;
-    if (TRACE)
+    if (TRACE && !NA)
         for (int q = tid; q < P * LPR * 12; q += blockDim.x) tbtab[q] = A.tbtab[q];
     for (int q = tid; q < (nsym + 1) * nsym; q += blockDim.x) ssim[q] = (q < nsym * nsym) ? A.sim_p[q] : 0;
     __syncthreads();
@@ -505,6 +513,24 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                     kh1[0] = t1;                         // x=0100
                     kh1[1] = c16_a6;                     // x=1000
                     kh1[2] = vadd2(mu1, vadd2(c16_h12, pB1));  // x=1100
+                } else if (NA) {
+                    // non-affine scores (pyx:233-248) + (15 - case index) in the low four bits when TRACE
+                    constexpr int T_ = TRACE ? 1 : 0;
+                    kF[0] = k2G + T_ * (15 - 2);                       // x=0101  case 2
+                    kF[1] = 0; inF[1] = NEGP;                          // x=0110  does not exist (pyx:250-252)
+                    kF[2] = mu2 + kGD + pW + T_ * (15 - 10);           // x=0111  case 10
+                    kF[3] = 0; inF[3] = NEGP;                          // x=1001  does not exist
+                    kF[4] = k2G + T_ * (15 - 1);                       // x=1010  case 1
+                    kF[5] = mu2 + kGD + pB0 + T_ * (15 - 9);           // x=1011  case 9
+                    kF[6] = mu1 + kGD + pU1 + T_ * (15 - 12);          // x=1101  case 12
+                    kF[7] = mu1 + kGD + pB1 + T_ * (15 - 11);          // x=1110  case 11
+                    kF[8] = mu1 + mu2 + T_ * 15;                       // x=1111  case 0
+                    kh2[0] = kGD + pB0 + T_ * (15 - 8);                // x=0001  case 8
+                    kh2[1] = kGD + pW + T_ * (15 - 7);                 // x=0010  case 7
+                    kh2[2] = mu2 + A.k_d + pW + pB0 + T_ * (15 - 4);   // x=0011  case 4: mu2 + Delta
+                    kh1[0] = kGD + pB1 + T_ * (15 - 6);                // x=0100  case 6
+                    kh1[1] = kGD + pU1 + T_ * (15 - 5);                // x=1000  case 5
+                    kh1[2] = mu1 + A.k_d + pU1 + pB1 + T_ * (15 - 3);  // x=1100  case 3: mu1 + Delta
                 } else {
                     kF[0] = k2G;                       // x=0101
                     kF[1] = k2G2D + pW + pB1;          // x=0110
@@ -567,7 +593,15 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                 }
 
                 // ---- traceback code word + re-arm the tie-break bits for the role as a source
-                if (TRACE) {
+                if (TRACE && NA) {
+                    // the cell's single traceback code: case index of the best state (value desc, case order asc)
+                    const int bestp = vmax3(vmax3(M[0], M[1], M[2]), vmax3(M[3], M[4], M[5]), vmax3(M[6], M[7], M[8]));
+                    if ((unsigned)j <= (unsigned)m && (P == W || bb < W))
+                        *reinterpret_cast<uint2*>(code_ptr + j * W + bb) = make_uint2(15u - (unsigned)(bestp & 15), 0u);
+                    const int msk = ~((1 << TB) - 1);
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) M[t] &= msk;  // as a source a state carries no tie information
+                } else if (TRACE) {
                     const unsigned lo = (M[0] & 31) | ((M[1] & 31) << 5) | ((M[2] & 31) << 10) | ((M[3] & 31) << 15) |
                                         ((M[4] & 31) << 20) | ((M[5] & 31) << 25);
                     const unsigned hi = (M[6] & 31) | ((M[7] & 31) << 5) | ((M[8] & 31) << 10);
@@ -738,6 +772,34 @@ int occ_p16_t(int G, size_t smem) {
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, G * 32, smem);
     return nb;
+}
+
+// non-affine flavour (gap_opening_cost == 0)
+template <int S, bool TRACE, bool PAD>
+cudaError_t launch_na_t(const SysArgs& A, int grid, int G, size_t smem, cudaStream_t st) {
+    auto kern = fill_systolic_kernel<S, TRACE, PAD, true, false, false, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, G * 32, smem, st>>>(A);
+    return cudaGetLastError();
+}
+template <int S, bool TRACE, bool PAD>
+int occ_na_t(int G, size_t smem) {
+    auto kern = fill_systolic_kernel<S, TRACE, PAD, true, false, false, true>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, G * 32, smem);
+    return nb;
+}
+template <int S>
+cudaError_t launch_na_s(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, cudaStream_t st) {
+    if (pad) return trace ? launch_na_t<S, true, true>(A, grid, G, smem, st) : launch_na_t<S, false, true>(A, grid, G, smem, st);
+    return trace ? launch_na_t<S, true, false>(A, grid, G, smem, st) : launch_na_t<S, false, false>(A, grid, G, smem, st);
+}
+template <int S>
+int occ_na_s(bool trace, bool pad, int G, size_t smem) {
+    if (pad) return trace ? occ_na_t<S, true, true>(G, smem) : occ_na_t<S, false, true>(G, smem);
+    return trace ? occ_na_t<S, true, false>(G, smem) : occ_na_t<S, false, false>(G, smem);
 }
 
 // LONG flavour: cooperative launch (all CTAs must be co-resident: they wait on one another)

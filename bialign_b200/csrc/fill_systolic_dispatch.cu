@@ -11,7 +11,9 @@ namespace ba {
     int sys_occupancy_long_s##s(bool, bool, int, size_t);                                                              \
     size_t sys_smem_bytes_s##s(bool, int, int, int, bool);                                                              \
     cudaError_t launch_fill_systolic_p16_s##s(const SysArgs&, int, int, size_t, cudaStream_t);                          \
-    int sys_occupancy_p16_s##s(int, size_t);
+    int sys_occupancy_p16_s##s(int, size_t);                                                                            \
+    cudaError_t launch_fill_systolic_na_s##s(const SysArgs&, int, int, size_t, bool, bool, cudaStream_t);               \
+    int sys_occupancy_na_s##s(bool, bool, int, size_t);
 DECL(0) DECL(1) DECL(2) DECL(3) DECL(4)
 #undef DECL
 
@@ -93,6 +95,27 @@ cudaError_t launch_fill_systolic(const SysArgs& A, int grid, int G, size_t smem,
         case 2: return launch_fill_systolic_s2(A, grid, G, smem, trace, pad, bneg, st);
         case 3: return launch_fill_systolic_s3(A, grid, G, smem, trace, pad, bneg, st);
         case 4: return launch_fill_systolic_s4(A, grid, G, smem, trace, pad, bneg, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+int sys_occupancy_na(int S, bool trace, bool pad, int G, size_t smem) {
+    switch (S) {
+        case 0: return sys_occupancy_na_s0(trace, pad, G, smem);
+        case 1: return sys_occupancy_na_s1(trace, pad, G, smem);
+        case 2: return sys_occupancy_na_s2(trace, pad, G, smem);
+        case 3: return sys_occupancy_na_s3(trace, pad, G, smem);
+        default: return sys_occupancy_na_s4(trace, pad, G, smem);
+    }
+}
+
+cudaError_t launch_fill_systolic_na(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, cudaStream_t st) {
+    switch (A.sc.s) {
+        case 0: return launch_fill_systolic_na_s0(A, grid, G, smem, trace, pad, st);
+        case 1: return launch_fill_systolic_na_s1(A, grid, G, smem, trace, pad, st);
+        case 2: return launch_fill_systolic_na_s2(A, grid, G, smem, trace, pad, st);
+        case 3: return launch_fill_systolic_na_s3(A, grid, G, smem, trace, pad, st);
+        case 4: return launch_fill_systolic_na_s4(A, grid, G, smem, trace, pad, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -16,4 +16,8 @@ cudaError_t launch_fill_systolic_p16_s0(const SysArgs& A, int grid, int G, size_
     return sys::launch_p16_t<0>(A, grid, G, smem, st);
 }
 int sys_occupancy_p16_s0(int G, size_t smem) { return sys::occ_p16_t<0>(G, smem); }
+cudaError_t launch_fill_systolic_na_s0(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, cudaStream_t st) {
+    return sys::launch_na_s<0>(A, grid, G, smem, trace, pad, st);
+}
+int sys_occupancy_na_s0(bool trace, bool pad, int G, size_t smem) { return sys::occ_na_s<0>(trace, pad, G, smem); }
 }  // namespace ba

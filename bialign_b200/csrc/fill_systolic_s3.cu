@@ -16,4 +16,8 @@ cudaError_t launch_fill_systolic_p16_s3(const SysArgs& A, int grid, int G, size_
     return sys::launch_p16_t<3>(A, grid, G, smem, st);
 }
 int sys_occupancy_p16_s3(int G, size_t smem) { return sys::occ_p16_t<3>(G, smem); }
+cudaError_t launch_fill_systolic_na_s3(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, cudaStream_t st) {
+    return sys::launch_na_s<3>(A, grid, G, smem, trace, pad, st);
+}
+int sys_occupancy_na_s3(bool trace, bool pad, int G, size_t smem) { return sys::occ_na_s<3>(trace, pad, G, smem); }
 }  // namespace ba

@@ -30,6 +30,7 @@ struct SysArgs {
     Scoring sc;               // unscaled, for s / nsym
     int w_p, beta_p;          // structure weight, gap opening (scaled, shifted)
     int k_gd, k_2g, k_2g2d, k_2d;  // gamma+Delta, 2*gamma, 2*gamma+2*Delta, 2*Delta (scaled, shifted)
+    int k_d;                  // Delta (scaled, shifted): half-match columns of the non-affine model
     int negp;                 // "minus infinity" in the packed domain
     int tb_bits;              // low bits reserved for the tie-break (0 when score-only)
     int gscale;               // gcd the scores were divided by
@@ -78,6 +79,8 @@ int sys_occupancy(int S, bool trace, bool pad, bool bneg, int G, size_t smem);
 int sys_boff(int S, bool pad, int G);
 int sys_bpad(int S, bool pad, int G, int mmax);
 cudaError_t launch_fill_systolic(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, bool bneg, cudaStream_t st);
+int sys_occupancy_na(int S, bool trace, bool pad, int G, size_t smem);
+cudaError_t launch_fill_systolic_na(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, cudaStream_t st);
 int sys_occupancy_long(int S, bool trace, bool pad, int G, size_t smem);
 cudaError_t launch_fill_systolic_long(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, cudaStream_t st);
 

@@ -60,7 +60,8 @@ typedef struct ba_stats {
     int64_t code_bytes;       /* traceback-code bytes written to HBM                             */
     int32_t kernel_kind;      /* 0 = generic level kernel, 1 = systolic pad-free, 2 = systolic padded,
                                  3 / 4 = the same two in multi-CTA long-pair mode,
-                                 5 = systolic pad-free, two pairs per lane in packed 16-bit halves */
+                                 5 = systolic pad-free, two pairs per lane in packed 16-bit halves,
+                                 6 / 7 = systolic pad-free / padded running the non-affine model   */
     int32_t device;
     int32_t warps_per_cta;    /* CTA width the systolic kernel ran with (0 for the general kernel)      */
     int32_t reserved;

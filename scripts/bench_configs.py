@@ -37,7 +37,7 @@ def run(name, al, res, cls, off, pa, pb, want_trace, reps=3):
 
 
 def main():
-    which = sys.argv[1:] or ["1", "2", "3", "4", "5"]
+    which = sys.argv[1:] or ["1", "2", "3", "4", "5", "na"]
     prot = workloads.PROTEIN_PARAMS
     if "1" in which:
         seqs = ["RAKLPLKEKKLTATANYHPGIRYIMTGYSAKYIYSSTYARFR", "KAKLPLKEKKLTRTANYHPGIRYIMTGYSAKRIYSSTYAYFR"]
@@ -61,6 +61,16 @@ def main():
         res, cls, off, pa, pb = workloads.rna_pairs(125000, seed=4)
         run("cfg4 125k RNA pairs len 120 s=2 score-only", al, res, cls, off, pa, pb, False)
         run("cfg4 125k RNA pairs len 120 s=2 trace", al, res, cls, off, pa, pb, True)
+    if "na" in which:
+        na = dict(prot, gap_opening_cost=0, gap_cost=-200, shift_cost=-250)
+        al = BatchAligner(max_shift=2, **na)
+        res, cls, off, pa, pb = workloads.protein_pairs(3000, seed=3)
+        run("non-affine: 3000 protein pairs 200-500 s=2 trace", al, res, cls, off, pa, pb, True)
+        run("non-affine: 3000 protein pairs 200-500 s=2 score-only", al, res, cls, off, pa, pb, False)
+        al.engine.set_option("kernel", 0)
+        res, cls, off, pa, pb = workloads.protein_pairs(64, seed=3)
+        run("non-affine, general level kernel: 64 pairs trace", al, res, cls, off, pa, pb, True, reps=1)
+        al.engine.set_option("kernel", -1)
     if "5" in which:
         al = BatchAligner(max_shift=3, **prot)
         res, cls, off, pa, pb = workloads.protein_pairs(1, lo=8192, hi=8192, seed=5)

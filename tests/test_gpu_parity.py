@@ -466,3 +466,31 @@ def test_tie_storms_at_multipass_sizes(variant):
         assert _check_batch(al, seqs, structs, pairs, params, table_pairs=3) in (1, 2)  # CTA-per-pair mode
     finally:
         _unselect(al.engine)
+
+
+@pytest.mark.parametrize("kernel", [0, 1, 2])
+@pytest.mark.parametrize("s", [0, 1, 2, 3, 4])
+def test_nonaffine_model_vs_oracle(s, kernel):
+    """gap_opening_cost == 0 (the CLI default): level kernel and both systolic flavours against the oracle's literal
+    restatement of pyx:443-471 / 513-531 -- scores and first-case-wins traces, ragged multi-pass batch."""
+    from bialign_b200.batch import trace_hex
+
+    rng = np.random.default_rng(2300 + s)
+    for var in ({}, {"shift_cost": 0}, {"gap_cost": 0, "structure_weight": 0}):
+        params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=0, gap_cost=-200,
+                      shift_cost=-250, max_shift=s)
+        params.update(var)
+        seqs, structs, pairs = _random_protein_batch(rng, 8, 1, 110)
+        al = _aligner(params)
+        _select(al.engine, kernel)
+        try:
+            scores, cols, offsets, complete = al.align(seqs, structs, pairs, want_trace=True)
+            kind = al.engine.stats()["kernel_kind"]
+            assert kind == (0 if kernel == 0 else 5 + kernel)
+            for q, (ia, ib) in enumerate(pairs):
+                r = oracle.run(seqs[ia], seqs[ib], structs[ia], structs[ib], params)
+                assert int(scores[q]) == r["score"], (q, var)
+                assert trace_hex(cols, offsets, q) == r["trace"], (q, var)
+            assert (al.align(seqs, structs, pairs, want_trace=False) == scores).all()
+        finally:
+            _unselect(al.engine)
