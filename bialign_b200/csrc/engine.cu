@@ -4,8 +4,11 @@
 //   res/cls     concatenated uint8 residue codes / structure classes of the sequence table
 //   sim         nsym x nsym int32 similarity table
 //   desc        PairDesc per pair, sorted by decreasing cost (LPT order inside the device)
-//   codes       traceback-code arena: one uint64 per band cell, nibble t = winning case of state t;
+//   codes       traceback-code arena: one uint64 per band cell (level kernel: nibble t = winning case of state t;
+//               systolic kernel: 5-bit tie field per state; non-affine: case index in the low nibble);
 //               pairs are processed in waves that fit the arena, traceback runs per wave
+//   bnd         systolic kernel: boundary streams between row blocks (per CTA, or 2 * grid in long-pair mode)
+//   code_dump   per-CTA strips where lanes outside a pair stream their code words
 //   trace       one slot of 2(n+m)+2 bytes per pair, columns written backwards by the traceback
 //   scores/start_state/end_values/trace_len/complete   per pair, caller order
 #include <algorithm>
