@@ -56,22 +56,29 @@ def rna_pairs(npairs, length=120, seed=4):
     nseq = 2 * npairs
     res = rng.integers(0, 4, size=nseq * length).astype(np.uint8)
     u = rng.random(size=(nseq, length))
+    # stack process per sequence (open p=.3; close p=.3 if the innermost open is >= 3 back; else '.'), run for all
+    # sequences in lock step: one vectorised update per position
+    partner = np.full((nseq, length), -1, dtype=np.int32)
+    stack = np.zeros((nseq, length), dtype=np.int32)
+    sp = np.zeros(nseq, dtype=np.int32)
+    rows = np.arange(nseq)
+    for i in range(length):
+        ui = u[:, i]
+        opening = ui < 0.3
+        top = stack[rows, np.maximum(sp - 1, 0)]
+        closing = (~opening) & (ui < 0.6) & (sp > 0) & (i - top >= 3)
+        ro = rows[opening]
+        stack[ro, sp[ro]] = i
+        rc = rows[closing]
+        jc = top[closing]
+        partner[rc, i] = jc
+        partner[rc, jc] = i
+        sp += opening.astype(np.int32) - closing.astype(np.int32)
+    pos = np.arange(length, dtype=np.int32)[None, :]
+    paired = partner >= 0
     cls = np.zeros((nseq, length), dtype=np.uint8)
-    # stack process per sequence (open p=.3; close p=.3 if the innermost open is >= 3 back; else '.')
-    for q in range(nseq):
-        stack = []
-        row = u[q]
-        partner = np.zeros(length, dtype=np.int64) - 1
-        for i in range(length):
-            if row[i] < 0.3:
-                stack.append(i)
-            elif row[i] < 0.6 and stack and i - stack[-1] >= 3:
-                j = stack.pop()
-                partner[i], partner[j] = j, i
-        paired = partner >= 0
-        pos = np.arange(length)
-        cls[q, paired & (partner <= pos - 2)] = encoding.UP
-        cls[q, paired & (partner >= pos + 1)] = encoding.DOWN
+    cls[paired & (partner <= pos - 2)] = encoding.UP
+    cls[paired & (partner >= pos + 1)] = encoding.DOWN
     off = (np.arange(nseq + 1) * length).astype(np.int64)
     pa = np.arange(0, nseq, 2, dtype=np.int32)
     return res, cls.reshape(-1), off, pa, pa + 1

@@ -217,3 +217,14 @@ def test_header_is_valid_c_and_links(tmp_path):
                            "-L", libdir, "-l:libbialign_b200.so", "-Wl,-rpath," + libdir])
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and "bialign_b200" in out.stdout
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    """No fallback: without the built CUDA library the loader raises (and says how to build it)."""
+    from bialign_b200 import _capi
+
+    monkeypatch.setattr(_capi, "_lib", None)
+    monkeypatch.setattr(_capi, "LIB_PATH", "/nonexistent/libbialign_b200.so")
+    with pytest.raises(ImportError) as ei:
+        _capi.load_library()
+    assert "no CPU implementation" in str(ei.value)
