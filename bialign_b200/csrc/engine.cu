@@ -555,6 +555,9 @@ int ba_run(ba_engine* e, int want_trace) {
                 if (sysG == 0 || cost < best * 0.97) { best = cost; sysG = G; }  // prefer the narrower CTA on near-ties
             }
             if (sysG == 0) sysG = 2;
+            // a handful of long pairs will run in long-pair mode, where the pipeline fill (CTAs x lag) matters as much
+            // as the per-CTA rate: 4 warps measured best on both the 928 x 933 and the 8192 x 8192 pair
+            if (N <= 4 && affine && !p16 && e->opt_long != 0 && (nmax + 1) > 8 * 4 * geo.R) sysG = std::max(4, (18 * geo.LPR + 31) / 32);
         }
         // one boundary-record element per thread: a CTA needs at least 18 * LPR threads
         sysG = std::max(sysG, (18 * sys_geo(s, plan.pad).LPR + 31) / 32);

@@ -22,6 +22,11 @@ for G in range(2, 9):
     elif which == "3":
         al = BatchAligner(max_shift=2, **workloads.PROTEIN_PARAMS)
         args = workloads.protein_pairs(3000, seed=3) + (True,)
+    elif which == "2":
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", "dnapol1.json")))
+        al = BatchAligner(**g["params"])
+        res, cls, off = al.encode([g["seqA"], g["seqB"]], [g["strA"], g["strB"]])
+        args = (res, cls, off, np.array([0], np.int32), np.array([1], np.int32), True)
     else:
         al = BatchAligner(max_shift=3, **workloads.PROTEIN_PARAMS)
         args = workloads.protein_pairs(1, lo=8192, hi=8192, seed=5) + (True,)
