@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -114,7 +115,6 @@ struct ba_engine {
     bool have_tlen = false;
 
     int64_t opt_code_arena_bytes = 0;  // 0 = auto
-    int64_t arena_from_option = 0;     // option value the current arena was sized with
     bool arena_is_budget = false;      // current arena = the full memory budget (not just "all pairs fit")
     int opt_kernel = -1;               // -1 auto
     ba_stats stats{};
@@ -443,20 +443,22 @@ int ba_run(ba_engine* e, int want_trace) {
         }
         // The arena is sticky: once allocated it is reused as long as the largest pair fits (a 90 GB
         // cudaFree + cudaMalloc costs tens of milliseconds and free memory drifts from run to run).
-        if ((int64_t)e->d_codes.cap >= max_words && (e->opt_code_arena_bytes <= 0 || e->arena_from_option == e->opt_code_arena_bytes) &&
-            ((int64_t)e->d_codes.cap >= total_words || e->arena_is_budget)) {
-            arena_words = (size_t)std::min<int64_t>((int64_t)e->d_codes.cap, total_words);
+        // An explicit "code_arena_bytes" is an upper bound on what a wave may use (at least one pair always fits).
+        const int64_t limit_words = e->opt_code_arena_bytes > 0 ? std::max<int64_t>(e->opt_code_arena_bytes / 8, max_words)
+                                                                 : std::numeric_limits<int64_t>::max();
+        const int64_t want_words = std::min(total_words, limit_words);
+        if ((int64_t)e->d_codes.cap >= max_words &&
+            ((int64_t)e->d_codes.cap >= want_words || (e->opt_code_arena_bytes <= 0 && e->arena_is_budget))) {
+            arena_words = (size_t)std::min<int64_t>((int64_t)e->d_codes.cap, want_words);
         } else {
-            int64_t budget_bytes = e->opt_code_arena_bytes;
-            if (budget_bytes <= 0) {
+            int64_t budget_words = limit_words;
+            if (e->opt_code_arena_bytes <= 0) {
                 size_t fr = 0, tot = 0;
                 CU(cudaMemGetInfo(&fr, &tot));
-                budget_bytes = (int64_t)(fr + e->d_codes.cap * 8) / 2;
+                budget_words = std::max<int64_t>((int64_t)(fr + e->d_codes.cap * 8) / 2 / 8, max_words);
             }
-            int64_t budget_words = std::max<int64_t>(budget_bytes / 8, max_words);
             arena_words = (size_t)std::min(budget_words, total_words);
-            e->arena_is_budget = budget_words <= total_words;
-            e->arena_from_option = e->opt_code_arena_bytes;
+            e->arena_is_budget = e->opt_code_arena_bytes <= 0 && budget_words <= total_words;
         }
         cudaError_t ce = e->d_codes.ensure(arena_words);
         if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "traceback-code arena: " + std::string(cudaGetErrorString(ce)));

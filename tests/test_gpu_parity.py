@@ -494,3 +494,32 @@ def test_nonaffine_model_vs_oracle(s, kernel):
             assert (al.align(seqs, structs, pairs, want_trace=False) == scores).all()
         finally:
             _unselect(al.engine)
+
+
+def test_many_waves_with_a_tiny_code_arena():
+    """A traceback-code arena far smaller than the batch forces many waves (fill + traceback per wave); results must
+    not depend on the wave structure."""
+    from bialign_b200.batch import trace_hex
+
+    rng = np.random.default_rng(4242)
+    params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150, gap_cost=-50,
+                  shift_cost=-150, max_shift=2)
+    seqs, structs, pairs = _random_protein_batch(rng, 40, 40, 120)
+    al = _aligner(params)
+    ref_scores, ref_cols, ref_off, _ = al.align(seqs, structs, pairs, want_trace=True)
+    assert al.engine.stats()["waves"] == 1
+    try:
+        for kernel in (1, 0):
+            al.engine.set_option("kernel", kernel)
+            al.engine.set_option("code_arena_bytes", 3 << 20)  # ~ 2-3 pairs per wave
+            scores, cols, offsets, complete = al.align(seqs, structs, pairs, want_trace=True)
+            assert al.engine.stats()["waves"] >= 10
+            assert (scores == ref_scores).all() and complete.all()
+            assert all(trace_hex(cols, offsets, q) == trace_hex(ref_cols, ref_off, q) for q in range(len(pairs)))
+    finally:
+        al.engine.set_option("code_arena_bytes", 0)
+        _unselect(al.engine)
+    for q in (0, 7, 39):
+        ia, ib = pairs[q]
+        r = oracle.run(seqs[ia], seqs[ib], structs[ia], structs[ib], params, mode="codes")
+        assert int(ref_scores[q]) == r["score"] and trace_hex(ref_cols, ref_off, q) == r["trace"]
