@@ -217,14 +217,18 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
 
     // per-lane source bases inside the ring array (in ints): U sources sit one row up, W one lane left
     const int own_ring = (g + 1) * RING * RSLOT;
-    const int up_ring = row0 ? g * RING * RSLOT + R * LPR : own_ring;  // row 0 reads the last row of the warp above
-    const int baseU0 = up_ring + lane - LPR;                           // source lane for x0=1,x2=1 (same column)
-    const int baseU1 = up_ring + lane - (LPR - 1);                     // x0=1,x2=0 (column + 1)
+    // The 32 - R*LPR idle lanes behind the last row shadow lane 0's ring loads (same addresses = a broadcast).  With
+    // their own lane index they would hit the banks of row 0's loads from the warp above: a 2-way conflict on the six
+    // loads that head the iteration's dependency chain (measured: 648 -> 666 GCUPS on config 3).
+    const int alane = (r >= R) ? 0 : lane;
+    const int up_ring = (row0 || r >= R) ? g * RING * RSLOT + R * LPR : own_ring;  // row 0 reads the last row of the warp above
+    const int baseU0 = up_ring + alane - LPR;                          // source lane for x0=1,x2=1 (same column)
+    const int baseU1 = up_ring + alane - (LPR - 1);                    // x0=1,x2=0 (column + 1)
     // lane 0 has no left neighbour; lane 31 is a pad or idle lane (PAD) or lane 0's W inputs are poisoned
     // (!PAD), so lane 0 simply reads lane 31 (no special case in the loop)
     const int lsrcW = (lane == 0) ? 31 : lane - 1;
-    const int baseW = own_ring + lsrcW;                                // x0=0,x2=1
-    const int baseS = own_ring + lane;                                 // self
+    const int baseW = own_ring + ((alane == 0) ? 31 : alane - 1);      // x0=0,x2=1
+    const int baseS = own_ring + alane;                                // self
     // the same as shared-memory byte addresses: slot * RSLOT * 4 is then the only per-iteration address arithmetic
     const unsigned rU0 = smem_u32(ring + baseU0), rU1 = smem_u32(ring + baseU1), rW = smem_u32(ring + baseW), rS = smem_u32(ring + baseS);
     const int xs_in = g * 4 * NX * LPR;                                // xs block feeding this warp's row 0
