@@ -98,6 +98,20 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
 }
+// Predicated forms (no branch, so no divergence bookkeeping in the iteration loop and the compiler is free to move the
+// feeding loads away from the store): the operation happens iff c.
+__device__ __forceinline__ void stg32_if(void* p, int v, bool c) {
+    asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %2, 0;\n @pp st.global.b32 [%0], %1;\n}\n" ::"l"(p), "r"(v), "r"((int)c) : "memory");
+}
+__device__ __forceinline__ void stg64_if(void* p, unsigned lo, unsigned hi, bool c) {
+    asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %3, 0;\n @pp st.global.v2.b32 [%0], {%1, %2};\n}\n" ::"l"(p), "r"(lo), "r"(hi), "r"((int)c) : "memory");
+}
+__device__ __forceinline__ void sts32_if(unsigned addr, int v, bool c) {
+    asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %2, 0;\n @pp st.shared.s32 [%0], %1;\n}\n" ::"r"(addr), "r"(v), "r"((int)c) : "memory");
+}
+__device__ __forceinline__ void cp_async4s_if(unsigned smem_dst, const void* gsrc, bool c) {
+    asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %2, 0;\n @pp cp.async.ca.shared.global [%0], [%1], 4;\n}\n" ::"r"(smem_dst), "l"(gsrc), "r"((int)c) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
@@ -301,7 +315,11 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
             const unsigned long long tag_out = (unsigned long long)(pass + 1) << 32;
             // boundary I/O descriptors: thread e moves record element e (= v*LPR + cs) every iteration
             const bool io_thread = tid < REAL;
-            const int io_v = tid / LPR, io_cs = tid - io_v * LPR;
+            // Threads beyond the record shadow element 0 for the (harmless) loads; their stores and copies are predicated off.
+            // (Letting them duplicate thread 0's work instead, which makes all of this thread-independent, measured 5 % slower:
+            // the fourth warp skipping the boundary I/O matters more than the divergence bookkeeping.)
+            const int io_e = io_thread ? tid : 0;
+            const int io_v = io_e / LPR, io_cs = io_e - io_v * LPR;
             const bool io_ring = io_v < NV;
             const int io_stride = io_ring ? RSLOT : NX * LPR;
             const int io_col = io_ring ? io_v * 32 + (R - 1) * LPR + io_cs
@@ -327,9 +345,9 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                     lg_dst[u] = smem_u32(smem + (rg ? v * 32 + (R - 1) * LPR + cs : (int)((G + 1) * RING * RSLOT) + (v - NV) * LPR + cs));
                 }
             }
-            int* fl_g = bnd_out + tid;                                                   // record q-1 of iteration q = -PRE
-            const int* st_g = bnd_in + (size_t)(2 * RT + LA + 1) * REC + tid;            // record (q + LA + 2RT) of q = -PRE
-            const unsigned fl_s = smem_u32(smem + fl_src), st_s = smem_u32(smem + st_dst), pb_s = smem_u32(pb + tid);
+            int* fl_g = bnd_out + io_e;                                                  // record q-1 of iteration q = -PRE
+            const int* st_g = bnd_in + (size_t)(2 * RT + LA + 1) * REC + io_e;           // record (q + LA + 2RT) of q = -PRE
+            const unsigned fl_s = smem_u32(smem + fl_src), st_s = smem_u32(smem + st_dst), pb_s = smem_u32(pb + io_e);
             const int io_stride_b = io_stride * 4;
             const int q_rec_lim = nit - 2 * RT;                                          // records beyond are "minus infinity"
             // iteration at which this lane sits on the origin / on the end cell (INT_MIN: never)
@@ -429,7 +447,7 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                 // ---- flush the CTA's last row of iteration q-1 to the outgoing boundary stream
                 {
                     const int ps = RP2 ? ((q - 1) & (RING - 1)) : ((wslot == 0) ? RING - 1 : wslot - 1);
-                    if (do_flush) *fl_g = lds32(fl_s + (io_ring ? ps : ((q - 1) & 3)) * io_stride_b);
+                    stg32_if(fl_g, lds32(fl_s + (io_ring ? ps : ((q - 1) & 3)) * io_stride_b), do_flush);
                     fl_g += REC;
                 }
 
@@ -600,8 +618,7 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                 if (TRACE && NA) {
                     // the cell's single traceback code: case index of the best state (value desc, case order asc)
                     const int bestp = vmax3(vmax3(M[0], M[1], M[2]), vmax3(M[3], M[4], M[5]), vmax3(M[6], M[7], M[8]));
-                    if ((unsigned)j <= (unsigned)m && (P == W || bb < W))
-                        *reinterpret_cast<uint2*>(code_ptr + j * W + bb) = make_uint2(15u - (unsigned)(bestp & 15), 0u);
+                    stg64_if(code_ptr + j * W + bb, 15u - (unsigned)(bestp & 15), 0u, (unsigned)j <= (unsigned)m && (P == W || bb < W));
                     const int msk = ~((1 << TB) - 1);
 #pragma unroll
                     for (int t = 0; t < 9; ++t) M[t] &= msk;  // as a source a state carries no tie information
@@ -611,8 +628,7 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                     const unsigned hi = (M[6] & 31) | ((M[7] & 31) << 5) | ((M[8] & 31) << 10);
                     // cells of a valid column always lie inside this lane's code row (those with l outside the pair
                     // are unused slots); pad cells (P > W) would spill into the next column and are skipped
-                    if ((unsigned)j <= (unsigned)m && (P == W || bb < W))
-                        *reinterpret_cast<uint2*>(code_ptr + j * W + bb) = make_uint2(lo, hi);
+                    stg64_if(code_ptr + j * W + bb, lo, hi, (unsigned)j <= (unsigned)m && (P == W || bb < W));
                     // table layout [source state][b][lane column]: for one source state the lanes of a warp read
                     // (at most P*LPR <= 32) consecutive words -> no bank conflicts
                     const int* tp = tbtab + bb * LPR + c;
@@ -703,11 +719,11 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                     cp_async_commit();
                 } else if (has_in) {
                     cp_async_wait<LA - 1>();
-                    if (do_stage) {
+                    {
                         int val = lds32(pb_s + (q & (PB - 1)) * (REC * 4));
                         val = (q < q_rec_lim) ? val : NEGP;
-                        sts32(st_s + (io_ring ? wslot : (q & 3)) * io_stride_b, val);
-                        if (q + LA < q_rec_lim) cp_async4s(pb_s + ((q + LA) & (PB - 1)) * (REC * 4), st_g);
+                        sts32_if(st_s + (io_ring ? wslot : (q & 3)) * io_stride_b, val, do_stage);
+                        cp_async4s_if(pb_s + ((q + LA) & (PB - 1)) * (REC * 4), st_g, do_stage && q + LA < q_rec_lim);
                     }
                     st_g += REC;
                     cp_async_commit();
