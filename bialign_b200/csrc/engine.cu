@@ -28,7 +28,7 @@
 using namespace ba;
 
 namespace {
-std::string g_create_error;
+thread_local std::string g_create_error;  // ba_engine_create failures have no engine to hold the text
 
 template <class T>
 struct DevBuf {
@@ -290,11 +290,19 @@ const char* ba_last_error(const ba_engine* e) { return e ? e->err.c_str() : g_cr
 
 int ba_set_option(ba_engine* e, const char* key, int64_t value) {
     if (!e || !key) return BA_ERR_INVALID_ARG;
-    if (!strcmp(key, "code_arena_bytes")) e->opt_code_arena_bytes = value;
-    else if (!strcmp(key, "kernel")) e->opt_kernel = (int)value;
-    else if (!strcmp(key, "pad")) e->opt_pad = (int)value;
-    else if (!strcmp(key, "long")) e->opt_long = (int)value;
-    else if (!strcmp(key, "p16")) e->opt_p16 = (int)value;
+    auto tri = [&](int* dst) {  // -1 auto, 0 off, 1 force
+        if (value < -1 || value > 1) return fail(e, BA_ERR_INVALID_ARG, std::string(key) + " must be -1 (auto), 0 or 1");
+        *dst = (int)value;
+        return (int)BA_OK;
+    };
+    if (!strcmp(key, "code_arena_bytes")) {
+        if (value < 0) return fail(e, BA_ERR_INVALID_ARG, "code_arena_bytes must be >= 0 (0 = auto)");
+        e->opt_code_arena_bytes = value;
+    }
+    else if (!strcmp(key, "kernel")) return tri(&e->opt_kernel);
+    else if (!strcmp(key, "pad")) return tri(&e->opt_pad);
+    else if (!strcmp(key, "long")) return tri(&e->opt_long);
+    else if (!strcmp(key, "p16")) return tri(&e->opt_p16);
     else if (!strcmp(key, "warps_per_cta")) {
         if (value < 0 || value > 8) return fail(e, BA_ERR_INVALID_ARG, "warps_per_cta must be in 0..8 (0 = auto)");
         e->opt_warps = (int)value;
@@ -328,8 +336,11 @@ int ba_load_sequences(ba_engine* e, const uint8_t* residues, const uint8_t* clas
                       int64_t n_seq) {
     if (!e) return BA_ERR_INVALID_ARG;
     if (!offsets || n_seq < 0) return fail(e, BA_ERR_INVALID_ARG, "offsets is NULL or n_seq < 0");
-    for (int64_t q = 0; q < n_seq; ++q)
+    for (int64_t q = 0; q < n_seq; ++q) {
         if (offsets[q + 1] < offsets[q] || offsets[q] < 0) return fail(e, BA_ERR_INVALID_ARG, "offsets not monotone");
+        if (offsets[q + 1] - offsets[q] > BA_MAX_SEQ_LEN)
+            return fail(e, BA_ERR_INVALID_ARG, "sequence " + std::to_string(q) + " is longer than BA_MAX_SEQ_LEN");
+    }
     const int64_t total = n_seq ? offsets[n_seq] : 0;
     if (total > 0 && (!residues || !classes)) return fail(e, BA_ERR_INVALID_ARG, "residues/classes NULL");
     if (total - (n_seq ? offsets[0] : 0) > (int64_t)1 << 40) return fail(e, BA_ERR_INVALID_ARG, "sequence table too large");

@@ -46,6 +46,7 @@ extern "C" {
 
 #define BA_MAX_SHIFT 16         /* largest band half-width accepted (general level kernel)          */
 #define BA_SYSTOLIC_MAX_SHIFT 4 /* the fast systolic kernels are instantiated for max_shift 0..4    */
+#define BA_MAX_SEQ_LEN (1 << 24) /* longest single sequence accepted by ba_load_sequences             */
 
 typedef struct ba_engine ba_engine;
 

@@ -352,6 +352,19 @@ def test_error_codes_range_and_alphabet():
     with pytest.raises(_capi.BialignError) as ei:  # pair index outside the sequence table
         ok.align_encoded(res[:2], np.zeros(2, np.uint8), np.array([0, 1, 2], np.int64), np.array([0], np.int32), np.array([7], np.int32))
     assert ei.value.code == _capi.BA_ERR_INVALID_ARG
+    for key, bad in [("kernel", 2), ("pad", -2), ("long", 5), ("p16", 2), ("warps_per_cta", 9), ("code_arena_bytes", -1),
+                     ("no_such_option", 0)]:
+        with pytest.raises(_capi.BialignError) as ei:
+            ok.engine.set_option(key, bad)
+        assert ei.value.code == _capi.BA_ERR_INVALID_ARG, key
+    with pytest.raises(_capi.BialignError) as ei:  # offsets that are not monotone
+        ok.align_encoded(res[:2], np.zeros(2, np.uint8), np.array([0, 2, 1], np.int64), np.array([0], np.int32), np.array([1], np.int32))
+    assert ei.value.code == _capi.BA_ERR_INVALID_ARG
+    # the engine is still usable after the rejected calls
+    params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150, gap_cost=-50,
+                  shift_cost=-150, max_shift=1)
+    want = oracle.run("ACDW", "ACW", "HHHC", "HHC", params, mode="codes")["score"]
+    assert ok.align(["ACDW", "ACW"], ["HHHC", "HHC"], [(0, 1)], want_trace=False).tolist() == [want]
 
 
 @pytest.mark.parametrize("s", [0, 1, 2, 3, 4])
