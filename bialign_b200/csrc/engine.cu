@@ -472,6 +472,14 @@ int ba_run(ba_engine* e, int want_trace) {
             e->arena_is_budget = e->opt_code_arena_bytes <= 0 && budget_words <= total_words;
         }
         cudaError_t ce = e->d_codes.ensure(arena_words);
+        // automatic sizing only: a failed allocation (fragmentation, another tenant on the GPU) is retried with half
+        // the arena, i.e. more waves, down to the largest single pair
+        while (ce == cudaErrorMemoryAllocation && e->opt_code_arena_bytes <= 0 && (int64_t)arena_words > max_words) {
+            cudaGetLastError();  // clear the sticky allocation error
+            arena_words = (size_t)std::max<int64_t>((int64_t)arena_words / 2, max_words);
+            e->arena_is_budget = true;
+            ce = e->d_codes.ensure(arena_words);
+        }
         if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "traceback-code arena: " + std::string(cudaGetErrorString(ce)));
     }
     {
