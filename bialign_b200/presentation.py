@@ -4,7 +4,6 @@ files.  Behavioural spec: src/bialignment.pyx:835-950 and src/bialignment_nonpyx
 reference; written from that behaviour, not from its text."""
 import sys
 from collections import defaultdict
-from math import sqrt
 
 import numpy as np
 

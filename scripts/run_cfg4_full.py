@@ -1,7 +1,6 @@
 #!/usr/bin/env python3
 """BASELINE config 4 at full size on one GPU: 1 000 000 RNA pairs of length 120, score only."""
 import os, sys, time
-import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from bialign_b200 import workloads

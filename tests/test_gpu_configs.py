@@ -6,7 +6,6 @@ import hashlib
 import json
 import os
 
-import numpy as np
 import pytest
 
 import oracle

@@ -1,6 +1,5 @@
 """CPU tests of the host side: C-ABI export list, encoders, scheduler arithmetic, presentation layer
 (against rows recorded from the unmodified reference).  No GPU, no compute calls into the library."""
-import ctypes
 import io
 import contextlib
 import os
