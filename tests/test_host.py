@@ -227,3 +227,26 @@ def test_missing_library_fails_loudly(monkeypatch):
     with pytest.raises(ImportError) as ei:
         _capi.load_library()
     assert "no CPU implementation" in str(ei.value)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's own CPU path from oracle/_ref, or the C port): one JSON line with the
+    contract keys on rank 0, nothing (exit 0) on the other ranks of a torchrun launch.  No GPU involved."""
+    import json
+    import subprocess
+    import sys
+
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--pairs-per-gpu", "64"]
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    other = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert other.returncode == 0 and other.stdout.strip() == ""
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-400:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "GCUPS" and line["higher_is_better"] is True
+    assert line["metric"] == "batched bialign GCUPS (cell-states/s)" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"] and "sample" in line["cpu_baseline"]
+    assert line["e2e"] == {"value": line["value"], "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["workload"].startswith("cfg3") and line["vs_baseline"] is None
