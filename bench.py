@@ -232,7 +232,7 @@ def main():
     os.environ["BIALIGN_DEVICE"] = str(local_rank)
     al = BatchAligner(device=local_rank, **params)
     if args.warps:
-        al.engine.set_option("warps_per_cta", args.warps)
+        al.set_option("warps_per_cta", args.warps)
     lens = np.diff(off)
     mine = lpt_shards(pair_cost(lens[pa], lens[pb], MAX_SHIFT), world)[rank]
     total_cs = int(cell_states_of(off, pa, pb, MAX_SHIFT).sum())

@@ -13,7 +13,10 @@ BA_OK, BA_ERR_INVALID_ARG, BA_ERR_NO_DEVICE, BA_ERR_CUDA, BA_ERR_OOM, BA_ERR_SCO
 SYMBOLS = ["ba_engine_create", "ba_engine_destroy", "ba_last_error", "ba_set_scoring", "ba_load_sequences",
            "ba_load_pairs", "ba_run", "ba_fetch_scores", "ba_trace_bytes", "ba_fetch_traces", "ba_align_batch",
            "ba_get_stats", "ba_set_option", "ba_debug_fetch_codes", "ba_debug_fetch_end_values", "ba_microbench_int",
-           "ba_version"]
+           "ba_version", "ba_engine_create_multi", "ba_engine_device_count"]
+
+
+ENGINE_OPTIONS = {"kernel": -1, "pad": -1, "long": -1, "p16": -1, "warps_per_cta": 0, "code_arena_bytes": 0}
 
 
 class BaStats(ctypes.Structure):
@@ -43,6 +46,8 @@ def load_library():
     L = ctypes.CDLL(LIB_PATH)
     vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
     L.ba_engine_create.argtypes = [i32, ctypes.POINTER(vp)]
+    L.ba_engine_create_multi.argtypes = [vp, i32, ctypes.POINTER(vp)]
+    L.ba_engine_device_count.argtypes = [vp]
     L.ba_engine_destroy.argtypes = [vp]
     L.ba_engine_destroy.restype = None
     L.ba_last_error.argtypes = [vp]
@@ -70,16 +75,23 @@ def _ptr(a):
 
 
 class Engine:
-    """One engine per process per GPU (thin RAII wrapper of ba_engine)."""
+    """Thin RAII wrapper of ba_engine: one GPU (`device`), or several GPUs of the box behind one handle
+    (`devices` = list of CUDA ordinals, or "all").  Calls on one engine must not overlap (one thread at a time)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
         self._L = load_library()
         h = ctypes.c_void_p()
-        rc = self._L.ba_engine_create(int(device), ctypes.byref(h))
+        if devices is not None:
+            ids = None if devices == "all" else np.ascontiguousarray(list(devices), dtype=np.int32)
+            rc = self._L.ba_engine_create_multi(_ptr(ids) if ids is not None else None, 0 if ids is None else ids.size,
+                                                ctypes.byref(h))
+        else:
+            rc = self._L.ba_engine_create(int(device), ctypes.byref(h))
         if rc:
             raise BialignError(rc, self._L.ba_last_error(None).decode())
         self._h = h
-        self.device = int(device)
+        self.n_devices = int(self._L.ba_engine_device_count(h))
+        self.device = int(device) if devices is None else None
 
     def close(self):
         if getattr(self, "_h", None):
@@ -98,6 +110,13 @@ class Engine:
 
     def set_option(self, key, value):
         self._check(self._L.ba_set_option(self._h, key.encode(), int(value)))
+
+    def apply_options(self, options=None):
+        """Every tuning option back to automatic, then `options` (dict).  Engines are shared per device, so each
+        aligner calls this before it runs: settings of a previous user of the engine never leak into its alignments."""
+        options = options or {}
+        for key, auto in ENGINE_OPTIONS.items():
+            self.set_option(key, options.get(key, auto))
 
     def set_scoring(self, sim, structure_weight, gap_opening_cost, gap_cost, shift_cost, max_shift):
         sim = np.ascontiguousarray(sim, dtype=np.int32)
@@ -180,8 +199,14 @@ def microbench_int(device, kind):
 _engines = {}
 
 
-def get_engine(device=None):
-    """Process-wide engine for `device` (default: LOCAL_RANK, else 0)."""
+def get_engine(device=None, devices=None):
+    """Process-wide engine for one `device` (default: BIALIGN_DEVICE / LOCAL_RANK, else 0) or for a set of `devices`
+    (list of ordinals, or "all") behind one multi-GPU handle.  Shared: see BatchAligner for how options are scoped."""
+    if devices is not None:
+        key = "all" if devices == "all" else tuple(int(d) for d in devices)
+        if key not in _engines:
+            _engines[key] = Engine(devices=devices)
+        return _engines[key]
     if device is None:
         device = int(os.environ.get("BIALIGN_DEVICE", os.environ.get("LOCAL_RANK", "0")))
     if device not in _engines:

@@ -58,31 +58,46 @@ def lpt_shards(costs, world_size):
 
 
 class BatchAligner:
-    """Scores (and optionally traces) for a list of pairs under one scoring model."""
+    """Scores (and optionally traces) for a list of pairs under one scoring model.
+
+    Scoring arguments are the reference's (BiAligner's **params, pyx:179-193); anything else raises TypeError.
+    `device` = one CUDA ordinal (default: LOCAL_RANK); `devices` = a list of ordinals or "all": the pair list is
+    then sharded over those GPUs inside the library (one host thread per GPU, no collective).
+    Engines are shared per device within the process, so tuning options belong to the aligner (`set_option`) and are
+    applied -- all others reset to automatic -- each time it configures the engine; one thread at a time per engine."""
 
     def __init__(self, type="Protein", simmatrix=None, structure_weight=400, gap_opening_cost=0, gap_cost=-200,
                  shift_cost=-250, max_shift=2, sequence_match_similarity=100, sequence_mismatch_similarity=0,
-                 device=None, **_ignored):
+                 device=None, devices=None, nameA=None, nameB=None, outmode=None, nodescription=None):
+        # (nameA, nameB, outmode, nodescription: presentation parameters of the reference's param dict, unused here)
         self.type = type
         self.max_shift = int(max_shift)
         self.params = dict(structure_weight=int(structure_weight), gap_opening_cost=int(gap_opening_cost),
                            gap_cost=int(gap_cost), shift_cost=int(shift_cost), max_shift=int(max_shift))
+        self.known = None
         if simmatrix:
             matrix = encoding.read_simmatrix(simmatrix)
-            self.symbols, self.table, _ = encoding.simmatrix_table(matrix)
+            self.symbols, self.table, self.known = encoding.simmatrix_table(matrix)
         else:
             # match/mismatch scoring (pyx:409-412): residues are raw bytes, re-coded densely per batch
             self.symbols = None
             self._match = (int(sequence_match_similarity), int(sequence_mismatch_similarity))
             self.table = encoding.match_table(*self._match, nsym=4)
         self._device = device
+        self._devices = devices
         self._engine = None
+        self.options = {}
 
     @property
     def engine(self):
         if self._engine is None:
-            self._engine = get_engine(self._device)
+            self._engine = get_engine(self._device, self._devices)
         return self._engine
+
+    def set_option(self, key, value):
+        """Tuning option of this aligner (see ba_set_option); validated by the library right away."""
+        self.engine.set_option(key, value)
+        self.options[key] = int(value)
 
     def encode(self, seqs, structs):
         """Strings -> (residues, classes, offsets) of the C ABI."""
@@ -101,13 +116,32 @@ class BatchAligner:
             self.table = encoding.match_table(*self._match, nsym=max(len(used), 1))
         return res, cat(cls), np.array(off, dtype=np.int64)
 
+    def check_known(self, res, off, pair_a, pair_b):
+        """KeyError when a pair needs a residue combination the similarity matrix does not define -- what the reference's
+        dict-of-dicts lookup raises (pyx:407).  Only matrices with holes (sparse / asymmetric files) need the check."""
+        if self.known is None or self.known.all():
+            return
+        off = np.asarray(off)
+        nsym = self.known.shape[0]
+        present = np.zeros((len(off) - 1, nsym), dtype=bool)  # which symbols each sequence contains
+        seq_of = np.repeat(np.arange(len(off) - 1), np.diff(off))
+        present[seq_of, np.asarray(res)[off[0]:off[-1]]] = True
+        pa, pb = np.asarray(pair_a), np.asarray(pair_b)
+        for a, b in set(zip(pa.tolist(), pb.tolist())):
+            bad = present[a][:, None] & present[b][None, :] & ~self.known
+            if bad.any():
+                i, j = np.argwhere(bad)[0]
+                raise KeyError(self.symbols[j] if self.symbols[i] in self.symbols else self.symbols[i])
+
     def configure(self):
-        p = self.params
-        self.engine.set_scoring(self.table, p["structure_weight"], p["gap_opening_cost"], p["gap_cost"],
-                                p["shift_cost"], p["max_shift"])
+        eng, p = self.engine, self.params
+        eng.apply_options(self.options)  # options of whoever used the shared engine before do not leak in
+        eng.set_scoring(self.table, p["structure_weight"], p["gap_opening_cost"], p["gap_cost"],
+                        p["shift_cost"], p["max_shift"])
 
     def align_encoded(self, res, cls, off, pair_a, pair_b, want_trace=False):
         """End-to-end on host arrays.  Returns scores, or (scores, cols, offsets, complete)."""
+        self.check_known(res, off, pair_a, pair_b)
         self.configure()
         scores = self.engine.align_batch(res, cls, off, pair_a, pair_b, want_trace=want_trace)
         if not want_trace:
@@ -161,3 +195,40 @@ def gather_scores(mine, scores, n_total, device=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(full, op=dist.ReduceOp.SUM)  # shards are disjoint, so SUM == concatenation
     return full.cpu().numpy()
+
+
+def gather_traces(mine, cols, offsets, complete, n_total, device=None, dst=None):
+    """All ranks' traces in caller order: returns (cols uint8, offsets int64[n_total+1], complete uint8[n_total]).
+    `mine` = this rank's pair indices, (cols, offsets, complete) = what its engine returned for them.  Trace lengths
+    and flags travel like the scores (disjoint scatters, SUM); the columns are placed at their global positions in a flat
+    byte buffer that is then SUM-reduced -- supports are disjoint, so the sum is the concatenation.  With `dst` only
+    that rank receives the columns (torch.distributed.reduce); the others get an empty cols array."""
+    import torch
+    import torch.distributed as dist
+
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    mine = np.asarray(mine, dtype=np.int64)
+    offsets = np.asarray(offsets, dtype=np.int64)
+    lens = np.diff(offsets)
+    meta = torch.zeros((2, n_total), dtype=torch.int64, device=device)
+    idx = torch.as_tensor(mine, device=device)
+    meta[0, idx] = torch.as_tensor(lens, device=device)
+    meta[1, idx] = torch.as_tensor(np.asarray(complete, dtype=np.int64), device=device)
+    if multi:
+        dist.all_reduce(meta, op=dist.ReduceOp.SUM)
+    meta_h = meta.cpu().numpy()
+    goff = np.concatenate([[0], np.cumsum(meta_h[0])]).astype(np.int64)
+    total_local = int(offsets[-1] - offsets[0])
+    place = np.repeat(goff[mine] - offsets[:-1], lens) + np.arange(offsets[0], offsets[0] + total_local)
+    flat = torch.zeros(int(goff[-1]), dtype=torch.uint8, device=device)
+    if total_local:
+        flat[torch.as_tensor(place, device=device)] = torch.as_tensor(np.asarray(cols[offsets[0]:offsets[-1]]), device=device)
+    if multi:
+        if dst is None:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        else:
+            dist.reduce(flat, dst=dst, op=dist.ReduceOp.SUM)
+            if dist.get_rank() != dst:
+                flat = flat[:0]
+    return flat.cpu().numpy(), goff, meta_h[1].astype(np.uint8)
+

@@ -169,6 +169,7 @@ class BiAligner:
             raise IndexError("string index out of range")  # the reference's seq[-1] on an empty string (pyx:407)
         ra, rb, ca, cb, table = self._encoded()
         eng = get_engine()
+        eng.apply_options()  # the engine is shared per device: run with automatic settings whatever was set before
         eng.set_scoring(table, self._params["structure_weight"], self.beta, self.gamma, self._params["shift_cost"],
                         self.max_shift)
         res = np.concatenate([ra, rb]).astype(np.uint8)

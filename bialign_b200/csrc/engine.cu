@@ -8,7 +8,6 @@
 //               systolic kernel: 5-bit tie field per state; non-affine: case index in the low nibble);
 //               pairs are processed in waves that fit the arena, traceback runs per wave
 //   bnd         systolic kernel: boundary streams between row blocks (per CTA, or 2 * grid in long-pair mode)
-//   code_dump   per-CTA strips where lanes outside a pair stream their code words
 //   trace       one slot of 2(n+m)+2 bytes per pair, columns written backwards by the traceback
 //   scores/start_state/end_values/trace_len/complete   per pair, caller order
 #include <algorithm>
@@ -19,6 +18,7 @@
 #include <limits>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/bialign_b200.h"
@@ -100,19 +100,25 @@ struct ba_engine {
     DevBuf<int> d_counter;
     DevBuf<int> d_simp, d_tbtab, d_bnd;
     DevBuf<unsigned long long> d_progress;
-    DevBuf<uint64_t> d_code_dump;
     int opt_long = -1;                 // multi-CTA long-pair mode: -1 auto, 0 off, 1 force
     int opt_p16 = -1;                  // 16-bit pair mode for score-only batches: -1 auto, 0 off, 1 force
     std::vector<int32_t> h_sim;
     int opt_warps = 0;                 // warps per CTA of the systolic kernel (0 = chosen per batch)
     int opt_pad = -1;                  // systolic flavour: -1 auto, 0 pad-free, 1 padded
-    int last_fmt = 0;
+    int last_fmt = 0, last_sysG = 0;   // code-table layout of the last run (debug fetch)
+    bool last_pad = false;
     DevBuf<long long> d_scores;
     DevBuf<uint8_t> d_start, d_complete, d_trace;
     DevBuf<int> d_endv, d_tlen;
     PinnedBuf<uint8_t> h_stage;
     std::vector<int32_t> h_tlen;
     bool have_tlen = false;
+
+    // Multi-GPU front (ba_engine_create_multi): this object owns no device state; it shards the pair list over one
+    // child engine per device (LPT), drives them from one host thread each and merges results in caller order.
+    std::vector<ba_engine*> kids;
+    std::vector<std::vector<int32_t>> shard;  // per child: caller-order pair indices it owns
+    std::vector<int64_t> m_tlen;              // caller order, after ba_trace_bytes / ba_fetch_traces
 
     int64_t opt_code_arena_bytes = 0;  // 0 = auto
     bool arena_is_budget = false;      // current arena = the full memory budget (not just "all pairs fit")
@@ -134,6 +140,8 @@ int fail(ba_engine* e, int code, const std::string& msg) {
             return fail(e, _e == cudaErrorMemoryAllocation ? BA_ERR_OOM : BA_ERR_CUDA,               \
                         std::string(#call) + ": " + cudaGetErrorString(_e));                         \
     } while (0)
+
+constexpr size_t kSysSmemLimit = 220 * 1024;  // dynamic shared memory one systolic CTA may ask for
 
 int64_t band_cells(int64_t n, int64_t m, int64_t s) {
     // C(n,m,s) of SURVEY 8: exact count of band-valid cells (k in [max(0,i-s), min(n,i+s)] etc.)
@@ -241,6 +249,20 @@ SysPlan plan_systolic(const ba_engine* e, int nmax, int mmax, bool trace, bool b
 
 }  // namespace
 
+// Multi-GPU front (defined at the end of this file): every entry point forwards here when the engine has children.
+namespace multi {
+void destroy(ba_engine* e);
+int set_option(ba_engine* e, const char* key, int64_t value);
+int set_scoring(ba_engine* e, const int32_t* sim, int nsym, int w, int beta, int gamma, int delta, int s);
+int load_sequences(ba_engine* e, const uint8_t* residues, const uint8_t* classes, const int64_t* offsets, int64_t n_seq);
+int load_pairs(ba_engine* e, const int32_t* seq_a, const int32_t* seq_b, int64_t n_pairs);
+int run(ba_engine* e, int want_trace);
+int fetch_scores(ba_engine* e, int64_t* scores);
+int trace_bytes(ba_engine* e, int64_t* total);
+int fetch_traces(ba_engine* e, uint8_t* cols, int64_t* offsets, uint8_t* complete);
+int debug_route(ba_engine* e, int64_t pair, ba_engine** kid, int64_t* local);
+}  // namespace multi
+
 extern "C" {
 
 const char* ba_version(void) { return "bialign_b200 0.1 (sm_100a)"; }
@@ -276,12 +298,13 @@ int ba_engine_create(int device, ba_engine** out) {
 
 void ba_engine_destroy(ba_engine* e) {
     if (!e) return;
+    if (!e->kids.empty()) { multi::destroy(e); return; }
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     e->d_sim.release(); e->d_res.release(); e->d_cls.release(); e->d_desc.release(); e->d_codes.release();
     e->d_scratch.release(); e->d_counter.release(); e->d_scores.release(); e->d_start.release();
     e->d_complete.release(); e->d_trace.release(); e->d_endv.release(); e->d_tlen.release(); e->h_stage.release();
-    e->d_simp.release(); e->d_tbtab.release(); e->d_bnd.release(); e->d_progress.release(); e->d_code_dump.release();
+    e->d_simp.release(); e->d_tbtab.release(); e->d_bnd.release(); e->d_progress.release();
     cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -290,6 +313,7 @@ const char* ba_last_error(const ba_engine* e) { return e ? e->err.c_str() : g_cr
 
 int ba_set_option(ba_engine* e, const char* key, int64_t value) {
     if (!e || !key) return BA_ERR_INVALID_ARG;
+    if (!e->kids.empty()) return multi::set_option(e, key, value);
     auto tri = [&](int* dst) {  // -1 auto, 0 off, 1 force
         if (value < -1 || value > 1) return fail(e, BA_ERR_INVALID_ARG, std::string(key) + " must be -1 (auto), 0 or 1");
         *dst = (int)value;
@@ -314,6 +338,7 @@ int ba_set_option(ba_engine* e, const char* key, int64_t value) {
 int ba_set_scoring(ba_engine* e, const int32_t* sim, int nsym, int structure_weight, int gap_opening_cost,
                    int gap_cost, int shift_cost, int max_shift) {
     if (!e) return BA_ERR_INVALID_ARG;
+    if (!e->kids.empty()) return multi::set_scoring(e, sim, nsym, structure_weight, gap_opening_cost, gap_cost, shift_cost, max_shift);
     if (!sim || nsym <= 0 || nsym > 256) return fail(e, BA_ERR_INVALID_ARG, "sim is NULL or nsym not in 1..256");
     if (max_shift < 0 || max_shift > BA_MAX_SHIFT)
         return fail(e, BA_ERR_INVALID_ARG, "max_shift must be in 0.." + std::to_string(BA_MAX_SHIFT));
@@ -335,6 +360,7 @@ int ba_set_scoring(ba_engine* e, const int32_t* sim, int nsym, int structure_wei
 int ba_load_sequences(ba_engine* e, const uint8_t* residues, const uint8_t* classes, const int64_t* offsets,
                       int64_t n_seq) {
     if (!e) return BA_ERR_INVALID_ARG;
+    if (!e->kids.empty()) return multi::load_sequences(e, residues, classes, offsets, n_seq);
     if (!offsets || n_seq < 0) return fail(e, BA_ERR_INVALID_ARG, "offsets is NULL or n_seq < 0");
     for (int64_t q = 0; q < n_seq; ++q) {
         if (offsets[q + 1] < offsets[q] || offsets[q] < 0) return fail(e, BA_ERR_INVALID_ARG, "offsets not monotone");
@@ -365,6 +391,7 @@ int ba_load_sequences(ba_engine* e, const uint8_t* residues, const uint8_t* clas
 
 int ba_load_pairs(ba_engine* e, const int32_t* seq_a, const int32_t* seq_b, int64_t n_pairs) {
     if (!e) return BA_ERR_INVALID_ARG;
+    if (!e->kids.empty()) return multi::load_pairs(e, seq_a, seq_b, n_pairs);
     if (!e->have_seqs) return fail(e, BA_ERR_STATE, "ba_load_sequences first");
     if (n_pairs < 0 || (n_pairs > 0 && (!seq_a || !seq_b))) return fail(e, BA_ERR_INVALID_ARG, "pair arrays NULL");
     if (n_pairs > 0x7fffffff) return fail(e, BA_ERR_INVALID_ARG, "too many pairs for one call");
@@ -381,6 +408,7 @@ int ba_load_pairs(ba_engine* e, const int32_t* seq_a, const int32_t* seq_b, int6
 
 int ba_run(ba_engine* e, int want_trace) {
     if (!e) return BA_ERR_INVALID_ARG;
+    if (!e->kids.empty()) return multi::run(e, want_trace);
     if (!e->have_scoring) return fail(e, BA_ERR_STATE, "ba_set_scoring first");
     if (!e->have_pairs) return fail(e, BA_ERR_STATE, "ba_load_sequences and ba_load_pairs first");
     const bool affine = e->sc.beta != 0;  // pyx:203-205
@@ -442,13 +470,89 @@ int ba_run(ba_engine* e, int want_trace) {
         }
 
     lap("sort + slots");
+    // ---- kernel choice: systolic when its exactness conditions hold, else the generic level kernel
+    SysPlan plan;
+    bool p16 = false;
+    if (e->opt_kernel != 0 && affine && !want_trace && e->opt_p16 != 0 && e->opt_pad != 1 && N >= 2) {
+        plan = plan_systolic(e, nmax, mmax, false, true);  // do the scores provably fit 16 bits?
+        p16 = plan.ok;
+    }
+    if (e->opt_p16 == 1 && !p16 && !want_trace && affine && N >= 2)
+        return fail(e, BA_ERR_SCORE_RANGE, "16-bit pair mode requested but the score range does not fit");
+    if (!p16 && e->opt_kernel != 0) plan = plan_systolic(e, nmax, mmax, want_trace != 0, false, !affine);
+    if (e->opt_kernel == 1 && !plan.ok)
+        return fail(e, BA_ERR_SCORE_RANGE, "systolic kernel requested but its packed-integer range conditions do not hold");
+    int kernel = plan.ok ? 1 : 0;
+    int max_grid = e->sm_count * 2;
+    size_t scratch_stride = 0, sys_smem = 0;
+    int sysG = e->opt_warps;
+    SysArgs SA{};
+    bool long_mode = false;
+    int long_grid_max = 0, sys_occ = 0;
+    if (kernel == 1) {
+        if (sysG == 0) {
+            // Pick the CTA width that minimises the estimated warp-iterations per resident warp:
+            // a pair costs passes(G) * iterations(G) on G warps; an SM runs occ(G) CTAs, and more than ~12
+            // resident warps do not add throughput (the ALU pipe is saturated).  Short pairs want a CTA that
+            // covers all rows in one pass; long ones want few warps per CTA and several CTAs per SM.
+            const SysGeo geo = sys_geo(s, plan.pad);
+            double best = 0;
+            for (int G = std::max(2, (18 * geo.LPR + 31) / 32); G <= 8; ++G) {
+                const size_t sm = sys_smem_bytes(s, plan.pad, G, e->sc.nsym, mmax, p16);
+                if (sm > kSysSmemLimit) continue;
+                const int occ = p16 ? sys_occupancy_p16(s, G, sm)
+                                    : !affine ? sys_occupancy_na(s, want_trace != 0, plan.pad, G, sm)
+                                              : sys_occupancy(s, want_trace != 0, plan.pad, plan.bneg, G, sm);
+                if (occ < 1) continue;
+                const double eff = std::min(occ * G, 12);
+                double cost = 0;
+                const int64_t stride = std::max<int64_t>(1, N / 4096);  // sample large batches
+                for (int64_t p = 0; p < N; p += stride) {
+                    const int rows = G * geo.R;
+                    const double passes = (ln[p] + rows) / rows;
+                    cost += passes * (double)sys_iters(s, plan.pad, G, lm[p]) * G;
+                }
+                cost /= eff;
+                if (sysG == 0 || cost < best * 0.97) { best = cost; sysG = G; }  // prefer the narrower CTA on near-ties
+            }
+            if (sysG == 0) sysG = 2;
+            // a handful of long pairs will run in long-pair mode, where the pipeline fill (CTAs x lag) matters as much
+            // as the per-CTA rate: 4 warps measured best on both the 928 x 933 and the 8192 x 8192 pair
+            if (N <= 4 && affine && !p16 && e->opt_long != 0 && (nmax + 1) > 8 * 4 * geo.R) sysG = std::max(4, (18 * geo.LPR + 31) / 32);
+        }
+        // one boundary-record element per thread: a CTA needs at least 18 * LPR threads, and never fewer -- a narrower
+        // CTA would silently drop record elements between the row blocks of a multi-pass pair
+        const int minG = (18 * sys_geo(s, plan.pad).LPR + 31) / 32;
+        sysG = std::max(sysG, minG);
+        while (sysG > minG && sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax, p16) > kSysSmemLimit) --sysG;
+        sys_smem = sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax, p16);
+        sys_occ = sys_smem > kSysSmemLimit ? 0
+                        : p16 ? sys_occupancy_p16(s, sysG, sys_smem)
+                              : !affine ? sys_occupancy_na(s, want_trace != 0, plan.pad, sysG, sys_smem)
+                                        : sys_occupancy(s, want_trace != 0, plan.pad, plan.bneg, sysG, sys_smem);
+        if (sys_occ < 1) {
+            // molecule B is staged in shared memory: a very long B does not fit next to the rings even at the
+            // minimum CTA width.  The general level kernel has no such limit.
+            if (e->opt_kernel == 1)
+                return fail(e, BA_ERR_CUDA, "systolic kernel does not fit on an SM (shared memory " + std::to_string(sys_smem) + ")");
+            kernel = 0;
+            p16 = false;
+        }
+    }
+    // Code words of one pair: the level kernel uses the cell-major table of common.cuh; the systolic kernel writes in the
+    // order it computes -- [row block][warp][iteration][lane], 256 contiguous bytes per warp and iteration -- so its table
+    // also holds the skewed pipeline's idle slots (about 10-15 % more memory, 15x fewer store transactions).
+    auto pair_code_words = [&](int n, int m) -> int64_t {
+        if (kernel != 1) return code_words(n, m, s);
+        return sys_code_words(s, plan.pad, sysG, n, m);
+    };
     // code arena
     size_t arena_words = 0;
     std::vector<int64_t> wave_begin;  // indices into sorted order
     if (want_trace && N) {
         int64_t total_words = 0, max_words = 0;
         for (int64_t p = 0; p < N; ++p) {
-            const int64_t wds = code_words(ln[p], lm[p], s);
+            const int64_t wds = pair_code_words(ln[p], lm[p]);
             total_words += wds;
             max_words = std::max(max_words, wds);
         }
@@ -497,7 +601,7 @@ int ba_run(ba_engine* e, int want_trace) {
             d.trace_cap = e->h_slot_cap[p];
             d.code_off = 0;
             if (want_trace) {
-                const int64_t wds = code_words(d.n, d.m, s);
+                const int64_t wds = pair_code_words(d.n, d.m);
                 if (used + wds > (int64_t)arena_words) {
                     wave_begin.push_back(q);
                     used = 0;
@@ -530,65 +634,8 @@ int ba_run(ba_engine* e, int want_trace) {
     lap("result buffers");
     int64_t biggest_wave = 0;
     for (int w = 0; w < n_waves; ++w) biggest_wave = std::max(biggest_wave, wave_begin[w + 1] - wave_begin[w]);
-    // ---- kernel choice: systolic when its exactness conditions hold, else the generic level kernel
-    SysPlan plan;
-    bool p16 = false;
-    if (e->opt_kernel != 0 && affine && !want_trace && e->opt_p16 != 0 && e->opt_pad != 1 && N >= 2) {
-        plan = plan_systolic(e, nmax, mmax, false, true);  // do the scores provably fit 16 bits?
-        p16 = plan.ok;
-    }
-    if (e->opt_p16 == 1 && !p16 && !want_trace && affine && N >= 2)
-        return fail(e, BA_ERR_SCORE_RANGE, "16-bit pair mode requested but the score range does not fit");
-    if (!p16 && e->opt_kernel != 0) plan = plan_systolic(e, nmax, mmax, want_trace != 0, false, !affine);
-    if (e->opt_kernel == 1 && !plan.ok)
-        return fail(e, BA_ERR_SCORE_RANGE, "systolic kernel requested but its packed-integer range conditions do not hold");
-    const int kernel = plan.ok ? 1 : 0;
-    int max_grid = e->sm_count * 2;
-    size_t scratch_stride = 0, sys_smem = 0;
-    int sysG = e->opt_warps;
-    SysArgs SA{};
-    bool long_mode = false;
-    int long_grid_max = 0;
     if (kernel == 1) {
-        if (sysG == 0) {
-            // Pick the CTA width that minimises the estimated warp-iterations per resident warp:
-            // a pair costs passes(G) * iterations(G) on G warps; an SM runs occ(G) CTAs, and more than ~12
-            // resident warps do not add throughput (the ALU pipe is saturated).  Short pairs want a CTA that
-            // covers all rows in one pass; long ones want few warps per CTA and several CTAs per SM.
-            const SysGeo geo = sys_geo(s, plan.pad);
-            double best = 0;
-            for (int G = std::max(2, (18 * geo.LPR + 31) / 32); G <= 8; ++G) {
-                const size_t sm = sys_smem_bytes(s, plan.pad, G, e->sc.nsym, mmax, p16);
-                if (sm > 220 * 1024) continue;
-                const int occ = p16 ? sys_occupancy_p16(s, G, sm)
-                                    : !affine ? sys_occupancy_na(s, want_trace != 0, plan.pad, G, sm)
-                                              : sys_occupancy(s, want_trace != 0, plan.pad, plan.bneg, G, sm);
-                if (occ < 1) continue;
-                const double eff = std::min(occ * G, 12);
-                double cost = 0;
-                const int64_t stride = std::max<int64_t>(1, N / 4096);  // sample large batches
-                for (int64_t p = 0; p < N; p += stride) {
-                    const int rows = G * geo.R;
-                    const double passes = (ln[p] + rows) / rows;
-                    cost += passes * (double)sys_iters(s, plan.pad, G, lm[p]) * G;
-                }
-                cost /= eff;
-                if (sysG == 0 || cost < best * 0.97) { best = cost; sysG = G; }  // prefer the narrower CTA on near-ties
-            }
-            if (sysG == 0) sysG = 2;
-            // a handful of long pairs will run in long-pair mode, where the pipeline fill (CTAs x lag) matters as much
-            // as the per-CTA rate: 4 warps measured best on both the 928 x 933 and the 8192 x 8192 pair
-            if (N <= 4 && affine && !p16 && e->opt_long != 0 && (nmax + 1) > 8 * 4 * geo.R) sysG = std::max(4, (18 * geo.LPR + 31) / 32);
-        }
-        // one boundary-record element per thread: a CTA needs at least 18 * LPR threads
-        sysG = std::max(sysG, (18 * sys_geo(s, plan.pad).LPR + 31) / 32);
-        while (sysG > 1 && sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax, p16) > 200 * 1024) --sysG;
-        sys_smem = sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax, p16);
-        const int occ = p16 ? sys_occupancy_p16(s, sysG, sys_smem)
-                            : !affine ? sys_occupancy_na(s, want_trace != 0, plan.pad, sysG, sys_smem)
-                                      : sys_occupancy(s, want_trace != 0, plan.pad, plan.bneg, sysG, sys_smem);
-        if (occ < 1) return fail(e, BA_ERR_CUDA, "systolic kernel does not fit on an SM (shared memory " + std::to_string(sys_smem) + ")");
-        max_grid = e->sm_count * occ;
+        max_grid = e->sm_count * sys_occ;
         const int grid = (int)std::min<int64_t>(biggest_wave, max_grid);
         const int rows_pass = sysG * sys_geo(s, plan.pad).R;
         const bool multi_pass = nmax + 1 > rows_pass;
@@ -633,9 +680,6 @@ int ba_run(ba_engine* e, int want_trace) {
         SA.progress = e->d_progress.p;
         SA.bnd = e->d_bnd.p; SA.bnd_iters = biters + 8;  // matches sys_boundary_ints: slack records in front
         SA.codes = want_trace ? e->d_codes.p : nullptr;
-        SA.code_dump_stride = (size_t)(mmax + 2) * (2 * s + 1) + 8;
-        if (want_trace) CU(e->d_code_dump.ensure(SA.code_dump_stride * (size_t)std::max({max_grid, long_grid_max, 1})));
-        SA.code_dump = e->d_code_dump.p;
         SA.scores = e->d_scores.p; SA.start_state = e->d_start.p; SA.end_values = e->d_endv.p;
     } else {
         scratch_stride = generic_scratch_ints(nmax, s);  // sized for nine states; the non-affine kernel uses a ninth
@@ -701,6 +745,10 @@ int ba_run(ba_engine* e, int want_trace) {
             TraceArgs T{};
             T.pairs = e->d_desc.p + b; T.npairs = (int)cnt; T.s = s; T.codes = e->d_codes.p; T.fmt = affine ? kernel : 2;
             T.start_state = e->d_start.p; T.trace = e->d_trace.p; T.trace_len = e->d_tlen.p; T.complete = e->d_complete.p;
+            if (kernel == 1) {
+                const SysGeo geo = sys_geo(s, plan.pad);
+                T.sysG = sysG; T.R = geo.R; T.LPR = geo.LPR; T.P = geo.P; T.RING = geo.RING;
+            }
             launch_traceback(T, e->stream);
             e->stats.kernel_launches++;
             CU(cudaGetLastError());
@@ -726,13 +774,15 @@ int ba_run(ba_engine* e, int want_trace) {
     if (want_trace) {
         for (int64_t q = wave_begin[n_waves - 1]; q < N; ++q) e->h_last_code_off[e->h_desc[q].orig] = e->h_desc[q].code_off;
         int64_t cb = 0;
-        for (int64_t p = 0; p < N; ++p) cb += code_words(ln[p], lm[p], s) * 8;
+        for (int64_t p = 0; p < N; ++p) cb += pair_code_words(ln[p], lm[p]) * 8;
         e->stats.code_bytes = cb;
     }
     e->stats.waves = n_waves;
     e->stats.kernel_kind = kernel == 0 ? 0 : (p16 ? 5 : !affine ? (plan.pad ? 7 : 6) : (plan.pad ? 2 : 1) + (long_mode ? 2 : 0));
     e->stats.warps_per_cta = kernel == 0 ? 0 : sysG;
     e->last_fmt = kernel;
+    e->last_sysG = kernel == 1 ? sysG : 0;
+    e->last_pad = kernel == 1 && plan.pad;
     e->ran = true;
     e->ran_trace = want_trace != 0;
     return BA_OK;
@@ -740,6 +790,7 @@ int ba_run(ba_engine* e, int want_trace) {
 
 int ba_fetch_scores(ba_engine* e, int64_t* scores) {
     if (!e) return BA_ERR_INVALID_ARG;
+    if (!e->kids.empty()) return multi::fetch_scores(e, scores);
     if (!e->ran) return fail(e, BA_ERR_STATE, "ba_run first");
     if (e->n_pairs == 0) return BA_OK;
     if (!scores) return fail(e, BA_ERR_INVALID_ARG, "scores is NULL");
@@ -761,8 +812,22 @@ static int fetch_lens(ba_engine* e) {
     return BA_OK;
 }
 
+// D2H of all trace slots into the engine's pinned staging buffer (pair p's columns end at
+// h_stage + h_slot_off[p] + h_slot_cap[p]) and of the completeness flags into `complete` (engine order).
+static int stage_traces(ba_engine* e, uint8_t* complete) {
+    const int64_t N = e->n_pairs;
+    if (N == 0) return BA_OK;
+    const size_t slot_bytes = (size_t)e->h_slot_off[N - 1] + ((e->h_slot_cap[N - 1] + 15) & ~15);
+    CU(e->h_stage.ensure(slot_bytes));
+    CU(cudaMemcpyAsync(e->h_stage.p, e->d_trace.p, slot_bytes, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(complete, e->d_complete.p, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return BA_OK;
+}
+
 int ba_trace_bytes(ba_engine* e, int64_t* total) {
     if (!e || !total) return BA_ERR_INVALID_ARG;
+    if (!e->kids.empty()) return multi::trace_bytes(e, total);
     if (!e->ran || !e->ran_trace) return fail(e, BA_ERR_STATE, "ba_run(want_trace=1) first");
     CU(cudaSetDevice(e->device));
     int rc = fetch_lens(e);
@@ -775,6 +840,7 @@ int ba_trace_bytes(ba_engine* e, int64_t* total) {
 
 int ba_fetch_traces(ba_engine* e, uint8_t* cols, int64_t* offsets, uint8_t* complete) {
     if (!e) return BA_ERR_INVALID_ARG;
+    if (!e->kids.empty()) return multi::fetch_traces(e, cols, offsets, complete);
     if (!e->ran || !e->ran_trace) return fail(e, BA_ERR_STATE, "ba_run(want_trace=1) first");
     if (!offsets) return fail(e, BA_ERR_INVALID_ARG, "offsets is NULL");
     CU(cudaSetDevice(e->device));
@@ -784,11 +850,8 @@ int ba_fetch_traces(ba_engine* e, uint8_t* cols, int64_t* offsets, uint8_t* comp
     offsets[0] = 0;
     if (N == 0) return BA_OK;
     if (!complete) return fail(e, BA_ERR_INVALID_ARG, "complete is NULL");
-    const size_t slot_bytes = (size_t)e->h_slot_off[N - 1] + ((e->h_slot_cap[N - 1] + 15) & ~15);
-    CU(e->h_stage.ensure(slot_bytes));
-    CU(cudaMemcpyAsync(e->h_stage.p, e->d_trace.p, slot_bytes, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaMemcpyAsync(complete, e->d_complete.p, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
+    rc = stage_traces(e, complete);
+    if (rc) return rc;
     int64_t pos = 0;
     for (int64_t p = 0; p < N; ++p) {
         const int32_t len = e->h_tlen[p];
@@ -818,21 +881,55 @@ int ba_get_stats(const ba_engine* e, ba_stats* out) {
 
 int ba_debug_fetch_codes(ba_engine* e, int64_t pair, uint64_t* out, int64_t words) {
     if (!e || !out) return BA_ERR_INVALID_ARG;
+    if (!e->kids.empty()) {
+        ba_engine* kid = nullptr;
+        int64_t local = 0;
+        int rc = multi::debug_route(e, pair, &kid, &local);
+        if (rc) return rc;
+        rc = ba_debug_fetch_codes(kid, local, out, words);
+        if (rc) e->err = kid->err;
+        return rc;
+    }
     if (!e->ran || !e->ran_trace) return fail(e, BA_ERR_STATE, "ba_run(want_trace=1) first");
     if (pair < 0 || pair >= e->n_pairs || e->h_last_code_off[pair] < 0)
         return fail(e, BA_ERR_INVALID_ARG, "pair not in the last wave");
     CU(cudaSetDevice(e->device));
     const int n = (int)(e->h_off[e->h_pa[pair] + 1] - e->h_off[e->h_pa[pair]]);
     const int m = (int)(e->h_off[e->h_pb[pair] + 1] - e->h_off[e->h_pb[pair]]);
-    const int64_t need = code_words(n, m, e->sc.s);
+    const int S = e->sc.s;
+    const int64_t need = code_words(n, m, S);
     if (words < need) return fail(e, BA_ERR_INVALID_ARG, "buffer too small");
-    CU(cudaMemcpyAsync(out, e->d_codes.p + e->h_last_code_off[pair], (size_t)need * 8, cudaMemcpyDeviceToHost, e->stream));
+    if (e->last_sysG == 0) {
+        CU(cudaMemcpyAsync(out, e->d_codes.p + e->h_last_code_off[pair], (size_t)need * 8, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        return BA_OK;
+    }
+    // systolic layout -> the cell-major table this hook promises (cells the kernel never visits read as all-ones)
+    const SysGeo geo = sys_geo(S, e->last_pad);
+    const int G = e->last_sysG, nit_all = sys_iters(S, e->last_pad, G, m) + 4;
+    const int64_t raw = sys_code_words(S, e->last_pad, G, n, m);
+    std::vector<uint64_t> tmp((size_t)raw);
+    CU(cudaMemcpyAsync(tmp.data(), e->d_codes.p + e->h_last_code_off[pair], (size_t)raw * 8, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i <= n; ++i)
+        for (int a = -S; a <= S; ++a)
+            for (int j = 0; j <= m; ++j)
+                for (int b = -S; b <= S; ++b)
+                    out[code_index(m, S, i, j, a, b)] = tmp[(size_t)sys_code_index(geo.R, geo.LPR, geo.P, S, G, nit_all, i, j, a, b)];
     return BA_OK;
 }
 
 int ba_debug_fetch_end_values(ba_engine* e, int64_t pair, int32_t* out9) {
     if (!e || !out9) return BA_ERR_INVALID_ARG;
+    if (!e->kids.empty()) {
+        ba_engine* kid = nullptr;
+        int64_t local = 0;
+        int rc = multi::debug_route(e, pair, &kid, &local);
+        if (rc) return rc;
+        rc = ba_debug_fetch_end_values(kid, local, out9);
+        if (rc) e->err = kid->err;
+        return rc;
+    }
     if (!e->ran) return fail(e, BA_ERR_STATE, "ba_run first");
     if (pair < 0 || pair >= e->n_pairs) return fail(e, BA_ERR_INVALID_ARG, "pair out of range");
     CU(cudaSetDevice(e->device));
@@ -842,3 +939,250 @@ int ba_debug_fetch_end_values(ba_engine* e, int64_t pair, int32_t* out9) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU front.  Pairs are independent units, so the whole box is driven from one process without any
+// collective: the pair list is dealt over the devices by cost (longest first; a snake deal for large batches,
+// exact LPT for small ones -- the same policy as bialign_b200/batch.py lpt_shards), every device gets the
+// sequence table, one host thread per device runs the ordinary single-device engine, and the results are
+// written into the caller's arrays in caller order.
+// ------------------------------------------------------------------------------------------------
+namespace multi {
+
+template <class F>
+int for_each_kid(ba_engine* e, F f) {  // one host thread per device; the first error wins
+    const size_t K = e->kids.size();
+    std::vector<int> rc(K, BA_OK);
+    std::vector<std::thread> th;
+    th.reserve(K);
+    for (size_t k = 0; k < K; ++k) th.emplace_back([&, k] { rc[k] = f(k, e->kids[k]); });
+    for (auto& t : th) t.join();
+    for (size_t k = 0; k < K; ++k)
+        if (rc[k]) {
+            e->err = "device " + std::to_string(e->kids[k]->device) + ": " + e->kids[k]->err;
+            return rc[k];
+        }
+    return BA_OK;
+}
+
+void destroy(ba_engine* e) {
+    for (ba_engine* k : e->kids) ba_engine_destroy(k);
+    e->kids.clear();
+    delete e;
+}
+
+int set_option(ba_engine* e, const char* key, int64_t value) {
+    for (ba_engine* k : e->kids) {
+        const int rc = ba_set_option(k, key, value);
+        if (rc) { e->err = k->err; return rc; }
+    }
+    return BA_OK;
+}
+
+int set_scoring(ba_engine* e, const int32_t* sim, int nsym, int w, int beta, int gamma, int delta, int s) {
+    const int rc = for_each_kid(e, [&](size_t, ba_engine* k) { return ba_set_scoring(k, sim, nsym, w, beta, gamma, delta, s); });
+    if (rc) return rc;
+    e->sc = e->kids[0]->sc;
+    e->have_scoring = true;
+    e->ran = false;
+    return BA_OK;
+}
+
+int load_sequences(ba_engine* e, const uint8_t* residues, const uint8_t* classes, const int64_t* offsets, int64_t n_seq) {
+    const int rc = for_each_kid(e, [&](size_t, ba_engine* k) { return ba_load_sequences(k, residues, classes, offsets, n_seq); });
+    if (rc) return rc;
+    e->h_off = e->kids[0]->h_off;
+    e->n_seq = n_seq;
+    e->have_seqs = true;
+    e->have_pairs = false;
+    e->ran = false;
+    return BA_OK;
+}
+
+int load_pairs(ba_engine* e, const int32_t* seq_a, const int32_t* seq_b, int64_t n_pairs) {
+    if (!e->have_seqs) return fail(e, BA_ERR_STATE, "ba_load_sequences first");
+    if (n_pairs < 0 || (n_pairs > 0 && (!seq_a || !seq_b))) return fail(e, BA_ERR_INVALID_ARG, "pair arrays NULL");
+    if (n_pairs > 0x7fffffff) return fail(e, BA_ERR_INVALID_ARG, "too many pairs for one call");
+    for (int64_t p = 0; p < n_pairs; ++p)
+        if (seq_a[p] < 0 || seq_a[p] >= e->n_seq || seq_b[p] < 0 || seq_b[p] >= e->n_seq)
+            return fail(e, BA_ERR_INVALID_ARG, "pair " + std::to_string(p) + " references a sequence outside the table");
+    const size_t K = e->kids.size();
+    std::vector<int64_t> cost((size_t)n_pairs);
+    for (int64_t p = 0; p < n_pairs; ++p)
+        cost[p] = (e->h_off[seq_a[p] + 1] - e->h_off[seq_a[p]] + 1) * (e->h_off[seq_b[p] + 1] - e->h_off[seq_b[p]] + 1);
+    std::vector<int32_t> order((size_t)n_pairs);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return cost[x] > cost[y]; });
+    e->shard.assign(K, {});
+    if (n_pairs > 4096) {  // snake deal of the sorted list
+        for (int64_t q = 0; q < n_pairs; ++q) {
+            const int64_t rnd = q / (int64_t)K, pos = q % (int64_t)K;
+            e->shard[(rnd & 1) ? K - 1 - pos : pos].push_back(order[q]);
+        }
+    } else {  // exact LPT: next pair to the least loaded device
+        std::vector<int64_t> load(K, 0);
+        for (int64_t q = 0; q < n_pairs; ++q) {
+            const size_t k = std::min_element(load.begin(), load.end()) - load.begin();
+            e->shard[k].push_back(order[q]);
+            load[k] += cost[order[q]];
+        }
+    }
+    for (auto& sh : e->shard) std::sort(sh.begin(), sh.end());
+    const int rc = for_each_kid(e, [&](size_t k, ba_engine* kid) {
+        const auto& sh = e->shard[k];
+        std::vector<int32_t> a(sh.size()), b(sh.size());
+        for (size_t q = 0; q < sh.size(); ++q) { a[q] = seq_a[sh[q]]; b[q] = seq_b[sh[q]]; }
+        return ba_load_pairs(kid, a.data(), b.data(), (int64_t)sh.size());
+    });
+    if (rc) return rc;
+    e->n_pairs = n_pairs;
+    e->have_pairs = true;
+    e->ran = false;
+    return BA_OK;
+}
+
+int run(ba_engine* e, int want_trace) {
+    if (!e->have_scoring) return fail(e, BA_ERR_STATE, "ba_set_scoring first");
+    if (!e->have_pairs) return fail(e, BA_ERR_STATE, "ba_load_sequences and ba_load_pairs first");
+    e->ran = false;
+    e->m_tlen.clear();
+    const int rc = for_each_kid(e, [&](size_t, ba_engine* k) { return ba_run(k, want_trace); });
+    if (rc) return rc;
+    ba_stats st{};
+    st.device = e->kids[0]->device;
+    st.kernel_kind = e->kids[0]->stats.kernel_kind;
+    st.warps_per_cta = e->kids[0]->stats.warps_per_cta;
+    for (ba_engine* k : e->kids) {  // sums of work, max of device times (the devices run side by side)
+        st.pairs += k->stats.pairs;
+        st.cell_states += k->stats.cell_states;
+        st.kernel_launches += k->stats.kernel_launches;
+        st.code_bytes += k->stats.code_bytes;
+        st.waves = std::max(st.waves, k->stats.waves);
+        st.fill_ms = std::max(st.fill_ms, k->stats.fill_ms);
+        st.traceback_ms = std::max(st.traceback_ms, k->stats.traceback_ms);
+        st.total_ms = std::max(st.total_ms, k->stats.total_ms);
+    }
+    e->stats = st;
+    e->ran = true;
+    e->ran_trace = want_trace != 0;
+    return BA_OK;
+}
+
+int fetch_scores(ba_engine* e, int64_t* scores) {
+    if (!e->ran) return fail(e, BA_ERR_STATE, "ba_run first");
+    if (e->n_pairs == 0) return BA_OK;
+    if (!scores) return fail(e, BA_ERR_INVALID_ARG, "scores is NULL");
+    return for_each_kid(e, [&](size_t k, ba_engine* kid) {
+        const auto& sh = e->shard[k];
+        std::vector<int64_t> tmp(sh.size());
+        const int rc = ba_fetch_scores(kid, tmp.data());
+        if (rc) return rc;
+        for (size_t q = 0; q < sh.size(); ++q) scores[sh[q]] = tmp[q];
+        return (int)BA_OK;
+    });
+}
+
+static int gather_lens(ba_engine* e) {
+    if (!e->m_tlen.empty() || e->n_pairs == 0) return BA_OK;
+    std::vector<int64_t> tl((size_t)e->n_pairs, 0);
+    const int rc = for_each_kid(e, [&](size_t k, ba_engine* kid) {
+        cudaSetDevice(kid->device);
+        const int r = fetch_lens(kid);
+        if (r) return r;
+        const auto& sh = e->shard[k];
+        for (size_t q = 0; q < sh.size(); ++q) tl[sh[q]] = kid->h_tlen[q];
+        return (int)BA_OK;
+    });
+    if (rc) return rc;
+    e->m_tlen.swap(tl);
+    return BA_OK;
+}
+
+int trace_bytes(ba_engine* e, int64_t* total) {
+    if (!e->ran || !e->ran_trace) return fail(e, BA_ERR_STATE, "ba_run(want_trace=1) first");
+    const int rc = gather_lens(e);
+    if (rc) return rc;
+    int64_t t = 0;
+    for (int64_t x : e->m_tlen) t += x;
+    *total = t;
+    return BA_OK;
+}
+
+int fetch_traces(ba_engine* e, uint8_t* cols, int64_t* offsets, uint8_t* complete) {
+    if (!e->ran || !e->ran_trace) return fail(e, BA_ERR_STATE, "ba_run(want_trace=1) first");
+    if (!offsets) return fail(e, BA_ERR_INVALID_ARG, "offsets is NULL");
+    int rc = gather_lens(e);
+    if (rc) return rc;
+    const int64_t N = e->n_pairs;
+    offsets[0] = 0;
+    if (N == 0) return BA_OK;
+    if (!complete) return fail(e, BA_ERR_INVALID_ARG, "complete is NULL");
+    for (int64_t p = 0; p < N; ++p) offsets[p + 1] = offsets[p] + e->m_tlen[p];
+    if (offsets[N] && !cols) return fail(e, BA_ERR_INVALID_ARG, "cols is NULL");
+    // every device copies its trace slots to its own pinned staging buffer, then its host thread places each
+    // pair's columns directly at the pair's position in the caller's array
+    return for_each_kid(e, [&](size_t k, ba_engine* kid) {
+        const auto& sh = e->shard[k];
+        std::vector<uint8_t> comp(sh.size() + 1);
+        cudaSetDevice(kid->device);
+        const int r = stage_traces(kid, comp.data());
+        if (r) return r;
+        for (size_t q = 0; q < sh.size(); ++q) {
+            const int32_t len = kid->h_tlen[q];
+            if (len) memcpy(cols + offsets[sh[q]], kid->h_stage.p + kid->h_slot_off[q] + kid->h_slot_cap[q] - len, (size_t)len);
+            complete[sh[q]] = comp[q];
+        }
+        return (int)BA_OK;
+    });
+}
+
+int debug_route(ba_engine* e, int64_t pair, ba_engine** kid, int64_t* local) {
+    if (!e->ran) return fail(e, BA_ERR_STATE, "ba_run first");
+    for (size_t k = 0; k < e->kids.size(); ++k) {
+        const auto& sh = e->shard[k];
+        const auto it = std::lower_bound(sh.begin(), sh.end(), (int32_t)pair);
+        if (it != sh.end() && *it == pair) {
+            *kid = e->kids[k];
+            *local = it - sh.begin();
+            return BA_OK;
+        }
+    }
+    return fail(e, BA_ERR_INVALID_ARG, "pair out of range");
+}
+
+}  // namespace multi
+
+extern "C" int ba_engine_create_multi(const int* devices, int n_devices, ba_engine** out) {
+    if (!out) return fail(nullptr, BA_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    if (n_devices == 0 || !devices) {  // all visible devices
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            return fail(nullptr, BA_ERR_NO_DEVICE, "no CUDA device (bialign_b200 has no CPU path)");
+    } else if (n_devices < 0) {
+        return fail(nullptr, BA_ERR_INVALID_ARG, "n_devices < 0");
+    }
+    const int K = ndev ? ndev : n_devices;
+    for (int k = 0; k < K; ++k)
+        for (int q = 0; q < k; ++q)
+            if (!ndev && devices[k] == devices[q]) return fail(nullptr, BA_ERR_INVALID_ARG, "device listed twice");
+    ba_engine* e = new ba_engine();
+    for (int k = 0; k < K; ++k) {
+        ba_engine* kid = nullptr;
+        const int rc = ba_engine_create(ndev ? k : devices[k], &kid);
+        if (rc) {  // g_create_error holds the text
+            for (ba_engine* x : e->kids) ba_engine_destroy(x);
+            delete e;
+            return rc;
+        }
+        e->kids.push_back(kid);
+    }
+    e->device = e->kids[0]->device;
+    e->sm_count = e->kids[0]->sm_count;
+    e->stats.device = e->device;
+    *out = e;
+    return BA_OK;
+}
+
+extern "C" int ba_engine_device_count(const ba_engine* e) { return e ? (e->kids.empty() ? 1 : (int)e->kids.size()) : 0; }
+

@@ -39,6 +39,8 @@
 // field of the winner (5 bits per state, 45 bits per cell) is streamed to HBM, one 8-byte word per
 // cell, each lane writing its own contiguous stream.
 #pragma once
+#include <utility>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -112,6 +114,58 @@ __device__ __forceinline__ void sts32_if(unsigned addr, int v, bool c) {
 __device__ __forceinline__ void cp_async4s_if(unsigned smem_dst, const void* gsrc, bool c) {
     asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %2, 0;\n @pp cp.async.ca.shared.global [%0], [%1], 4;\n}\n" ::"r"(smem_dst), "l"(gsrc), "r"((int)c) : "memory");
 }
+// Forms with a compile-time byte offset folded into the instruction (the statically unrolled "steady" iterations)
+template <int OFF>
+__device__ __forceinline__ void lds32o_if(int& v, unsigned addr, bool c) {  // v = [addr + OFF] iff c, else v keeps its value
+    asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %2, 0;\n @pp ld.shared.s32 %0, [%1+%3];\n}\n" : "+r"(v) : "r"(addr), "r"((int)c), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void sts32o(unsigned addr, int v) { asm volatile("st.shared.s32 [%0+%2], %1;\n" ::"r"(addr), "r"(v), "n"(OFF) : "memory"); }
+template <int OFF>
+__device__ __forceinline__ void sts32o_if(unsigned addr, int v, bool c) {
+    asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %2, 0;\n @pp st.shared.s32 [%0+%3], %1;\n}\n" ::"r"(addr), "r"(v), "r"((int)c), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void stg32o_if(const void* p, int v, bool c) {
+    asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %2, 0;\n @pp st.global.b32 [%0+%3], %1;\n}\n" ::"l"(p), "r"(v), "r"((int)c), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void stg64o_if(const void* p, unsigned lo, unsigned hi, bool c) {
+    asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %3, 0;\n @pp st.global.v2.b32 [%0+%4], {%1, %2};\n}\n" ::"l"(p), "r"(lo), "r"(hi), "r"((int)c), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void stg64o(const void* p, unsigned lo, unsigned hi) {
+    asm volatile("st.global.v2.b32 [%0+%3], {%1, %2};\n" ::"l"(p), "r"(lo), "r"(hi), "n"(OFF) : "memory");
+}
+template <int SOFF, int GOFF>
+__device__ __forceinline__ void cp_async4so_if(unsigned smem_dst, const void* gsrc, bool c) {
+    asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %2, 0;\n @pp cp.async.ca.shared.global [%0+%3], [%1+%4], 4;\n}\n" ::"r"(smem_dst), "l"(gsrc), "r"((int)c), "n"(SOFF), "n"(GOFF) : "memory");
+}
+// predicated vector forms for the short-delay exchange block (row 0 reads / last row writes)
+template <int OFF>
+__device__ __forceinline__ void lds64o_if(int& x, int& y, unsigned addr, bool c) {
+    asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %3, 0;\n @pp ld.shared.v2.s32 {%0, %1}, [%2+%4];\n}\n" : "+r"(x), "+r"(y) : "r"(addr), "r"((int)c), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void lds128o_if(int& x, int& y, int& z, int& w, unsigned addr, bool c) {
+    asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %5, 0;\n @pp ld.shared.v4.s32 {%0, %1, %2, %3}, [%4+%6];\n}\n"
+                 : "+r"(x), "+r"(y), "+r"(z), "+r"(w) : "r"(addr), "r"((int)c), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void sts64o_if(unsigned addr, int x, int y, bool c) {
+    asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %3, 0;\n @pp st.shared.v2.s32 [%0+%4], {%1, %2};\n}\n" ::"r"(addr), "r"(x), "r"(y), "r"((int)c), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void sts128o_if(unsigned addr, int x, int y, int z, int w, bool c) {
+    asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %5, 0;\n @pp st.shared.v4.s32 [%0+%6], {%1, %2, %3, %4};\n}\n" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w), "r"((int)c), "n"(OFF) : "memory");
+}
+template <int V> struct IC { static constexpr int value = V; };
+template <bool V> struct BC_ { static constexpr bool value = V; };
+// one statically unrolled ring period: iteration u uses ring slot u; one CTA barrier per iteration
+template <class F, int... U>
+__device__ __forceinline__ void steady_block(F& f, const int q, std::integer_sequence<int, U...>) {
+    ((f(BC_<true>{}, IC<U>{}, q + U), __syncthreads()), ...);
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
@@ -135,10 +189,9 @@ __device__ __forceinline__ void open3(int i0, int i1, int i2, int beta, int& o0,
 #ifndef BA_SYS_MAXNREG
 #define BA_SYS_MAXNREG 168  // 3 CTAs of 128 threads per SM: 65536 / 384 = 170
 #endif
-constexpr int LA = 8;   // cp.async look-ahead (iterations) of the boundary staging
-constexpr int LQ = 32;   // long-pair mode: progress flags are published / polled every LQ iterations (power of two);
-                        // measured on the 8192 x 8192 pair: 4 -> 158 ms (the extra barrier and the spinning thread dominate),
-                        // 16 -> 86 ms, 32 -> 84 ms, 64 -> 84 ms
+constexpr int LQ = 32;   // long-pair mode: progress flags are published / polled about every LQ iterations (rounded up to whole
+                        // ring periods); measured on the 8192 x 8192 pair: 4 -> 158 ms (the extra barrier and the spinning
+                        // thread dominate), 16 -> 86 ms, 32 -> 84 ms, 64 -> 84 ms
 constexpr int PRE = 4;  // iterations run before position 0: the virtual row above row 0 is 2 iterations ahead,
                         // so its first records must be staged before lane (0,0) reaches its first cell
 
@@ -151,26 +204,41 @@ struct Geo {
     static constexpr int RING = P + 3;                       // ring depth in iterations (max delay P+2; +1: reads never meet the write)
     static constexpr int NV = 12;                            // ring values per lane per iteration
     static constexpr int NX = 6;                             // short-delay values crossing a warp boundary
-    static constexpr int PB = 16;                            // prefetch-buffer depth (iterations), power of two > LA
+    static constexpr int LA = RING;                          // cp.async look-ahead (iterations) of the boundary staging
+    static constexpr int PB = 2 * RING;                      // prefetch-buffer depth (iterations): two ring periods
     static constexpr int REAL = (NV + NX) * LPR;             // values per boundary record (one iteration of one row)
     static constexpr int REC = (REAL + 3) & ~3;              // record stride in ints (16-byte multiple)
     static constexpr int RSLOT = NV * 32;
+    // short-delay exchange block, per slot: recB [LPR+1][4] = {Q[10][01] of the iteration before, L[10][01,10,11]} then
+    // recA [LPR+1][2] = {Q[10][11] of the iteration before, Q[10][10]} (one spare element: the last lane of row 0 reads past its row)
+    static constexpr int XSLOT = (6 * (LPR + 1) + 3) & ~3;   // ints per slot (16-byte multiple)
+    static constexpr int XA = 4 * (LPR + 1);                 // offset of recA inside a slot
+    static constexpr int LQB = ((LQ + RING - 1) / RING) * RING;  // flag period in iterations (whole ring periods)
 };
 
 // Shared-memory carve-up (ints unless noted):
 //   ring   [(G+1)][RING][NV][32]      ring[0] = staging ring of the virtual warp above warp 0
-//   xs     [(G+1)][4][NX][LPR]        short-delay values of the row above each warp; xs[G] = CTA output
+//   xs     [(G+1)][RING][XSLOT]       short-delay values of the row above each warp (two packed records per lane,
+//                                     see Geo); xs[G] = CTA output
 //   pb     [PB][REC]                  cp.async landing zone for the incoming boundary stream
 //   tb     [9][P][LPR] (+pad)         tie-break constants per (source state, b, lane column)  (TRACE)
 //   sim    [(nsym+1)][nsym]           similarity table (<< TB), last row zero
 //   resB/clsB  bytes, padded
+//
+// Iterations come in two forms.  The GENERIC form handles everything (range guards, origin, end cell, pad cells) with
+// ring slots computed from the iteration counter.  The STEADY form is used for whole ring periods (RING iterations,
+// statically unrolled, slot = position in the block) in which every lane of the warp sits strictly inside its pair
+// (S < j <= m - S): there all range tests are true, no end/origin event can occur, every ring / exchange / prefetch
+// slot is an immediate offset, the history registers are renamed instead of moved, and lanes outside the pair (rows
+// beyond n) simply compute garbage that no valid cell ever reads (sources have smaller coordinates; the band edges are
+// poisoned).  Each warp picks the form per ring period on its own; both forms execute one CTA barrier per iteration.
 //
 // LONG = one long pair spread over the whole grid (cooperative launch): CTA b runs the row blocks
 // ("passes") b, b+NC, b+2NC, ... and the boundary stream of pass p is consumed by pass p+1 on another
 // CTA while it is being produced.  Streams live in 2*NC global buffers (pass p -> buffer
 // p%NC + NC*((p/NC)&1): by the time it is overwritten, at pass p+2NC, pass p+1 has finished because
 // every later pass transitively depends on it).  Progress flags (pass id << 32 | records complete)
-// are published every LQ iterations with release semantics and polled with acquire loads; stream
+// are published every LQB iterations with release semantics and polled with acquire loads; stream
 // reads are 16-byte cp.async.cg (L2 only), so no stale L1 line can be seen across SMs.
 //
 // P16 = two pairs per work item in packed 16-bit halves (score only, pad-free, beta < 0): twice the pairs per
@@ -188,15 +256,20 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
     static_assert(!NA || (BNEG && !LONG && !P16), "non-affine flavour: batch mode, 32-bit");
     using G_ = Geo<S, PAD>;
     constexpr int W = G_::W, P = G_::P, LPR = G_::LPR, R = G_::R, RING = G_::RING, NV = G_::NV, NX = G_::NX, PB = G_::PB;
-    constexpr int RSLOT = G_::RSLOT, REC = G_::REC, REAL = G_::REAL;
-    constexpr bool RP2 = (RING & (RING - 1)) == 0;  // power-of-two ring: slots are masks of the iteration counter
+    constexpr int RSLOT = G_::RSLOT, REC = G_::REC, REAL = G_::REAL, LA = G_::LA, XSLOT = G_::XSLOT, LQB = G_::LQB, XA = G_::XA;
+    constexpr int RSLOTB = RSLOT * 4, XSLOTB = XSLOT * 4, RECB = REC * 4;
     constexpr bool PF = LONG && (P - 1) >= 2;       // ring inputs fetched one iteration ahead (pays off in the long-pair pipeline only)
+#ifdef BA_SYS_NO_STEADY
+    constexpr bool STEADY_OK = false;
+#else
+    constexpr bool STEADY_OK = !PAD;                // pad cells need the per-cell validity select
+#endif
     extern __shared__ __align__(16) int smem[];
     const int G = blockDim.x >> 5;
     const int RT = G * R;  // rows per pass
     int* ring = smem;
     int* xs = ring + (size_t)(G + 1) * RING * RSLOT;
-    int* pb = xs + (G + 1) * 4 * NX * LPR;
+    int* pb = xs + (G + 1) * RING * XSLOT;
     int* tbtab = pb + PB * REC;
     int* ssim = tbtab + P * LPR * 12;
     const int nsym = A.sc.nsym;
@@ -212,7 +285,7 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
     const bool lane_real = (r < R) && (c < W);
     const int a = c - S;
     const int sigma = 2 * (g * R + r) + c;
-    const bool row0 = (r == 0);
+    const bool row0 = (r == 0), lastrow = (r == R - 1);
     const int TB = TRACE ? A.tb_bits : 0;
     const int NEGP = P16 ? pack2(A.negp) : A.negp;
     const int beta = P16 ? pack2(A.beta_p) : A.beta_p, kGD = P16 ? pack2(A.k_gd) : A.k_gd, k2G = P16 ? pack2(A.k_2g) : A.k_2g;
@@ -223,7 +296,7 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
     const int pW = (!PAD && c == 0) ? NEGP : 0;
 
     // ---- one-time shared-memory initialisation: everything "minus infinity"
-    for (int q = tid; q < (int)((G + 1) * RING * RSLOT + (G + 1) * 4 * NX * LPR + PB * REC); q += blockDim.x) smem[q] = NEGP;
+    for (int q = tid; q < (int)((G + 1) * RING * RSLOT + (G + 1) * RING * XSLOT + PB * REC); q += blockDim.x) smem[q] = NEGP;
     if (TRACE && !NA)
         for (int q = tid; q < P * LPR * 12; q += blockDim.x) tbtab[q] = A.tbtab[q];
     for (int q = tid; q < (nsym + 1) * nsym; q += blockDim.x) ssim[q] = (q < nsym * nsym) ? A.sim_p[q] : 0;
@@ -245,9 +318,12 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
     const int baseS = own_ring + alane;                                // self
     // the same as shared-memory byte addresses: slot * RSLOT * 4 is then the only per-iteration address arithmetic
     const unsigned rU0 = smem_u32(ring + baseU0), rU1 = smem_u32(ring + baseU1), rW = smem_u32(ring + baseW), rS = smem_u32(ring + baseS);
-    const int xs_in = g * 4 * NX * LPR;                                // xs block feeding this warp's row 0
-    const int xs_out = (g + 1) * 4 * NX * LPR;
-    int* const xs_scratch = tbtab + 9 * P * LPR + c;  // 3*P*LPR >= 6*LPR spare ints behind the [9][P][LPR] table
+    const unsigned wS = smem_u32(ring + own_ring + lane);              // this lane's column of its own ring (writes)
+    const int xs_in = g * RING * XSLOT;                                // xs block feeding this warp's row 0
+    const int xs_out = (g + 1) * RING * XSLOT;
+    // byte addresses of this lane's recB entry (slot 0) in the block it reads as row 0 / writes as the last row
+    const unsigned xsi_b = smem_u32(xs + xs_in + 4 * c), xso_b = smem_u32(xs + xs_out + 4 * c);
+    const unsigned tb_b = smem_u32(tbtab + c);
 
     bool long_done = false;
     for (;;) {
@@ -321,10 +397,12 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
             const int io_e = io_thread ? tid : 0;
             const int io_v = io_e / LPR, io_cs = io_e - io_v * LPR;
             const bool io_ring = io_v < NV;
-            const int io_stride = io_ring ? RSLOT : NX * LPR;
+            const int io_stride = io_ring ? RSLOT : XSLOT;
+            // record elements beyond the ring values are the exchange block's 4*LPR recB ints, then its 2*LPR recA ints
+            const int io_x = io_e - NV * LPR;
             const int io_col = io_ring ? io_v * 32 + (R - 1) * LPR + io_cs
-                                       : (int)((G + 1) * RING * RSLOT) + (io_v - NV) * LPR + io_cs;
-            const int fl_src = io_col + (io_ring ? G * RING * RSLOT : G * 4 * NX * LPR);  // CTA output row
+                                       : (int)((G + 1) * RING * RSLOT) + (io_x < 4 * LPR ? io_x : XA + io_x - 4 * LPR);
+            const int fl_src = io_col + (io_ring ? G * RING * RSLOT : G * RING * XSLOT);  // CTA output row
             const int st_dst = io_col;                                                    // ring[0] / xs[0]
             // (the engine guarantees blockDim.x >= REAL, see engine.cu: one record element per thread)
             // Boundary streams hold record `rec` at offset (rec + PRE + 1) * REC, so the unconditional flush of
@@ -342,7 +420,8 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                     const bool rg = v < NV;
                     lg_ring |= rg ? (1 << u) : 0;
                     lg_real |= (e < REAL) ? (1 << u) : 0;
-                    lg_dst[u] = smem_u32(smem + (rg ? v * 32 + (R - 1) * LPR + cs : (int)((G + 1) * RING * RSLOT) + (v - NV) * LPR + cs));
+                    const int x = e - NV * LPR;
+                    lg_dst[u] = smem_u32(smem + (rg ? v * 32 + (R - 1) * LPR + cs : (int)((G + 1) * RING * RSLOT) + (x < 4 * LPR ? x : XA + x - 4 * LPR)));
                 }
             }
             int* fl_g = bnd_out + io_e;                                                  // record q-1 of iteration q = -PRE
@@ -358,17 +437,32 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
             const int c16_a1 = P16 ? vadd2(k2G2D, pW) : 0, c16_a3 = P16 ? vadd2(k2G2D, pU1) : 0;
             const int c16_a2 = P16 ? vadd2(kGD, pW) : 0, c16_a6 = P16 ? vadd2(kGD, pU1) : 0;
             const int c16_h22 = P16 ? vadd2(k2D, pW) : 0, c16_h12 = P16 ? vadd2(k2D, pU1) : 0;
-            // dead lanes (rows beyond n, band offsets outside [0,n]) stream their code words into a dump strip,
-            // so the store needs no lane test: only "is column j inside the pair"
-            uint64_t* code_ptr = nullptr;
-            if (TRACE) code_ptr = lane_ok ? A.codes + d.code_off + ((long long)i * W + c) * (long long)(m + 1) * W
-                                           : A.code_dump + (size_t)blockIdx.x * A.code_dump_stride;  // one strip per CTA
+            // Traceback codes are stored in the order they are computed: row block, warp, iteration, lane -- every warp
+            // appends 256 contiguous bytes per iteration to its own stream (two full lines per store instruction; the
+            // cell-major layout costs one 32-byte sector per lane).  Every lane stores in every iteration: slots of lanes
+            // or iterations outside the pair are simply never read (sys_code_index, kernels.cuh).
+            uint64_t* cw = nullptr;  // this lane's slot of the current iteration
+            if (TRACE) cw = A.codes + d.code_off + ((long long)pass * G + g) * (long long)(nit + PRE) * 32 + lane;
+
+            // Steady range of this warp [st_lo, st_hi): every lane of the warp has S < j <= m - max(S,1) throughout
+            // (all range tests true, no origin / end cell), the staged records exist, and no lane of the warp
+            // is a band offset below row 0 (k < 0, first rows of the first pass: their cells ARE read, as "minus infinity").
+            int st_lo = 0, st_hi = 0;
+            if (STEADY_OK) {
+                const int sig_lo = 2 * (g * R), sig_hi = 2 * (g * R + R - 1) + LPR - 1;
+                const int m_eff = P16 ? min(d.m, dh.m) : d.m;
+                st_lo = (S + 1) * P + sig_hi;
+                st_hi = (m_eff - (S > 0 ? S : 1) + 1) * P + sig_lo;
+                if (has_in) st_hi = min(st_hi, q_rec_lim - LA);
+                if (pass == 0 && g * R < S) st_hi = st_lo;
+            }
 
             // position of this lane one iteration before the first one (q = -PRE)
             int pos = -PRE - 1 - sigma;
             int j = -((-pos + P - 1) / P);
             int bb = pos - j * P;
-            int wslot = (((-PRE - 1) % RING) + RING) % RING;  // == (q & (RING-1)) below when RING is a power of two
+            int wslot = (((-PRE - 1) % RING) + RING) % RING;  // slot of the previous iteration: q mod RING
+            int pslot = (((-PRE - 1) % PB) + PB) % PB;        // prefetch-buffer slot of the previous iteration: q mod PB
             int mu1 = 0;
 
             // history registers (outputs of the last 1..3 iterations), all "minus infinity"
@@ -391,42 +485,36 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                 for (int t0 = -PRE; t0 < LA - PRE; ++t0) {
                     const int rec = t0 + 2 * RT;
                     if (tid < NVEC && rec < nit)
-                        cp_async16s(smem_u32(pb + (t0 & (PB - 1)) * REC + 4 * tid), bnd_in + (size_t)(rec + PRE + 1) * REC + 4 * tid);
+                        cp_async16s(smem_u32(pb + ((t0 + PB) % PB) * REC + 4 * tid), bnd_in + (size_t)(rec + PRE + 1) * REC + 4 * tid);
                     cp_async_commit();
                 }
             } else if (has_in) {  // prime the cp.async pipeline: records for iterations -PRE..LA-PRE-1
                 for (int t0 = -PRE; t0 < LA - PRE; ++t0) {
                     for (int e = tid; e < REAL; e += blockDim.x) {
                         const int rec = t0 + 2 * RT;
-                        if (rec >= 0 && rec < nit) cp_async4(pb + (t0 & (PB - 1)) * REC + e, bnd_in + (size_t)(rec + PRE + 1) * REC + e);
+                        if (rec >= 0 && rec < nit) cp_async4(pb + ((t0 + PB) % PB) * REC + e, bnd_in + (size_t)(rec + PRE + 1) * REC + e);
                     }
                     cp_async_commit();
                 }
             }
             __syncthreads();
 
-            for (int q = -PRE; q < nit; ++q) {
-                if (LONG && (q & (LQ - 1)) == 0) {
-                    if (tid == 0) {
-                        if (has_out && q > 0) {  // records 0..q-2 were stored before the last barrier
-                            __threadfence();
-                            st_release_u64(prog_out, tag_out | (unsigned long long)(q - 1));
-                        }
-                        if (has_in) {  // the next LQ iterations prefetch records up to q + LQ - 1 + LA + 2RT
-                            const unsigned long long want = tag_in | (unsigned long long)min(q + LQ + LA + 2 * RT, nit);
-                            while (ld_acquire_u64(prog_in) < want) __nanosleep(100);
-                        }
-                    }
-                    __syncthreads();
-                }
+            unsigned pb_cur = 0, pb_oth = 0;  // steady blocks: the two halves of the prefetch buffer (this thread's element)
+            // ---- one iteration (one band cell per lane).  ST: steady form, u = ring slot (compile time).
+            auto iteration = [&](auto st_, auto u_, const int q) __attribute__((always_inline)) {
+                constexpr bool ST = decltype(st_)::value;
+                constexpr int u = decltype(u_)::value;
                 // ---- advance position
                 ++bb;
                 if (bb == P) { bb = 0; ++j; }
-                wslot = RP2 ? (q & (RING - 1)) : ((wslot + 1 == RING) ? 0 : wslot + 1);
+                if (!ST) {
+                    wslot = (wslot + 1 == RING) ? 0 : wslot + 1;
+                    pslot = (pslot + 1 == PB) ? 0 : pslot + 1;
+                }
                 const int l = j + bb - S;
-                const bool valid = lane_ok && (bb < W) && ((unsigned)j <= (unsigned)d.m) && ((unsigned)l <= (unsigned)d.m);
+                const bool valid = ST || (lane_ok && (bb < W) && ((unsigned)j <= (unsigned)d.m) && ((unsigned)l <= (unsigned)d.m));
                 int vmask = 0, nmask = 0;  // P16: per-half validity
-                if (P16) {
+                if (P16 && !ST) {
                     const bool valid_hi = lane_ok_hi && (bb < W) && ((unsigned)j <= (unsigned)dh.m) && ((unsigned)l <= (unsigned)dh.m);
                     vmask = (valid ? 0x0000ffff : 0) | (valid_hi ? (int)0xffff0000 : 0);
                     nmask = NEGP & ~vmask;
@@ -445,9 +533,12 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                 }
 
                 // ---- flush the CTA's last row of iteration q-1 to the outgoing boundary stream
-                {
-                    const int ps = RP2 ? ((q - 1) & (RING - 1)) : ((wslot == 0) ? RING - 1 : wslot - 1);
-                    stg32_if(fl_g, lds32(fl_s + (io_ring ? ps : ((q - 1) & 3)) * io_stride_b), do_flush);
+                if constexpr (ST) {
+                    constexpr int ps = (u + RING - 1) % RING;
+                    stg32o_if<u * RECB>(fl_g, lds32(fl_s + ps * io_stride_b), do_flush);
+                } else {
+                    const int ps = (wslot == 0) ? RING - 1 : wslot - 1;
+                    stg32_if(fl_g, lds32(fl_s + ps * io_stride_b), do_flush);
                     fl_g += REC;
                 }
 
@@ -460,24 +551,30 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
 #pragma unroll
                     for (int y = 0; y < 3; ++y) { inH1[6 + y] = pfH[y]; inH1[y] = pfH[3 + y]; }
                     inF[8] = pfF[0]; inF[7] = pfF[1]; inF[6] = pfF[2]; inF[2] = pfF[3]; inF[1] = pfF[4]; inF[0] = pfF[5];
+                } else if constexpr (ST) {
+                    constexpr int oA = ((u + 2 * RING - (P + 2)) % RING) * RSLOTB, oB = ((u + 2 * RING - (P + 1)) % RING) * RSLOTB;
+                    constexpr int oC = ((u + 2 * RING - P) % RING) * RSLOTB, oD = ((u + 2 * RING - (P - 1)) % RING) * RSLOTB;
+                    inF[8] = lds32o<oA + 2 * 128>(rU0);  // x=1111 Q[11][11]
+                    inF[7] = lds32o<oB + 1 * 128>(rU0);  // x=1110 Q[11][10]
+                    inF[6] = lds32o<oB + 0 * 128>(rU1);  // x=1101 Q[11][01]
+                    inF[2] = lds32o<oB + 5 * 128>(rW);   // x=0111 Q[01][11]
+                    inF[1] = lds32o<oC + 4 * 128>(rW);   // x=0110 Q[01][10]
+                    inF[0] = lds32o<oC + 3 * 128>(rS);   // x=0101 Q[01][01]
+                    inH1[6] = lds32o<oC + 6 * 128>(rU1); inH1[7] = lds32o<oC + 7 * 128>(rU1); inH1[8] = lds32o<oC + 8 * 128>(rU1);  // x=1100 L[11][*]
+                    inH1[0] = lds32o<oD + 9 * 128>(rS); inH1[1] = lds32o<oD + 10 * 128>(rS); inH1[2] = lds32o<oD + 11 * 128>(rS);   // x=0100 L[01][*]
                 } else {
                     int rsA, rsB, rsC, rsD;  // ring slots written P+2, P+1, P, P-1 iterations ago
-                    if (RP2) {
-                        rsA = (q - (P + 2)) & (RING - 1); rsB = (q - (P + 1)) & (RING - 1);
-                        rsC = (q - P) & (RING - 1);       rsD = (q - (P - 1)) & (RING - 1);
-                    } else {
-                        rsA = wslot - (P + 2); if (rsA < 0) rsA += RING;
-                        rsB = wslot - (P + 1); if (rsB < 0) rsB += RING;
-                        rsC = wslot - P;       if (rsC < 0) rsC += RING;
-                        rsD = wslot - (P - 1); if (rsD < 0) rsD += RING;
-                    }
-                    inF[8] = lds32o<(2) * 128>(rU0 + rsA * (RSLOT * 4));  // x=1111 Q[11][11]
-                    inF[7] = lds32o<(1) * 128>(rU0 + rsB * (RSLOT * 4));  // x=1110 Q[11][10]
-                    inF[6] = lds32o<(0) * 128>(rU1 + rsB * (RSLOT * 4));  // x=1101 Q[11][01]
-                    inF[2] = lds32o<(5) * 128>(rW + rsB * (RSLOT * 4));   // x=0111 Q[01][11]
-                    inF[1] = lds32o<(4) * 128>(rW + rsC * (RSLOT * 4));   // x=0110 Q[01][10]
-                    inF[0] = lds32o<(3) * 128>(rS + rsC * (RSLOT * 4));   // x=0101 Q[01][01]
-                    const unsigned aU1C = rU1 + rsC * (RSLOT * 4), aSD = rS + rsD * (RSLOT * 4);
+                    rsA = wslot - (P + 2); if (rsA < 0) rsA += RING;
+                    rsB = wslot - (P + 1); if (rsB < 0) rsB += RING;
+                    rsC = wslot - P;       if (rsC < 0) rsC += RING;
+                    rsD = wslot - (P - 1); if (rsD < 0) rsD += RING;
+                    inF[8] = lds32o<(2) * 128>(rU0 + rsA * RSLOTB);  // x=1111 Q[11][11]
+                    inF[7] = lds32o<(1) * 128>(rU0 + rsB * RSLOTB);  // x=1110 Q[11][10]
+                    inF[6] = lds32o<(0) * 128>(rU1 + rsB * RSLOTB);  // x=1101 Q[11][01]
+                    inF[2] = lds32o<(5) * 128>(rW + rsB * RSLOTB);   // x=0111 Q[01][11]
+                    inF[1] = lds32o<(4) * 128>(rW + rsC * RSLOTB);   // x=0110 Q[01][10]
+                    inF[0] = lds32o<(3) * 128>(rS + rsC * RSLOTB);   // x=0101 Q[01][01]
+                    const unsigned aU1C = rU1 + rsC * RSLOTB, aSD = rS + rsD * RSLOTB;
                     inH1[6] = lds32o<6 * 128>(aU1C); inH1[7] = lds32o<7 * 128>(aU1C); inH1[8] = lds32o<8 * 128>(aU1C);  // x=1100 L[11][*]
                     inH1[0] = lds32o<9 * 128>(aSD); inH1[1] = lds32o<10 * 128>(aSD); inH1[2] = lds32o<11 * 128>(aSD);   // x=0100 L[01][*]
                 }
@@ -492,23 +589,22 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                     inH2[3 * y + 1] = __shfl_sync(0xffffffffu, hR[y][1], lsrcW);  // x=0010 D=1  R[y][10]
                     inH2[3 * y + 0] = hR[y][0];                                   // x=0001 D=1  R[y][01] (self)
                 }
-                {   // row 0: the row above lives in another warp (or in the staged boundary) -> xs, not shuffles.
-                    // Loads are unconditional (rows > 0 read the same in-bounds words and drop them); the last lane
-                    // of row 0 reads one element past its row: in bounds, and either invalid (PAD) or poisoned.
-                    const int* x3 = xs + xs_in + ((q - 3) & 3) * NX * LPR + c;
-                    const int* x2 = xs + xs_in + ((q - 2) & 3) * NX * LPR + c;
-                    const int* x1 = xs + xs_in + ((q - 1) & 3) * NX * LPR + c;
-                    const int a5 = x3[2 * LPR], a4 = x2[1 * LPR], a3 = x2[0 * LPR + 1];
-                    const int b0 = x1[3 * LPR + 1], b1 = x1[4 * LPR + 1], b2 = x1[5 * LPR + 1];
-                    inF[5] = row0 ? a5 : inF[5];    // Q[10][11] of lane c   (x2 = 1)
-                    inF[4] = row0 ? a4 : inF[4];    // Q[10][10] of lane c
-                    inF[3] = row0 ? a3 : inF[3];    // Q[10][01] of lane c+1 (x2 = 0)
-                    inH1[3] = row0 ? b0 : inH1[3];  // L[10][*]  of lane c+1
-                    inH1[4] = row0 ? b1 : inH1[4];
-                    inH1[5] = row0 ? b2 : inH1[5];
+                // row 0: the row above lives in another warp (or in the staged boundary) -> xs, not shuffles.
+                // Q[10][11] / Q[10][10] of lane c (x2 = 1), Q[10][01] and L[10][*] of lane c+1 (x2 = 0).  The last
+                // lane of row 0 reads one element past its row: in bounds, and either invalid (PAD) or poisoned.
+                if constexpr (ST) {
+                    constexpr int o1 = ((u + RING - 1) % RING) * XSLOTB, o2 = ((u + RING - 2) % RING) * XSLOTB;
+                    lds64o_if<o2 + XA * 4>(inF[5], inF[4], xsi_b - 8 * c, row0);          // recA of lane c, two iterations ago
+                    lds128o_if<o1 + 16>(inF[3], inH1[3], inH1[4], inH1[5], xsi_b, row0);  // recB of lane c+1, last iteration
+                } else {
+                    int s1 = wslot - 1, s2 = wslot - 2;
+                    if (s1 < 0) s1 += RING;
+                    if (s2 < 0) s2 += RING;
+                    lds64o_if<XA * 4>(inF[5], inF[4], xsi_b - 8 * c + s2 * XSLOTB, row0);
+                    lds128o_if<16>(inF[3], inH1[3], inH1[4], inH1[5], xsi_b + s1 * XSLOTB, row0);
+                    // origin: M[1111][0,0,0,0] = 0 (pyx:485) enters as the F input of state 1111 (mu1 = mu2 = 0 there)
+                    if (q == q_origin) inF[8] = 0;
                 }
-                // origin: M[1111][0,0,0,0] = 0 (pyx:485) enters as the F input of state 1111 (mu1 = mu2 = 0 there)
-                if (q == q_origin) inF[8] = 0;
 
                 // ---- additive constants per case (affine_score minus its gap-opening part), with the poisons
                 // of the pad-free flavour on exactly the cases whose source cell is outside the band:
@@ -581,11 +677,11 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                     const int v1 = xaddmax<P16>(inH1[t], kh1[t01], NEGP);  // floor: nothing ever drops below "minus infinity"
                     const int v = xaddmax<P16>(inH2[t], kh2[t23], v1);
                     M[t] = xaddmax<P16>(inF[t], kF[t], v);
-                    M[t] = P16 ? ((M[t] & vmask) | nmask) : (valid ? M[t] : NEGP);
+                    if (!ST) M[t] = P16 ? ((M[t] & vmask) | nmask) : (valid ? M[t] : NEGP);
                 }
 
                 // ---- results at the end cell
-                if (q == q_end) {
+                if (!ST && q == q_end) {
                     int Mv[9];  // plain values of the nine states (low half in 16-bit pair mode)
 #pragma unroll
                     for (int t = 0; t < 9; ++t) Mv[t] = P16 ? (int)(short)(M[t] & 0xffff) : (M[t] >> TB);
@@ -604,7 +700,7 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                     A.start_state[d.orig] = (uint8_t)st;
                 }
 
-                if (P16 && q == q_end_hi) {  // the second pair of the work item ends at its own cell
+                if (P16 && !ST && q == q_end_hi) {  // the second pair of the work item ends at its own cell
                     int best = M[0] >> 16;
 #pragma unroll
                     for (int t = 1; t < 9; ++t) best = max(best, M[t] >> 16);
@@ -618,23 +714,27 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                 if (TRACE && NA) {
                     // the cell's single traceback code: case index of the best state (value desc, case order asc)
                     const int bestp = vmax3(vmax3(M[0], M[1], M[2]), vmax3(M[3], M[4], M[5]), vmax3(M[6], M[7], M[8]));
-                    stg64_if(code_ptr + j * W + bb, 15u - (unsigned)(bestp & 15), 0u, (unsigned)j <= (unsigned)m && (P == W || bb < W));
+                    if constexpr (ST) stg64o<u * 256>(cw, 15u - (unsigned)(bestp & 15), 0u);
+                    else { stg64o<0>(cw, 15u - (unsigned)(bestp & 15), 0u); cw += 32; }
                     const int msk = ~((1 << TB) - 1);
 #pragma unroll
                     for (int t = 0; t < 9; ++t) M[t] &= msk;  // as a source a state carries no tie information
                 } else if (TRACE) {
-                    const unsigned lo = (M[0] & 31) | ((M[1] & 31) << 5) | ((M[2] & 31) << 10) | ((M[3] & 31) << 15) |
-                                        ((M[4] & 31) << 20) | ((M[5] & 31) << 25);
-                    const unsigned hi = (M[6] & 31) | ((M[7] & 31) << 5) | ((M[8] & 31) << 10);
-                    // cells of a valid column always lie inside this lane's code row (those with l outside the pair
-                    // are unused slots); pad cells (P > W) would spill into the next column and are skipped
-                    stg64_if(code_ptr + j * W + bb, lo, hi, (unsigned)j <= (unsigned)m && (P == W || bb < W));
+                    // nine 5-bit id fields: each funnel shift pushes one field in at the top of its word, so state t < 6 ends
+                    // at bit 2 + 5t of the low word and state t >= 6 at bit 17 + 5(t-6) of the high word (traceback.cu)
+                    unsigned lo = 0, hi = 0;
+#pragma unroll
+                    for (int t = 0; t < 6; ++t) lo = __funnelshift_r(lo, (unsigned)M[t], 5);
+#pragma unroll
+                    for (int t = 6; t < 9; ++t) hi = __funnelshift_r(hi, (unsigned)M[t], 5);
+                    if constexpr (ST) stg64o<u * 256>(cw, lo, hi);
+                    else { stg64o<0>(cw, lo, hi); cw += 32; }
                     // table layout [source state][b][lane column]: for one source state the lanes of a warp read
                     // (at most P*LPR <= 32) consecutive words -> no bank conflicts
-                    const int* tp = tbtab + bb * LPR + c;
+                    const unsigned tp = tb_b + bb * (LPR * 4);
                     const int msk = ~((1 << TB) - 1);
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) M[t] = (M[t] & msk) | tp[t * (P * LPR)];
+                    for (int t = 0; t < 9; ++t) M[t] = (M[t] & msk) | lds32(tp + t * (P * LPR * 4));
                 }
 
                 // ---- publish: R (second alignment decided), L (first decided), Q (both)
@@ -649,45 +749,57 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
 
                 // prefetch the ring inputs of the next iteration (slots written >= 2 iterations before it)
                 if (PF) {
-                    int rsA, rsB, rsC, rsD;
-                    if (RP2) {
-                        rsA = (q + 1 - (P + 2)) & (RING - 1); rsB = (q + 1 - (P + 1)) & (RING - 1);
-                        rsC = (q + 1 - P) & (RING - 1);       rsD = (q + 1 - (P - 1)) & (RING - 1);
+                    if constexpr (ST) {
+                        constexpr int oA = ((u + 1 + 2 * RING - (P + 2)) % RING) * RSLOTB, oB = ((u + 1 + 2 * RING - (P + 1)) % RING) * RSLOTB;
+                        constexpr int oC = ((u + 1 + 2 * RING - P) % RING) * RSLOTB, oD = ((u + 1 + 2 * RING - (P - 1)) % RING) * RSLOTB;
+                        pfF[0] = lds32o<oA + 2 * 128>(rU0);
+                        pfF[1] = lds32o<oB + 1 * 128>(rU0);
+                        pfF[2] = lds32o<oB + 0 * 128>(rU1);
+                        pfF[3] = lds32o<oB + 5 * 128>(rW);
+                        pfF[4] = lds32o<oC + 4 * 128>(rW);
+                        pfF[5] = lds32o<oC + 3 * 128>(rS);
+                        pfH[0] = lds32o<oC + 6 * 128>(rU1); pfH[1] = lds32o<oC + 7 * 128>(rU1); pfH[2] = lds32o<oC + 8 * 128>(rU1);
+                        pfH[3] = lds32o<oD + 9 * 128>(rS); pfH[4] = lds32o<oD + 10 * 128>(rS); pfH[5] = lds32o<oD + 11 * 128>(rS);
                     } else {
                         const int ns = (wslot + 1 == RING) ? 0 : wslot + 1;
+                        int rsA, rsB, rsC, rsD;
                         rsA = ns - (P + 2); if (rsA < 0) rsA += RING;
                         rsB = ns - (P + 1); if (rsB < 0) rsB += RING;
                         rsC = ns - P;       if (rsC < 0) rsC += RING;
                         rsD = ns - (P - 1); if (rsD < 0) rsD += RING;
+                        pfF[0] = lds32o<(2) * 128>(rU0 + rsA * RSLOTB);  // x=1111 Q[11][11]
+                        pfF[1] = lds32o<(1) * 128>(rU0 + rsB * RSLOTB);  // x=1110 Q[11][10]
+                        pfF[2] = lds32o<(0) * 128>(rU1 + rsB * RSLOTB);  // x=1101 Q[11][01]
+                        pfF[3] = lds32o<(5) * 128>(rW + rsB * RSLOTB);   // x=0111 Q[01][11]
+                        pfF[4] = lds32o<(4) * 128>(rW + rsC * RSLOTB);   // x=0110 Q[01][10]
+                        pfF[5] = lds32o<(3) * 128>(rS + rsC * RSLOTB);   // x=0101 Q[01][01]
+                        const unsigned aU1C = rU1 + rsC * RSLOTB, aSD = rS + rsD * RSLOTB;
+                        pfH[0] = lds32o<6 * 128>(aU1C); pfH[1] = lds32o<7 * 128>(aU1C); pfH[2] = lds32o<8 * 128>(aU1C);   // x=1100 L[11][*]
+                        pfH[3] = lds32o<9 * 128>(aSD); pfH[4] = lds32o<10 * 128>(aSD); pfH[5] = lds32o<11 * 128>(aSD);    // x=0100 L[01][*]
                     }
-                    pfF[0] = lds32o<(2) * 128>(rU0 + rsA * (RSLOT * 4));  // x=1111 Q[11][11]
-                    pfF[1] = lds32o<(1) * 128>(rU0 + rsB * (RSLOT * 4));  // x=1110 Q[11][10]
-                    pfF[2] = lds32o<(0) * 128>(rU1 + rsB * (RSLOT * 4));  // x=1101 Q[11][01]
-                    pfF[3] = lds32o<(5) * 128>(rW + rsB * (RSLOT * 4));   // x=0111 Q[01][11]
-                    pfF[4] = lds32o<(4) * 128>(rW + rsC * (RSLOT * 4));   // x=0110 Q[01][10]
-                    pfF[5] = lds32o<(3) * 128>(rS + rsC * (RSLOT * 4));   // x=0101 Q[01][01]
-                    const unsigned aU1C = rU1 + rsC * (RSLOT * 4), aSD = rS + rsD * (RSLOT * 4);
-                    pfH[0] = lds32o<6 * 128>(aU1C); pfH[1] = lds32o<7 * 128>(aU1C); pfH[2] = lds32o<8 * 128>(aU1C);   // x=1100 L[11][*]
-                    pfH[3] = lds32o<9 * 128>(aSD); pfH[4] = lds32o<10 * 128>(aSD); pfH[5] = lds32o<11 * 128>(aSD);    // x=0100 L[01][*]
                 }
 
-                // ring: long-delay values
-                int* wr = ring + own_ring + wslot * RSLOT + lane;
-#pragma unroll
-                for (int y = 0; y < 3; ++y) {
-                    wr[(0 + y) * 32] = Qv[2][y];
-                    wr[(3 + y) * 32] = Qv[0][y];
-                    wr[(6 + y) * 32] = Lv[2][y];
-                    wr[(9 + y) * 32] = Lv[0][y];
-                }
-                {   // short-delay values for the warp below / the next pass: only the last row's matter; the other
-                    // rows store into a scratch strip (the unused tail of the tie-break table) -- no divergent branch
-                    int* xo = (r == R - 1) ? xs + xs_out + (q & 3) * NX * LPR + c : xs_scratch;
+                // ring: long-delay values; short-delay values for the warp below / the next pass (only the last row's matter)
+                if constexpr (ST) {
 #pragma unroll
                     for (int y = 0; y < 3; ++y) {
-                        xo[y * LPR] = Qv[1][y];
-                        xo[(3 + y) * LPR] = Lv[1][y];
+                        if (y == 0) { sts32o<u * RSLOTB + 0 * 128>(wS, Qv[2][0]); sts32o<u * RSLOTB + 3 * 128>(wS, Qv[0][0]); sts32o<u * RSLOTB + 6 * 128>(wS, Lv[2][0]); sts32o<u * RSLOTB + 9 * 128>(wS, Lv[0][0]); }
+                        if (y == 1) { sts32o<u * RSLOTB + 1 * 128>(wS, Qv[2][1]); sts32o<u * RSLOTB + 4 * 128>(wS, Qv[0][1]); sts32o<u * RSLOTB + 7 * 128>(wS, Lv[2][1]); sts32o<u * RSLOTB + 10 * 128>(wS, Lv[0][1]); }
+                        if (y == 2) { sts32o<u * RSLOTB + 2 * 128>(wS, Qv[2][2]); sts32o<u * RSLOTB + 5 * 128>(wS, Qv[0][2]); sts32o<u * RSLOTB + 8 * 128>(wS, Lv[2][2]); sts32o<u * RSLOTB + 11 * 128>(wS, Lv[0][2]); }
                     }
+                    sts128o_if<u * XSLOTB>(xso_b, hQ10[0], Lv[1][0], Lv[1][1], Lv[1][2], lastrow);
+                    sts64o_if<u * XSLOTB + XA * 4>(xso_b - 8 * c, hQ10[2], Qv[1][1], lastrow);
+                } else {
+                    int* wr = ring + own_ring + wslot * RSLOT + lane;
+#pragma unroll
+                    for (int y = 0; y < 3; ++y) {
+                        wr[(0 + y) * 32] = Qv[2][y];
+                        wr[(3 + y) * 32] = Qv[0][y];
+                        wr[(6 + y) * 32] = Lv[2][y];
+                        wr[(9 + y) * 32] = Lv[0][y];
+                    }
+                    sts128o_if<0>(xso_b + wslot * XSLOTB, hQ10[0], Lv[1][0], Lv[1][1], Lv[1][2], lastrow);
+                    sts64o_if<XA * 4>(xso_b - 8 * c + wslot * XSLOTB, hQ10[2], Qv[1][1], lastrow);
                 }
                 // history shift
                 h3Q1011 = h2Q1011;
@@ -702,39 +814,82 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                 }
 
                 // ---- stage the incoming boundary: virtual row above warp 0, iteration q
+                const int ws = ST ? u : wslot;
                 if (LONG && has_in) {
                     cp_async_wait<LA - 1>();
                     if (tid < NVEC) {
+                        const int ps_r = ST ? ((pslot + 1 == PB ? 0 : pslot + 1) + u) : pslot;  // prefetch-buffer slot of q
+                        const int ps_w = ps_r >= LA ? ps_r - LA : ps_r + LA;                     // ... and of q + LA
                         int4 v4 = make_int4(NEGP, NEGP, NEGP, NEGP);
-                        if (q < q_rec_lim) v4 = *reinterpret_cast<const int4*>(pb + (q & (PB - 1)) * REC + 4 * tid);
+                        if (ST || q < q_rec_lim) v4 = *reinterpret_cast<const int4*>(pb + ps_r * REC + 4 * tid);
                         const int vals[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if ((lg_real >> u) & 1)
-                                sts32(lg_dst[u] + (((lg_ring >> u) & 1) ? wslot * (RSLOT * 4) : (q & 3) * (NX * LPR * 4)), vals[u]);
-                        if (q + LA < q_rec_lim)
-                            cp_async16s(smem_u32(pb + ((q + LA) & (PB - 1)) * REC + 4 * tid),
+                        for (int uu = 0; uu < 4; ++uu)
+                            if ((lg_real >> uu) & 1)
+                                sts32(lg_dst[uu] + (((lg_ring >> uu) & 1) ? ws * RSLOTB : ws * XSLOTB), vals[uu]);
+                        if (ST || q + LA < q_rec_lim)
+                            cp_async16s(smem_u32(pb + ps_w * REC + 4 * tid),
                                         bnd_in + (size_t)(q + LA + 2 * RT + PRE + 1) * REC + 4 * tid);
                     }
                     cp_async_commit();
                 } else if (has_in) {
                     cp_async_wait<LA - 1>();
-                    {
-                        int val = lds32(pb_s + (q & (PB - 1)) * (REC * 4));
+                    if constexpr (ST) {
+                        // pb_cur / pb_oth: this thread's element in the half of the prefetch buffer that holds iterations
+                        // q0..q0+RING-1 / that receives q0+LA.. (set per block below)
+                        const int val = lds32o<u * RECB>(pb_cur);
+                        sts32_if(st_s + u * io_stride_b, val, do_stage);
+                        cp_async4so_if<u * RECB, u * RECB>(pb_oth, st_g, do_stage);
+                    } else {
+                        int val = lds32(pb_s + pslot * RECB);
                         val = (q < q_rec_lim) ? val : NEGP;
-                        sts32_if(st_s + (io_ring ? wslot : (q & 3)) * io_stride_b, val, do_stage);
-                        cp_async4s_if(pb_s + ((q + LA) & (PB - 1)) * (REC * 4), st_g, do_stage && q + LA < q_rec_lim);
+                        sts32_if(st_s + wslot * io_stride_b, val, do_stage);
+                        const int pw = pslot >= LA ? pslot - LA : pslot + LA;
+                        cp_async4s_if(pb_s + pw * RECB, st_g, do_stage && q + LA < q_rec_lim);
+                        st_g += REC;
                     }
-                    st_g += REC;
                     cp_async_commit();
                 }
-                __syncthreads();
-            }  // iterations
+            };
+
+            int next_flag = 0;  // LONG: next iteration (a multiple of RING) at which progress is published / awaited
+            for (int q = -PRE; q < nit;) {
+                const bool aligned = (wslot == RING - 1);  // q is a multiple of RING
+                if (LONG && aligned && q >= next_flag) {
+                    if (tid == 0) {
+                        if (has_out && q > 0) {  // records 0..q-2 were stored before the last barrier
+                            __threadfence();
+                            st_release_u64(prog_out, tag_out | (unsigned long long)(q - 1));
+                        }
+                        if (has_in) {  // the iterations up to the next flag point prefetch records up to q + LQB - 1 + LA + 2RT
+                            const unsigned long long want = tag_in | (unsigned long long)min(q + LQB + LA + 2 * RT, nit);
+                            while (ld_acquire_u64(prog_in) < want) __nanosleep(100);
+                        }
+                    }
+                    next_flag = q + LQB;
+                    __syncthreads();
+                }
+                if (STEADY_OK && aligned && q >= st_lo && q + RING <= st_hi) {  // warp-uniform
+                    const int ph = (pslot + 1 == PB) ? 0 : pslot + 1;           // 0 or RING
+                    pb_cur = pb_s + ph * RECB;
+                    pb_oth = pb_s + (ph ? 0 : LA) * RECB;
+                    steady_block(iteration, q, std::make_integer_sequence<int, RING>{});
+                    q += RING;
+                    pslot = ph + RING - 1;
+                    fl_g += RING * REC;
+                    st_g += RING * REC;
+                    if (TRACE) cw += RING * 32;
+                } else {
+                    iteration(BC_<false>{}, IC<0>{}, q);
+                    __syncthreads();
+                    ++q;
+                }
+            }
             if (has_out) {  // last iteration's record, then make the stream visible to the next pass
                 for (int e = tid; e < REAL; e += blockDim.x) {
                     const int v = e / LPR, cs = e - v * LPR;
                     const int val = (v < NV) ? ring[(G * RING + wslot) * RSLOT + v * 32 + (R - 1) * LPR + cs]
-                                             : xs[(G * 4 + ((nit - 1) & 3)) * NX * LPR + (v - NV) * LPR + cs];
+                                             : xs[(G * RING + wslot) * XSLOT + (e - NV * LPR < 4 * LPR ? e - NV * LPR : XA + e - NV * LPR - 4 * LPR)];
                     bnd_out[(size_t)(nit + PRE) * REC + e] = val;
                 }
                 __threadfence();
@@ -750,7 +905,7 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
             if (!has_out && has_in) {
                 // leaving a multi-pass pair: the staging ring must read "minus infinity" again
                 for (int qq = tid; qq < RING * RSLOT; qq += blockDim.x) ring[qq] = NEGP;
-                for (int qq = tid; qq < 4 * NX * LPR; qq += blockDim.x) xs[qq] = NEGP;
+                for (int qq = tid; qq < RING * XSLOT; qq += blockDim.x) xs[qq] = NEGP;
             }
             __syncthreads();
         }  // passes
@@ -761,7 +916,7 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
 template <int S, bool PAD>
 size_t smem_bytes_t(int G, int nsym, int bpad, bool p16 = false) {
     using G_ = Geo<S, PAD>;
-    size_t ints = (size_t)(G + 1) * G_::RING * G_::RSLOT + (size_t)(G + 1) * 4 * G_::NX * G_::LPR + (size_t)G_::PB * G_::REC +
+    size_t ints = (size_t)(G + 1) * G_::RING * G_::RSLOT + (size_t)(G + 1) * G_::RING * G_::XSLOT + (size_t)G_::PB * G_::REC +
                   (size_t)G_::P * G_::LPR * 12 + (size_t)(nsym + 1) * nsym;
     size_t bytes = ints * 4 + (p16 ? 4 : 2) * (size_t)bpad;  // molecule B residues + classes (of both pairs in 16-bit pair mode)
     return (bytes + 15) & ~(size_t)15;

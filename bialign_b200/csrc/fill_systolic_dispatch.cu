@@ -32,6 +32,11 @@ int sys_iters(int S, bool pad, int G, int m) {
     const SysGeo g = sys_geo(S, pad);
     return (m + 1) * g.P + 2 * (G * g.R - 1) + g.LPR + g.RING;
 }
+long long sys_code_words(int S, bool pad, int G, int n, int m) {
+    const SysGeo g = sys_geo(S, pad);
+    const int RT = G * g.R;
+    return (long long)((n + RT) / RT) * G * (sys_iters(S, pad, G, m) + 4 /* PRE */) * 32;
+}
 // records -(PRE+1) .. nit-1 (PRE = 4 warm-up iterations of the kernel, one slack record in front)
 size_t sys_boundary_ints(int S, bool pad, int G, int mmax) { return (size_t)(sys_iters(S, pad, G, mmax) + 8) * sys_geo(S, pad).REC; }
 

@@ -43,8 +43,6 @@ struct SysArgs {
     int* bnd;                 // per CTA: two boundary streams of bnd_iters records
     int bnd_iters;
     uint64_t* codes;
-    uint64_t* code_dump;      // per CTA a strip of (mmax+2)*(2s+1) words: where lanes outside the pair stream
-    size_t code_dump_stride;  //   their code words (shared strips would serialise in L2)
     long long* scores;
     uint8_t* start_state;
     int* end_values;
@@ -57,6 +55,8 @@ struct TraceArgs {
     const uint64_t* codes;
     int fmt;                  // 0: nibble t = case id (generic kernel); 1: 5-bit tie fields (systolic kernel);
                               // 2: non-affine model, low nibble = case index 0..12
+    int sysG;                 // > 0: the table has the systolic kernel's layout (sys_code_index) with sysG warps per CTA
+    int R, LPR, P, RING;      //      and this geometry
     const uint8_t* start_state;
     uint8_t* trace;           // slots; columns are written backwards from the end of each slot
     int* trace_len;           // [n_pairs] caller order
@@ -74,6 +74,15 @@ size_t sys_smem_bytes(int S, bool pad, int G, int nsym, int mmax, bool p16 = fal
 int sys_occupancy_p16(int S, int G, size_t smem);
 cudaError_t launch_fill_systolic_p16(const SysArgs& A, int grid, int G, size_t smem, cudaStream_t st);
 int sys_iters(int S, bool pad, int G, int m);
+// Code-table geometry of the systolic kernel: [row block][warp][iteration][lane], one uint64 per slot.
+long long sys_code_words(int S, bool pad, int G, int n, int m);
+__host__ __device__ __forceinline__ long long sys_code_index(int R, int LPR, int P, int S, int G, int nit_all, int i, int j, int a, int b) {
+    // nit_all = iterations per row block incl. the PRE warm-up ones; lane (row r of warp g, column c = a+S) computes
+    // cell (j, b) at iteration j*P + (b+S) + 2*(g*R + r) + c  (fill_systolic.cuh)
+    const int RT = G * R, pass = i / RT, rr = i - pass * RT, g = rr / R, r = rr - g * R, c = a + S;
+    const int qq = j * P + (b + S) + 2 * rr + c + 4 /* PRE */;
+    return (((long long)pass * G + g) * nit_all + qq) * 32 + r * LPR + c;
+}
 size_t sys_boundary_ints(int S, bool pad, int G, int mmax);
 int sys_occupancy(int S, bool trace, bool pad, bool bneg, int G, size_t smem);
 int sys_boff(int S, bool pad, int G);

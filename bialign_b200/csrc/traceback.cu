@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(128) traceback_kernel(TraceArgs A) {
     const PairDesc d = A.pairs[pi];
     const uint64_t* codes = A.codes + d.code_off;
     const int s = A.s, n = d.n, m = d.m;
+    // iterations per row block in the systolic kernel's table (fill_systolic.cuh: nit + PRE)
+    const int nit_all = A.sysG ? (m + 1) * A.P + 2 * (A.sysG * A.R - 1) + A.LPR + A.RING + 4 : 0;
     int i = n, j = m, k = n, l = m;
     int state = A.start_state[d.orig];
     uint8_t* out = A.trace + d.trace_off + d.trace_cap;  // one past the end of the slot
@@ -29,7 +31,8 @@ __global__ void __launch_bounds__(128) traceback_kernel(TraceArgs A) {
             break;
         }
         first = false;
-        const uint64_t wd = __ldg(codes + code_index(m, s, i, j, k - i, l - j));
+        const uint64_t wd = __ldg(codes + (A.sysG ? sys_code_index(A.R, A.LPR, A.P, s, A.sysG, nit_all, i, j, k - i, l - j)
+                                                  : code_index(m, s, i, j, k - i, l - j)));
         int id;
         if (A.fmt == 2) {  // non-affine: the walk ends when no case reproduces the value (origin), pyx:521-528
             const int cidx = (int)(wd & 15);
@@ -43,13 +46,14 @@ __global__ void __launch_bounds__(128) traceback_kernel(TraceArgs A) {
         if (A.fmt == 0) {
             id = (int)((wd >> (4 * state)) & 15);
         } else {
-            // systolic format: fields 0..5 in the low word, 6..8 in the high word, 5 bits each.  The field is the
+            // systolic format: 5-bit fields, state t < 6 at bit 2 + 5t of the low word, t >= 6 at bit 17 + 5(t-6) of the high word
+            // (the fill pushes them in with funnel shifts).  The field is the
             // id part of the winner's tie-break: a source state src carries 27 - src;
             //   19..27        full column, case id = source = 27 - f                     (ids 0-8)
             //    9..17        x=(0,0,t2,t3), source (t01, h): f = 17 - 3*t01 - rank(h)   (ids 9-11, h = 11,10,01)
             //    0..8         x=(t0,t1,0,0), source (h, t23): f = 8 - 3*rank(h) - t23    (ids 12-14)
             const unsigned half = state < 6 ? (unsigned)wd : (unsigned)(wd >> 32);
-            const int f = (int)((half >> (5 * (state < 6 ? state : state - 6))) & 31);
+            const int f = (int)((half >> (state < 6 ? 2 + 5 * state : 17 + 5 * (state - 6))) & 31);
             const int t01 = state / 3, t23 = state % 3;
             id = 15;
             if (f >= 19 && f <= 27) id = 27 - f;

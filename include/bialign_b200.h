@@ -70,6 +70,15 @@ typedef struct ba_stats {
 
 /* One engine per process per GPU (device = CUDA ordinal, normally LOCAL_RANK). */
 BA_API int ba_engine_create(int device, ba_engine** out);
+/* One engine for several GPUs of the box, driven from this one process (replaces nothing in the
+ * reference, which is single-threaded: pairs are independent, so the pair list is sharded).  devices = n_devices
+ * CUDA ordinals, or NULL / 0 for all visible devices.  The returned handle takes every call below:
+ * ba_load_pairs deals the pairs over the devices by cost (longest first), ba_load_sequences uploads the sequence
+ * table to each, ba_run drives one host thread per device, and the fetch calls write scores / traces straight into the
+ * caller's arrays in the caller's pair order.  No collective and no peer traffic: results travel device -> host only. */
+BA_API int ba_engine_create_multi(const int* devices, int n_devices, ba_engine** out);
+/* Number of devices behind a handle (1 for ba_engine_create). */
+BA_API int ba_engine_device_count(const ba_engine* e);
 BA_API void ba_engine_destroy(ba_engine* e);
 /* Text of the last error on this engine (or of the last failed ba_engine_create when e == NULL). */
 BA_API const char* ba_last_error(const ba_engine* e);

@@ -67,10 +67,10 @@ def main():
         res, cls, off, pa, pb = workloads.protein_pairs(3000, seed=3)
         run("non-affine: 3000 protein pairs 200-500 s=2 trace", al, res, cls, off, pa, pb, True)
         run("non-affine: 3000 protein pairs 200-500 s=2 score-only", al, res, cls, off, pa, pb, False)
-        al.engine.set_option("kernel", 0)
+        al.set_option("kernel", 0)
         res, cls, off, pa, pb = workloads.protein_pairs(64, seed=3)
         run("non-affine, general level kernel: 64 pairs trace", al, res, cls, off, pa, pb, True, reps=1)
-        al.engine.set_option("kernel", -1)
+        al.set_option("kernel", -1)
     if "5" in which:
         al = BatchAligner(max_shift=3, **prot)
         res, cls, off, pa, pb = workloads.protein_pairs(1, lo=8192, hi=8192, seed=5)

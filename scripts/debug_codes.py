@@ -14,8 +14,8 @@ def main(s, seed, npairs, lo, hi, warps=4, kernel=1, pad=-1, long=-1, extra=None
     if extra: params.update(extra)
     seqs, structs, pairs = _random_protein_batch(rng, npairs, lo, hi)
     al = BatchAligner(**params)
-    al.engine.set_option("kernel", kernel); al.engine.set_option("warps_per_cta", warps)
-    al.engine.set_option("pad", pad); al.engine.set_option("long", long)
+    al.set_option("kernel", kernel); al.set_option("warps_per_cta", warps)
+    al.set_option("pad", pad); al.set_option("long", long)
     scores, cols, offsets, complete = al.align(seqs, structs, pairs, want_trace=True)
     kind = al.engine.stats()["kernel_kind"]
     W = 2 * s + 1

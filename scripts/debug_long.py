@@ -11,7 +11,7 @@ for s in (1, 2, 3):
     params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150, gap_cost=-50, shift_cost=-150, max_shift=s)
     seqs, structs, pairs = _random_protein_batch(rng, 3, 90, 260)
     al = BatchAligner(**params)
-    al.engine.set_option("kernel", 1); al.engine.set_option("pad", pad); al.engine.set_option("warps_per_cta", warps); al.engine.set_option("long", 1)
+    al.set_option("kernel", 1); al.set_option("pad", pad); al.set_option("warps_per_cta", warps); al.set_option("long", 1)
     for rep in range(3):
         scores, cols, offsets, complete = al.align(seqs, structs, pairs, want_trace=True)
         kind = al.engine.stats()["kernel_kind"]

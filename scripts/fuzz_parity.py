@@ -47,8 +47,8 @@ for rd in range(rounds):
     pad = int(rng.choice([-1, 0, 1]))
     al = BatchAligner(**params)
     try:
-        al.engine.set_option("kernel", kern if kern != 1 else -1); al.engine.set_option("pad", pad)
-        al.engine.set_option("long", int(rng.choice([-1, -1, 1]))); al.engine.set_option("warps_per_cta", int(rng.choice([0, 0, 2, 4, 6])))
+        al.set_option("kernel", kern if kern != 1 else -1); al.set_option("pad", pad)
+        al.set_option("long", int(rng.choice([-1, -1, 1]))); al.set_option("warps_per_cta", int(rng.choice([0, 0, 2, 4, 6])))
         try:
             scores, cols, offsets, complete = al.align(seqs, structs, pairs, want_trace=True)
             kind = al.engine.stats()["kernel_kind"]
@@ -61,7 +61,7 @@ for rd in range(rounds):
             raise
     finally:
         for k, v in (("kernel", -1), ("pad", -1), ("long", -1), ("warps_per_cta", 0)):
-            al.engine.set_option(k, v)
+            al.set_option(k, v)
     for q, (ia, ib) in enumerate(pairs):
         r = oracle.run(seqs[ia], seqs[ib], structs[ia], structs[ib], params, mode="literal")
         ok = int(scores[q]) == r["score"] and trace_hex(cols, offsets, q) == r["trace"] and int(s2[q]) == r["score"]

@@ -30,9 +30,9 @@ for G in range(2, 9):
     else:
         al = BatchAligner(max_shift=3, **workloads.PROTEIN_PARAMS)
         args = workloads.protein_pairs(1, lo=8192, hi=8192, seed=5) + (True,)
-    al.engine.set_option("warps_per_cta", G)
+    al.set_option("warps_per_cta", G)
     try:
         r = bc.run(f"cfg{which} G={G}", al, *args, reps=2)
     except Exception as ex:
         print("G", G, "failed", ex)
-    al.engine.set_option("warps_per_cta", 0)
+    al.set_option("warps_per_cta", 0)

@@ -16,7 +16,7 @@ def _worker(rank, world, port, out_dir):
     sys.path.insert(0, os.path.dirname(HERE))
     import oracle
     from bialign_b200 import workloads
-    from bialign_b200.batch import gather_scores, lpt_shards, pair_cost
+    from bialign_b200.batch import gather_scores, gather_traces, lpt_shards, pair_cost
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -26,14 +26,23 @@ def _worker(rank, world, port, out_dir):
     lens = np.diff(off)
     shards = lpt_shards(pair_cost(lens[pa], lens[pb], 1), world)
     mine = shards[rank]
-    scores = []
+    scores, cols, toff, comp = [], [], [0], []
     for p in mine:
         a, sa = workloads.decode_protein(res, cls, off, int(pa[p]))
         b, sb = workloads.decode_protein(res, cls, off, int(pb[p]))
-        scores.append(oracle.run(a, b, sa, sb, params, mode="codes")["score"])
+        r = oracle.run(a, b, sa, sb, params, mode="codes")
+        scores.append(r["score"])
+        cols.extend(int(ch, 16) for ch in r["trace"])
+        toff.append(len(cols))
+        comp.append(1 if r["complete"] else 0)
     full = gather_scores(mine, scores, len(pa))
     np.save(os.path.join(out_dir, f"rank{rank}.npy"), full)
     np.save(os.path.join(out_dir, f"mine{rank}.npy"), mine)
+    # traces: to every rank, then to rank 1 only
+    gc, go, gk = gather_traces(mine, np.array(cols, dtype=np.uint8), np.array(toff, dtype=np.int64), np.array(comp, dtype=np.uint8), len(pa))
+    np.savez(os.path.join(out_dir, f"traces{rank}.npz"), cols=gc, off=go, comp=gk)
+    dc, do, dk = gather_traces(mine, np.array(cols, dtype=np.uint8), np.array(toff, dtype=np.int64), np.array(comp, dtype=np.uint8), len(pa), dst=1)
+    np.savez(os.path.join(out_dir, f"traces_dst{rank}.npz"), cols=dc, off=do, comp=dk)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -56,3 +65,15 @@ def test_two_rank_sharding_and_gather(tmp_path):
         a, sa = workloads.decode_protein(res, cls, off, int(pa[p]))
         b, sb = workloads.decode_protein(res, cls, off, int(pb[p]))
         assert oracle.run(a, b, sa, sb, params, mode="codes")["score"] == r0[p]
+    t0, t1 = np.load(tmp_path / "traces0.npz"), np.load(tmp_path / "traces1.npz")
+    d0, d1 = np.load(tmp_path / "traces_dst0.npz"), np.load(tmp_path / "traces_dst1.npz")
+    for k in ("cols", "off", "comp"):
+        assert (t0[k] == t1[k]).all()
+    assert d0["cols"].size == 0 and (d1["cols"] == t0["cols"]).all() and (d0["off"] == t0["off"]).all()
+    for p in range(10):
+        a, sa = workloads.decode_protein(res, cls, off, int(pa[p]))
+        b, sb = workloads.decode_protein(res, cls, off, int(pb[p]))
+        r = oracle.run(a, b, sa, sb, params, mode="codes")
+        got = "".join("%x" % c for c in t0["cols"][t0["off"][p]:t0["off"][p + 1]])
+        assert got == r["trace"] and bool(t0["comp"][p]) == r["complete"]
+

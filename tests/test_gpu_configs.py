@@ -38,11 +38,11 @@ def test_config2_dnapol1_pair_full_traceback():
     g = json.load(open(os.path.join(ROOT, "tests", "golden", "dnapol1.json")))
     al = BatchAligner(**g["params"])
     for long_mode in (1, 0):
-        al.engine.set_option("long", long_mode)
+        al.set_option("long", long_mode)
         try:
             scores, cols, offsets, complete = al.align([g["seqA"], g["seqB"]], [g["strA"], g["strB"]], [(0, 1)], want_trace=True)
         finally:
-            al.engine.set_option("long", -1)
+            al.set_option("long", -1)
         assert int(scores[0]) == 761500 == g["score"]
         tr = _hex(cols, offsets, 0)
         assert tr == g["trace"] and bool(complete[0])
@@ -93,11 +93,11 @@ def test_config4_rna_slice_score_only():
     scores = al.align_encoded(res, cls, off, pa, pb, want_trace=False)
     assert al.engine.stats()["cell_states"] == 20000 * 3229209  # 3 229 209 cell-states per pair
     assert al.engine.stats()["kernel_kind"] == 5  # config 4 runs two pairs per lane in packed 16-bit halves
-    al.engine.set_option("p16", 0)
+    al.set_option("p16", 0)
     try:
         assert (al.align_encoded(res, cls, off, pa, pb, want_trace=False) == scores).all()  # 32-bit kernel agrees
     finally:
-        al.engine.set_option("p16", -1)
+        al.set_option("p16", -1)
     for p in list(range(0, 20000, 667)) + [19999]:
         a, sa = workloads.decode_rna(res, cls, off, int(pa[p]))
         b, sb = workloads.decode_rna(res, cls, off, int(pb[p]))

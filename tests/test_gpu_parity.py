@@ -88,7 +88,7 @@ def _decode_codes(words, kind):
         if kind == 0:
             out[:, t] = ((w >> np.uint64(4 * t)) & np.uint64(15)).astype(np.int64)
         else:
-            sh = 5 * t if t < 6 else 32 + 5 * (t - 6)
+            sh = 2 + 5 * t if t < 6 else 32 + 17 + 5 * (t - 6)
             f = ((w >> np.uint64(sh)) & np.uint64(31)).astype(np.int64)
             ids = np.full(f.shape, 15, dtype=np.int64)
             t01, t23 = t // 3, t % 3
@@ -138,18 +138,14 @@ def _check_batch(al, seqs, structs, pairs, params, table_pairs=0):
     return kind
 
 
-def _select(engine, kind):
+def _select(al, kind):
     """kind 0 = generic level kernel, 1 = systolic pad-free, 2 = systolic padded."""
-    engine.set_option("kernel", 0 if kind == 0 else 1)
-    engine.set_option("pad", -1 if kind == 0 else kind - 1)
+    al.set_option("kernel", 0 if kind == 0 else 1)
+    al.set_option("pad", -1 if kind == 0 else kind - 1)
 
 
-def _unselect(engine):
-    engine.set_option("kernel", -1)
-    engine.set_option("pad", -1)
-    engine.set_option("warps_per_cta", 0)
-    engine.set_option("long", -1)
-    engine.set_option("p16", -1)
+def _unselect(al):
+    al.options.clear()  # options belong to the aligner; the next configure() resets the shared engine to automatic
 
 
 @pytest.mark.parametrize("kernel", [0, 1, 2])
@@ -161,11 +157,11 @@ def test_random_batch_vs_oracle(s, kernel):
                   shift_cost=-150, max_shift=s)
     seqs, structs, pairs = _random_protein_batch(rng, 24, 1, 70)
     al = _aligner(params)
-    _select(al.engine, kernel)
+    _select(al, kernel)
     try:
         assert _check_batch(al, seqs, structs, pairs, params, table_pairs=24) == kernel
     finally:
-        _unselect(al.engine)
+        _unselect(al)
 
 
 @pytest.mark.parametrize("pad", [0, 1])
@@ -179,12 +175,12 @@ def test_systolic_multipass_and_cta_shapes(warps, pad):
         params.update(tie)
         seqs, structs, pairs = _random_protein_batch(rng, 6, 60, 150)
         al = _aligner(params)
-        _select(al.engine, 1 + pad)
-        al.engine.set_option("warps_per_cta", warps)
+        _select(al, 1 + pad)
+        al.set_option("warps_per_cta", warps)
         try:
             assert _check_batch(al, seqs, structs, pairs, params, table_pairs=2) == 1 + pad
         finally:
-            _unselect(al.engine)
+            _unselect(al)
 
 
 def test_positive_gap_opening_and_tie_storms():
@@ -230,8 +226,9 @@ def test_rna_batch_score_only_vs_oracle():
         assert int(scores[q]) == r["score"], q
 
 
-def test_cli_transcripts_match_reference(capsys):
-    """bin/bialign.py stdout == the reference CLI's stdout (tests/golden/cli_outputs.json), all output modes, -v."""
+def test_cli_transcripts_match_reference(capsys, monkeypatch):
+    """bin/bialign.py stdout == the reference CLI's stdout (tests/golden/cli_outputs.json), all output modes, -v,
+    and --fileinput on two CFSSP-format files (tests/golden/small_*.cfssp; the CLI runs from that directory)."""
     import importlib.util
     import json
     import os
@@ -241,6 +238,8 @@ def test_cli_transcripts_match_reference(capsys):
     cli = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(cli)
     cases = json.load(open(os.path.join(root, "tests", "golden", "cli_outputs.json")))
+    assert any("--filein" in c["argv"] for c in cases)
+    monkeypatch.chdir(os.path.join(root, "tests", "golden"))
     for c in cases:
         capsys.readouterr()
         try:
@@ -276,13 +275,13 @@ def test_long_pair_mode_multi_cta(warps, pad):
                       gap_cost=-50, shift_cost=-150, max_shift=s)
         seqs, structs, pairs = _random_protein_batch(rng, 3, 90, 260)
         al = _aligner(params)
-        _select(al.engine, 1 + pad)
-        al.engine.set_option("warps_per_cta", warps)
-        al.engine.set_option("long", 1)
+        _select(al, 1 + pad)
+        al.set_option("warps_per_cta", warps)
+        al.set_option("long", 1)
         try:
             assert _check_batch(al, seqs, structs, pairs, params, table_pairs=3) == 3 + pad
         finally:
-            _unselect(al.engine)
+            _unselect(al)
 
 
 def test_long_pair_auto_mode_many_passes():
@@ -317,7 +316,7 @@ def test_edge_cases_empty_and_tiny_sequences(kernel):
     structs = ["", "H", "HE", "HHHHHEEEEECCCCCHHHHH" * 4, "C", ""]
     pairs = [(0, 5), (0, 1), (1, 0), (1, 4), (1, 1), (2, 3), (3, 2), (3, 3), (0, 3), (3, 0)]
     al = _aligner(params)
-    _select(al.engine, kernel)
+    _select(al, kernel)
     try:
         from bialign_b200.batch import trace_hex
 
@@ -331,7 +330,7 @@ def test_edge_cases_empty_and_tiny_sequences(kernel):
         empty = al.align(seqs, structs, [], want_trace=True)
         assert len(empty[0]) == 0 and empty[2].tolist() == [0]
     finally:
-        _unselect(al.engine)
+        _unselect(al)
 
 
 def test_error_codes_range_and_alphabet():
@@ -355,7 +354,7 @@ def test_error_codes_range_and_alphabet():
     for key, bad in [("kernel", 2), ("pad", -2), ("long", 5), ("p16", 2), ("warps_per_cta", 9), ("code_arena_bytes", -1),
                      ("no_such_option", 0)]:
         with pytest.raises(_capi.BialignError) as ei:
-            ok.engine.set_option(key, bad)
+            ok.set_option(key, bad)
         assert ei.value.code == _capi.BA_ERR_INVALID_ARG, key
     with pytest.raises(_capi.BialignError) as ei:  # offsets that are not monotone
         ok.align_encoded(res[:2], np.zeros(2, np.uint8), np.array([0, 2, 1], np.int64), np.array([0], np.int32), np.array([1], np.int32))
@@ -391,14 +390,14 @@ def test_score_only_16bit_pair_mode(s):
             structs = [("(" * (len(x) // 3) + "." * (len(x) - 2 * (len(x) // 3)) + ")" * (len(x) // 3)) for x in seqs]
         al = _aligner(params)
         try:
-            al.engine.set_option("p16", 1)
+            al.set_option("p16", 1)
             s16 = al.align(seqs, structs, pairs, want_trace=False)
             assert al.engine.stats()["kernel_kind"] == 5
-            al.engine.set_option("p16", 0)
+            al.set_option("p16", 0)
             s32 = al.align(seqs, structs, pairs, want_trace=False)
             assert al.engine.stats()["kernel_kind"] in (1, 2)
         finally:
-            _unselect(al.engine)
+            _unselect(al)
         assert (s16 == s32).all()
         for q, (ia, ib) in enumerate(pairs):
             assert int(s16[q]) == oracle.run(seqs[ia], seqs[ib], structs[ia], structs[ib], params, mode="codes")["score"], q
@@ -412,12 +411,12 @@ def test_16bit_pair_mode_refused_when_range_does_not_fit():
     res, cls, off, pa, pb = workloads.protein_pairs(4, seed=3)  # length 200-500 with BLOSUM62 x100: needs > 16 bits
     al = BatchAligner(max_shift=2, **workloads.PROTEIN_PARAMS)
     try:
-        al.engine.set_option("p16", 1)
+        al.set_option("p16", 1)
         with pytest.raises(_capi.BialignError) as ei:
             al.align_encoded(res, cls, off, pa, pb, want_trace=False)
         assert ei.value.code == _capi.BA_ERR_SCORE_RANGE
     finally:
-        _unselect(al.engine)
+        _unselect(al)
     al.align_encoded(res, cls, off, pa, pb, want_trace=False)
     assert al.engine.stats()["kernel_kind"] in (1, 3)  # auto: falls back to a 32-bit kernel
 
@@ -474,11 +473,11 @@ def test_tie_storms_at_multipass_sizes(variant):
         structs[2 * q + 1] = (structs[2 * q][3:] + "HHH")[: len(b)].ljust(len(b), "C")
     al = _aligner(params)
     assert _check_batch(al, seqs, structs, pairs, params, table_pairs=3) in (3, 4)  # three long-ish pairs: long-pair mode
-    al.engine.set_option("long", 0)
+    al.set_option("long", 0)
     try:
         assert _check_batch(al, seqs, structs, pairs, params, table_pairs=3) in (1, 2)  # CTA-per-pair mode
     finally:
-        _unselect(al.engine)
+        _unselect(al)
 
 
 @pytest.mark.parametrize("kernel", [0, 1, 2])
@@ -495,7 +494,7 @@ def test_nonaffine_model_vs_oracle(s, kernel):
         params.update(var)
         seqs, structs, pairs = _random_protein_batch(rng, 8, 1, 110)
         al = _aligner(params)
-        _select(al.engine, kernel)
+        _select(al, kernel)
         try:
             scores, cols, offsets, complete = al.align(seqs, structs, pairs, want_trace=True)
             kind = al.engine.stats()["kernel_kind"]
@@ -506,7 +505,7 @@ def test_nonaffine_model_vs_oracle(s, kernel):
                 assert trace_hex(cols, offsets, q) == r["trace"], (q, var)
             assert (al.align(seqs, structs, pairs, want_trace=False) == scores).all()
         finally:
-            _unselect(al.engine)
+            _unselect(al)
 
 
 def test_many_waves_with_a_tiny_code_arena():
@@ -523,15 +522,15 @@ def test_many_waves_with_a_tiny_code_arena():
     assert al.engine.stats()["waves"] == 1
     try:
         for kernel in (1, 0):
-            al.engine.set_option("kernel", kernel)
-            al.engine.set_option("code_arena_bytes", 3 << 20)  # ~ 2-3 pairs per wave
+            al.set_option("kernel", kernel)
+            al.set_option("code_arena_bytes", 3 << 20)  # ~ 2-3 pairs per wave
             scores, cols, offsets, complete = al.align(seqs, structs, pairs, want_trace=True)
             assert al.engine.stats()["waves"] >= 10
             assert (scores == ref_scores).all() and complete.all()
             assert all(trace_hex(cols, offsets, q) == trace_hex(ref_cols, ref_off, q) for q in range(len(pairs)))
     finally:
-        al.engine.set_option("code_arena_bytes", 0)
-        _unselect(al.engine)
+        al.set_option("code_arena_bytes", 0)
+        _unselect(al)
     for q in (0, 7, 39):
         ia, ib = pairs[q]
         r = oracle.run(seqs[ia], seqs[ib], structs[ia], structs[ib], params, mode="codes")
