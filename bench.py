@@ -119,10 +119,9 @@ def cpu_sample(res, cls, off, pa, pb, params, trunc, npairs):
     their first `trunc` residues (the reference runs ~7e4 cell-states/s/core; a full-length pair of
     this workload would take minutes per core)."""
     from bialign_b200 import workloads
-
-    jobs, cs = [], 0
     from bialign_b200.batch import cell_states
 
+    jobs, cs = [], 0
     for p in range(npairs):
         a, sa = workloads.decode_protein(res, cls, off, int(pa[p]))
         b, sb = workloads.decode_protein(res, cls, off, int(pb[p]))
@@ -133,19 +132,31 @@ def cpu_sample(res, cls, off, pa, pb, params, trunc, npairs):
     return jobs, cs
 
 
-def run_cpu_arm(jobs, cores, kind):
-    import multiprocessing as mp
+class CpuArm:
+    """A pool of host processes running the reference (or the C port) on a list of jobs.  The pool is created and its
+    workers warmed (module import, one tiny alignment each) once, outside every timed window."""
 
-    worker = _ref_worker if kind == "reference" else _port_worker
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
+    def __init__(self, cores, kind):
+        import multiprocessing as mp
+
+        self.kind, self.cores = kind, cores
+        self.worker = _ref_worker if kind == "reference" else _port_worker
+        self.pool = mp.get_context("fork").Pool(cores)
+        tiny = ("ACDEF", "ACDF", "HHHEE", "HHEE", dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800,
+                                                         gap_opening_cost=-150, gap_cost=-50, shift_cost=-150, max_shift=1), True)
+        self.pool.map(self.worker, [tiny] * (2 * cores), chunksize=1)
+
+    def run(self, jobs):
         t0 = time.perf_counter()
-        scores = pool.map(worker, jobs, chunksize=1)
-        dt = time.perf_counter() - t0
-    return dt, scores
+        scores = self.pool.map(self.worker, jobs, chunksize=1)
+        return time.perf_counter() - t0, scores
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
-def cpu_baseline(res, cls, off, pa, pb, params, budget_s=20.0):
+def cpu_baseline(res, cls, off, pa, pb, params):
     cores = os.cpu_count() or 1
     kind = "reference" if reference_available() else "port"
     if kind == "reference":
@@ -153,13 +164,66 @@ def cpu_baseline(res, cls, off, pa, pb, params, budget_s=20.0):
     else:
         trunc, npairs = 0, cores * 2
     jobs, cs = cpu_sample(res, cls, off, pa, pb, params, trunc, npairs)
-    dt, _ = run_cpu_arm(jobs, cores, kind)
+    arm = CpuArm(cores, kind)
+    dt, _ = arm.run(jobs)
+    arm.close()
     return {"value": cs / dt / 1e9, "unit": "GCUPS", "cores": cores, "kind": kind,
             "sample": f"first {npairs} pairs of the workload" + (f", molecules cut to {trunc} residues" if trunc else "") +
-                      f" ({cs} cell-states, {dt:.1f} s wall, multiprocessing pool of {cores})"}
+                      f" ({cs} cell-states, {dt:.1f} s wall, warm pool of {cores} processes)"}
 
 
 # ------------------------------------------------------------------------------------------------
+def verify_shard(res, cls, off, pa, pb, params, scores, cols, toff, complete, nrescore=32):
+    """Correctness of what the timed loops produced, checked with the CPU oracle (test infrastructure, used here only as
+    the checker): every sampled trace is complete, ends at (n, m, n, m) and re-scores to the reported score; the
+    smallest pair of the shard is recomputed from scratch (score and trace)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    from bialign_b200 import workloads
+    from bialign_b200.batch import trace_hex
+
+    n = len(pa)
+    ok, checked = True, 0
+    for q in np.unique(np.linspace(0, n - 1, num=min(nrescore, n)).astype(np.int64)):
+        a, sa = workloads.decode_protein(res, cls, off, int(pa[q]))
+        b, sb = workloads.decode_protein(res, cls, off, int(pb[q]))
+        v, end = oracle.eval_trace(a, b, sa, sb, params, trace_hex(cols, toff, q))
+        ok &= bool(complete[q]) and v == int(scores[q]) and end == [len(a), len(b)] * 2
+        checked += 1
+    lens = np.diff(off)
+    q = int(np.argmin((lens[pa] + 1) * (lens[pb] + 1)))
+    a, sa = workloads.decode_protein(res, cls, off, int(pa[q]))
+    b, sb = workloads.decode_protein(res, cls, off, int(pb[q]))
+    r = oracle.run(a, b, sa, sb, params, mode="codes")
+    ok &= r["score"] == int(scores[q]) and r["trace"] == trace_hex(cols, toff, q)
+    return {"ok": bool(ok), "traces_rescored": checked, "pairs_recomputed_by_oracle": 1,
+            "how": "oracle.eval_trace on sampled traces (score, end cell, completeness) + oracle.run on the smallest pair"}
+
+
+def time_shape(al, res, cls, off, pa, pb, want_trace, reps, local_rank, barrier):
+    """Device-resident timing of one workload shape on this rank: (best stats dict, wall ms of that run, clocks)."""
+    eng = al.engine
+    al.configure()
+    eng.load_sequences(res, cls, off)
+    eng.load_pairs(pa, pb)
+    eng.run(want_trace=want_trace)  # warm-up (allocations, first-use)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    best, wall = None, 0.0
+    t_begin, done = time.perf_counter(), 0
+    while done < reps or time.perf_counter() - t_begin < 0.7:  # short shapes repeat until nvidia-smi has sampled the clocks
+        t0 = time.perf_counter()
+        eng.run(want_trace=want_trace)
+        w = 1e3 * (time.perf_counter() - t0)
+        st = eng.stats()
+        done += 1
+        if best is None or st["total_ms"] < best["total_ms"]:
+            best, wall = st, w
+    barrier()
+    return best, wall, sampler.stop()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -168,6 +232,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs-per-gpu", type=int, default=PAIRS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shapes", action="store_true", help="skip the per-shape block (cfg1, cfg2, cfg4, cfg5, non-affine) and the strong-scaling run")
     ap.add_argument("--warps", type=int, default=0, help="warps per CTA of the systolic kernel (0 = library default)")
     args = ap.parse_args()
 
@@ -175,6 +240,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = max(args.gpus, 1)
+    if world != n_gpus:
+        raise SystemExit(f"bench.py: --gpus {n_gpus} but WORLD_SIZE is {world}: launch N > 1 through torch.distributed.run "
+                         "with one rank per GPU (the line's n_gpus, the workload size and the sharding must agree)")
 
     from bialign_b200 import workloads
 
@@ -182,7 +250,7 @@ def main():
     total_pairs = args.pairs_per_gpu * n_gpus
     res, cls, off, pa, pb = workloads.protein_pairs(total_pairs, seed=3)
     config = {"workload": WORKLOAD, "pairs_per_step": total_pairs, "pairs_per_gpu": args.pairs_per_gpu,
-              "sharding": f"LPT over {n_gpus} rank(s), no collective on the data path",
+              "sharding": f"LPT over {n_gpus} rank(s), no collective on the data path; results gathered on rank 0",
               "l2": "traceback-code stream per step (>= tens of GB) far exceeds the 126 MB L2; no explicit flush needed"}
 
     # ---------------------------------------------------------------- reference arm (CPU, rank 0 only)
@@ -193,15 +261,20 @@ def main():
         kind = "reference" if reference_available() else "port"
         trunc, npairs = (40, cores) if kind == "reference" else (0, cores)
         jobs, cs = cpu_sample(res, cls, off, pa, pb, params, trunc, npairs)
+        arm = CpuArm(cores, kind)  # processes forked and warmed before anything is timed
         times = []
         for it in range(args.warmup + args.steps):
-            dt, _ = run_cpu_arm(jobs, cores, kind)
+            dt, _ = arm.run(jobs)
             if it >= args.warmup:
                 times.append(dt)
+        arm.close()
         ms = 1e3 * float(np.mean(times))
         val = cs / (ms * 1e-3) / 1e9
         sample = (f"each step = first {npairs} pairs of the workload" +
                   (f", molecules cut to {trunc} residues" if trunc else "") + f" ({cs} cell-states) on {cores} host cores")
+        # the CPU arm times a bounded sample of the workload, not the workload: say so in its own config
+        config = dict(config, reference_sample={"pairs": npairs, "truncated_to": trunc or None, "cell_states": cs,
+                                                "comparable": "per-cell-state rate only (GCUPS); the GPU arm runs full-length pairs"})
         print(json.dumps({"impl": "reference", "metric": "batched bialign GCUPS (cell-states/s)", "value": val,
                           "unit": "GCUPS", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -226,10 +299,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     from bialign_b200 import _capi
-    from bialign_b200.batch import BatchAligner, compact_shard, lpt_shards, pair_cost
+    from bialign_b200.batch import BatchAligner, compact_shard, gather_scores, gather_traces, lpt_shards, pair_cost
 
     os.environ["BIALIGN_DEVICE"] = str(local_rank)
+    dev = torch.device("cuda", local_rank)
     al = BatchAligner(device=local_rank, **params)
     if args.warps:
         al.set_option("warps_per_cta", args.warps)
@@ -238,7 +326,6 @@ def main():
     total_cs = int(cell_states_of(off, pa, pb, MAX_SHIFT).sum())
     # this rank's share of the sequence table and pair list (what it uploads every end-to-end step)
     res, cls, off, my_pa, my_pb = compact_shard(res, cls, off, pa[mine], pb[mine])
-    lens = np.diff(off)
     my_cs = int(cell_states_of(off, my_pa, my_pb, MAX_SHIFT).sum())
 
     eng = al.engine
@@ -265,37 +352,57 @@ def main():
     clocks = sampler.stop()
     st = eng.stats()
 
-    # --- end-to-end leg: host buffers in, scores + traces out, every step
+    # --- end-to-end leg: host buffers in; scores + traces out and, with several ranks, gathered on rank 0 -- every step
     h2d = res.nbytes + cls.nbytes + off.nbytes + my_pa.nbytes + my_pb.nbytes
     d2h = 0
     scores = np.empty(len(my_pa), dtype=np.int64)
-    eng.align_batch(res, cls, off, my_pa, my_pb, want_trace=True, scores_out=scores)  # warm (first-use allocations)
-    eng.fetch_traces()
+
+    def e2e_step():
+        eng.align_batch(res, cls, off, my_pa, my_pb, want_trace=True, scores_out=scores)
+        cols, toff, complete = eng.fetch_traces()
+        nbytes = scores.nbytes + cols.nbytes + toff.nbytes + complete.nbytes  # what actually came back from the device
+        if world > 1:  # the one cross-rank step of the path: a result gather (NCCL), no data-path collective
+            full = gather_scores(mine, scores, total_pairs, device=dev)
+            gcols, goff, gcomp = gather_traces(mine, cols, toff, complete, total_pairs, device=dev, dst=0)
+            if rank == 0:
+                nbytes += full.nbytes + gcols.nbytes
+        return cols, toff, complete, nbytes
+
+    e2e_step()  # warm (first-use allocations)
     barrier()
     t1 = time.perf_counter()
     for _ in range(args.steps):
-        eng.align_batch(res, cls, off, my_pa, my_pb, want_trace=True, scores_out=scores)
-        cols, toff, complete = eng.fetch_traces()
-        d2h = scores.nbytes + int(np.sum(2 * (lens[my_pa] + lens[my_pb]) + 2)) + 5 * len(my_pa)
+        cols, toff, complete, d2h = e2e_step()
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t1)
-
-    def allmax(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def allsum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    verified = verify_shard(res, cls, off, my_pa, my_pb, params, scores, cols, toff, complete)
+    verified["ok"] = bool(allsum(0.0 if verified["ok"] else 1.0) == 0.0)
 
     ev_ms_max, wall_ms_max, e2e_ms_max = allmax(ev_ms), allmax(wall_ms), allmax(e2e_ms)
     launches_all, h2d_all, d2h_all = allsum(launches), allsum(h2d), allsum(d2h)
+
+    # --- roofline denominators: integer ALU, measured on this box
+    add_rate, sms = _capi.microbench_int(local_rank, 0)
+    fused_rate, _ = _capi.microbench_int(local_rank, 2)
+    mnmx_rate, _ = _capi.microbench_int(local_rank, 1)
+    int_peak = max(add_rate, mnmx_rate, 2.0 * fused_rate)  # algorithmic int ops/s (a fused add+max retires two)
+
+    # --- every other named shape of BASELINE.json (device-resident, CUDA-event times, clocks sampled per shape)
+    shapes, strong = None, None
+    if not args.no_shapes:
+        shapes = run_shapes(world, rank, local_rank, barrier, allmax, allsum, int_peak)
+        # strong scaling: the whole of config 3 (100 000 pairs) at every N, one warm-up and one timed step
+        sres, scls, soff, spa, spb = workloads.protein_pairs(PAIRS_PER_GPU * 8, seed=3)
+        slens = np.diff(soff)
+        smine = lpt_shards(pair_cost(slens[spa], slens[spb], MAX_SHIFT), world)[rank]
+        s_cs = int(cell_states_of(soff, spa, spb, MAX_SHIFT).sum())
+        sres, scls, soff, spa, spb = compact_shard(sres, scls, soff, spa[smine], spb[smine])
+        best, wall, sclk = time_shape(al, sres, scls, soff, spa, spb, True, 1, local_rank, barrier)
+        swall = allmax(wall)
+        strong = {"workload": "all of cfg3: 100000 pairs at every N", "pairs": PAIRS_PER_GPU * 8, "n_gpus": n_gpus,
+                  "ms_per_step": swall, "value": s_cs / swall / 1e6, "unit": "GCUPS", "steps": 1, "warmup": 1,
+                  "sm_mhz": sclk.get("sm_mhz")}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -305,11 +412,6 @@ def main():
     value = total_cs / (ms_per_step * 1e-3) / 1e9
     e2e_value = total_cs / (e2e_ms_max / args.steps * 1e-3) / 1e9
 
-    # --- roofline of the dominant kernel (the fill): integer ALU, measured on this box
-    add_rate, sms = _capi.microbench_int(local_rank, 0)
-    fused_rate, _ = _capi.microbench_int(local_rank, 2)
-    mnmx_rate, _ = _capi.microbench_int(local_rank, 1)
-    int_peak = max(add_rate, mnmx_rate, 2.0 * fused_rate)  # algorithmic int ops/s (a fused add+max retires two)
     fill_s = fill_ms / args.steps * 1e-3
     achieved = 30.0 * my_cs / fill_s  # 15 add + 15 max per cell-state
     peaks = {}
@@ -334,21 +436,91 @@ def main():
                 "traffic": (traffic * my_cs if traffic else None),
                 "hbm": {"achieved": st["code_bytes"] / fill_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": st["code_bytes"] / fill_s / 1e9 / hbm_peak,
-                        "what": "traceback-code stores (8 B per band cell) during the fill",
+                        "what": "traceback-code stores (8 B per lane and iteration, 256 B per warp) during the fill",
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}}
     out = {"metric": "batched bialign GCUPS (cell-states/s)", "value": value, "unit": "GCUPS", "n_gpus": n_gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
            "device_ms_per_step": ev_ms_max / args.steps, "clocks": clocks,
            "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
-                   "ms_per_step": e2e_ms_max / args.steps},
+                   "ms_per_step": e2e_ms_max / args.steps,
+                   "includes": "H2D of the sequence table and pair list, fill, traceback, D2H of scores and traces" +
+                               (", NCCL gather of scores and traces on rank 0" if world > 1 else "")},
            "gpu_launches": int(launches_all), "kernel_kind": st["kernel_kind"], "waves_per_step": st["waves"],
-           "roofline": roofline}
+           "verified": verified, "roofline": roofline}
+    if shapes is not None:
+        out["shapes"] = shapes
+        out["strong_scaling"] = strong
     if n_gpus == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(res, cls, off, my_pa, my_pb, params)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_shapes(world, rank, local_rank, barrier, allmax, allsum, int_peak):
+    """The other named shapes of BASELINE.json, each timed like the headline (device-resident inputs, CUDA events,
+    clocks sampled while it runs).  Batches (cfg1, cfg4, non-affine) are weak-scaled: a fixed number of pairs per GPU,
+    sharded like the headline.  Single long pairs (cfg2, cfg5) do not shard ("replicas only"): rank 0 runs
+    them on its GPU and the other ranks wait.  Returns a list of dicts (identical on every rank)."""
+    from bialign_b200 import workloads
+    from bialign_b200.batch import BatchAligner, cell_states
+
+    prot = workloads.PROTEIN_PARAMS
+    out = []
+
+    def record(name, al, res, cls, off, pa, pb, want_trace, reps, ops, sharded, note=None):
+        affine = al.params["gap_opening_cost"] != 0
+        active = sharded or rank == 0
+        if active:
+            best, wall, clk = time_shape(al, res, cls, off, pa, pb, want_trace, reps, local_rank, barrier if sharded else (lambda: None))
+        else:
+            best, wall, clk = {"cell_states": 0, "fill_ms": 0.0, "traceback_ms": 0.0, "total_ms": 0.0, "kernel_kind": 0,
+                               "warps_per_cta": 0, "waves": 0, "code_bytes": 0}, 0.0, {}
+        if not sharded:
+            barrier()
+        cs = allsum(float(best["cell_states"]))
+        wall_max, fill_max, dev_max = allmax(wall), allmax(best["fill_ms"]), allmax(best["total_ms"])
+        sm = allmax(float(clk.get("sm_mhz") or 0.0))
+        reasons = sorted(set(clk.get("reasons", []))) if rank == 0 else []
+        kk, wp = int(allmax(float(best["kernel_kind"]))), int(allmax(float(best["warps_per_cta"])))
+        out.append({"shape": name, "pairs": int(allsum(float(len(pa) if active else 0))), "n_gpus": world if sharded else 1,
+                    "want_trace": bool(want_trace), "model": "affine" if affine else "non-affine",
+                    "cell_states": int(cs), "gcups": cs / wall_max / 1e6, "ms": wall_max, "device_ms": dev_max,
+                    "fill_ms": fill_max, "gcups_fill": cs / fill_max / 1e6,
+                    "frac": ops * cs / (fill_max * 1e-3) / int_peak / (world if sharded else 1),
+                    "algorithmic_ops_per_cell_state": ops, "kernel_kind": kk, "warps_per_cta": wp,
+                    "sm_mhz": sm, "clock_reasons": reasons, "scaling": "weak" if sharded else "replicas only (one pair, one GPU)",
+                    **({"note": note} if note else {})})
+
+    # cfg1: the README toy pair (42 aa, max_shift 1), 100 000 copies per GPU, score + traceback
+    seqs = ["RAKLPLKEKKLTATANYHPGIRYIMTGYSAKYIYSSTYARFR", "KAKLPLKEKKLTRTANYHPGIRYIMTGYSAKRIYSSTYAYFR"]
+    structs = ["CHHHHHHHHHHHHHCCCCTCEEEEEEECCTCEEEEEEEECCC", "HHHHHHHHHHHHCCCCCCTCEEEEEEECCCCCEEEEEEEECC"]
+    al = BatchAligner(device=local_rank, max_shift=1, **prot)
+    res, cls, off = al.encode(seqs, structs)
+    record("cfg1: README protein toy pair x 100000 per GPU, max_shift 1, score+traceback", al, res, cls, off,
+           np.zeros(100000, np.int32), np.ones(100000, np.int32), True, 2, 30, True)
+    # cfg2: DNAPolymerase1 E. coli vs Xanthomonas (928 x 933), max_shift 1, full traceback
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "dnapol1.json")))
+    al = BatchAligner(device=local_rank, **g["params"])
+    res, cls, off = al.encode([g["seqA"], g["seqB"]], [g["strA"], g["strB"]])
+    record("cfg2: DNAPolymerase1 928 x 933, max_shift 1, score+traceback", al, res, cls, off,
+           np.array([0], np.int32), np.array([1], np.int32), True, 3, 30, False)
+    # cfg4: RNA pairs of length 120 with supplied structures, max_shift 2, score only: 125 000 per GPU (1M on 8)
+    al = BatchAligner(device=local_rank, max_shift=2, **workloads.RNA_PARAMS)
+    res, cls, off, pa, pb = workloads.rna_pairs(125000, seed=4 + 100 * rank)
+    record("cfg4: 125000 RNA pairs len 120 per GPU, max_shift 2, score only (16-bit pair mode)", al, res, cls, off, pa, pb,
+           False, 2, 30, True)
+    # non-affine model (the CLI default, gap_opening_cost 0) on the cfg3 shape: 3000 pairs per GPU, score + traceback
+    al = BatchAligner(device=local_rank, max_shift=2, **dict(prot, gap_opening_cost=0, gap_cost=-200, shift_cost=-250))
+    res, cls, off, pa, pb = workloads.protein_pairs(3000, seed=3 + 100 * rank)
+    record("non-affine model: 3000 protein pairs 200-500 per GPU, max_shift 2, score+traceback (cells/s)", al, res, cls, off,
+           pa, pb, True, 2, 26, True)
+    # cfg5: one 8192 x 8192 protein pair, max_shift 3, multi-CTA fill with traceback codes in HBM
+    al = BatchAligner(device=local_rank, max_shift=3, **prot)
+    res, cls, off, pa, pb = workloads.protein_pairs(1, lo=8192, hi=8192, seed=5)
+    record("cfg5: one 8192 x 8192 protein pair, max_shift 3, score+traceback", al, res, cls, off, pa, pb, True, 2, 30, False)
+    return out
 
 
 if __name__ == "__main__":

@@ -131,7 +131,7 @@ class BatchAligner:
             bad = present[a][:, None] & present[b][None, :] & ~self.known
             if bad.any():
                 i, j = np.argwhere(bad)[0]
-                raise KeyError(self.symbols[j] if self.symbols[i] in self.symbols else self.symbols[i])
+                raise KeyError(self.symbols[j])  # the inner key of simmatrix[a][b]
 
     def configure(self):
         eng, p = self.engine, self.params

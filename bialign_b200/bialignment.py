@@ -199,31 +199,14 @@ class BiAligner:
     # ------------------------------------------------------------------ presentation (host only)
     @staticmethod
     def _transfer_gaps(alistr, seqstr):
-        out, pos = [], 0
-        for c in alistr:
-            if c == "-":
-                out.append("-")
-            else:
-                out.append(seqstr[pos])
-                pos += 1
-        return "".join(out)
-
-    @staticmethod
-    def _shift_string(ali, idx):
-        def sym(i):
-            g1, g2 = ali[idx][i] == "-", ali[idx + 2][i] == "-"
-            if g1 == g2:
-                return "."
-            return ">" if g1 else "<"
-
-        return "".join(sym(i) for i in range(len(ali[0])))
+        """`seqstr` spread over the non-gap columns of `alistr` (its gaps kept)."""
+        symbols = iter(seqstr)
+        return "".join("-" if c == "-" else next(symbols) for c in alistr)
 
     @staticmethod
     def auto_complete(x, xs):
-        for y in sorted(xs):
-            if y.startswith(x):
-                return y
-        return x
+        """First of `xs` (alphabetically) that starts with `x`; `x` itself when none does."""
+        return next((y for y in sorted(xs) if y.startswith(x)), x)
 
     def _sbpp(self, mol):
         """Symmetric pair matrix with unpaired probability on the diagonal for a fixed structure
@@ -240,64 +223,56 @@ class BiAligner:
                 m[i, i] = 1.0
         return m
 
+    def _consensus_structure(self, ssA, ssB):
+        """Consensus-structure row of one of the two alignments, from the gapped structure strings of A and B."""
+        if not self._is_rna:
+            return consensus_sequence(ssA, ssB)
+        pairs = consensus_sbpp(alistrA=ssA, alistrB=ssB, sbppA=self._sbpp(self.molA), sbppB=self._sbpp(self.molB))
+        return mea(pairs, brackets="[]")[0]
+
     def decode_trace_full(self, trace=None):
-        """Trace -> the 14 named rows of pyx:633-707 (same order, same names)."""
+        """Trace -> 14 (name, row) pairs, the row set of pyx:633-707: for the sequence alignment (columns x0, x1) and then
+        for the structure alignment (columns x2, x3) the six rows `A ss`, `A`, `B ss`, `B`, `consensus ss`, `consensus`,
+        followed by the two shift rows."""
         if trace is None:
             trace = self.traceback()
-        mols = (self.molA, self.molB, self.molA, self.molB)
-        pos = [0, 0, 0, 0]
-        rows = [[], [], [], []]
-        for y in trace:
-            for q in range(4):
-                if y[q] == 0:
-                    rows[q].append("-")
-                elif y[q] == 1:
-                    rows[q].append(mols[q]["seq"][pos[q]])
-                    pos[q] += 1
-        alignment = ["".join(r) for r in rows]
-        cons_seq = [consensus_sequence(alignment[2 * q], alignment[2 * q + 1]) for q in range(2)]
-
-        anno = []
-        for alistr, mol in zip(alignment, mols):
-            anno.append(self._transfer_gaps(alistr, mol["structure"]))
-            anno.append(alistr)
-        # consensus structure rows: second copy first, then first copy (insertion order of pyx:662-673)
-        for i, j in [(4, 6), (0, 2)]:
-            if self._is_rna:
-                sb = consensus_sbpp(alistrA=anno[i], alistrB=anno[j], sbppA=self._sbpp(self.molA),
-                                    sbppB=self._sbpp(self.molB))
-                structure = mea(sb, brackets="[]")[0]
-            else:
-                structure = consensus_sequence(anno[i], anno[j])
-            anno.insert(j + 2, structure)
-        shifts = [self._shift_string(alignment, q) for q in range(2)]
-        out = anno
-        out.insert(len(out), cons_seq[1])
-        out.insert(len(out) // 2, cons_seq[0])
-        out.extend(shifts)
+        cols = np.asarray(trace, dtype=np.int64).reshape(-1, 4)
+        mols = (self.molA, self.molB)
         nameA, nameB = self._params["nameA"], self._params["nameB"]
-        ss = " ss"
-        names = [nameA + ss, nameA, nameB + ss, nameB, "consensus" + ss, "consensus"] * 2 + [nameA + " shifts",
-                                                                                             nameB + " shifts"]
-        return list(zip(names, out))
+        rows, gapped = [], []
+        for copy in (0, 1):
+            block = []
+            for which, mol in enumerate(mols):
+                advances = cols[:, 2 * copy + which] == 1
+                block.append("".join(np.where(advances, np.array(list(mol["seq"]) + ["-"], dtype="<U1")[
+                    np.minimum(np.cumsum(advances) - 1, mol["len"])], "-")) if len(cols) else "")
+            gapped.append(block)
+            ss = [self._transfer_gaps(row, mol["structure"]) for row, mol in zip(block, mols)]
+            rows += [(nameA + " ss", ss[0]), (nameA, block[0]), (nameB + " ss", ss[1]), (nameB, block[1]),
+                     ("consensus ss", self._consensus_structure(ss[0], ss[1])),
+                     ("consensus", consensus_sequence(block[0], block[1]))]
+        for which, name in enumerate((nameA, nameB)):
+            first, second = gapped[0][which], gapped[1][which]
+            rows.append((name + " shifts", "".join("." if (a == "-") == (b == "-") else (">" if a == "-" else "<")
+                                                   for a, b in zip(first, second))))
+        return rows
 
     def decode_trace(self, trace=None):
-        alignment = self.decode_trace_full(trace)
-        width = max(len(name) for name, _ in alignment) + 4
-        if "nodescription" not in self._params or not self._params["nodescription"]:
-            alignment = ["{:{width}}{}".format(name, s, width=width) for name, s in alignment]
+        """The rows selected by the output mode (pyx:168-177, 709-743), each prefixed with its left-justified name unless
+        `nodescription`; index 14 of an output mode is the empty separator line."""
+        rows = self.decode_trace_full(trace)
+        if self._params.get("nodescription"):
+            lines = [text for _, text in rows]
         else:
-            alignment = [s for _, s in alignment]
-        alignment.append("")
-        if "outmode" not in self._params:
-            self._params["outmode"] = "default"
-        mode = self.auto_complete(self._params["outmode"], self.outmodes.keys())
-        if mode in self.outmodes:
-            order = self.outmodes[mode]
-        else:
+            pad = 4 + max(len(label) for label, _ in rows)
+            lines = [label.ljust(pad) + text for label, text in rows]
+        lines.append("")
+        requested = self._params.setdefault("outmode", "default")
+        layout = self.outmodes.get(self.auto_complete(requested, self.outmodes.keys()))
+        if layout is None:
             print("WARNING: unknown output mode. Expect one of " + str(list(self.outmodes.keys())))
-            order = self.outmodes["sorted"]
-        return [alignment[i] for i in order]
+            layout = self.outmodes["sorted"]
+        return [lines[i] for i in layout]
 
     # ------------------------------------------------------------------ trace evaluation (-v)
     def _nonaffine_cases(self, idx):

@@ -497,7 +497,7 @@ int ba_run(ba_engine* e, int want_trace) {
             // covers all rows in one pass; long ones want few warps per CTA and several CTAs per SM.
             const SysGeo geo = sys_geo(s, plan.pad);
             double best = 0;
-            for (int G = std::max(2, (18 * geo.LPR + 31) / 32); G <= 8; ++G) {
+            for (int G = std::max(2, (12 * geo.LPR + 31) / 32); G <= 8; ++G) {
                 const size_t sm = sys_smem_bytes(s, plan.pad, G, e->sc.nsym, mmax, p16);
                 if (sm > kSysSmemLimit) continue;
                 const int occ = p16 ? sys_occupancy_p16(s, G, sm)
@@ -518,11 +518,11 @@ int ba_run(ba_engine* e, int want_trace) {
             if (sysG == 0) sysG = 2;
             // a handful of long pairs will run in long-pair mode, where the pipeline fill (CTAs x lag) matters as much
             // as the per-CTA rate: 4 warps measured best on both the 928 x 933 and the 8192 x 8192 pair
-            if (N <= 4 && affine && !p16 && e->opt_long != 0 && (nmax + 1) > 8 * 4 * geo.R) sysG = std::max(4, (18 * geo.LPR + 31) / 32);
+            if (N <= 4 && affine && !p16 && e->opt_long != 0 && (nmax + 1) > 8 * 4 * geo.R) sysG = std::max(4, (12 * geo.LPR + 31) / 32);
         }
-        // one boundary-record element per thread: a CTA needs at least 18 * LPR threads, and never fewer -- a narrower
+        // one boundary-record element per thread: a CTA needs at least 12 * LPR threads, and never fewer -- a narrower
         // CTA would silently drop record elements between the row blocks of a multi-pass pair
-        const int minG = (18 * sys_geo(s, plan.pad).LPR + 31) / 32;
+        const int minG = (12 * sys_geo(s, plan.pad).LPR + 31) / 32;
         sysG = std::max(sysG, minG);
         while (sysG > minG && sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax, p16) > kSysSmemLimit) --sysG;
         sys_smem = sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax, p16);

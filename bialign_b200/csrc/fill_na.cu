@@ -1,0 +1,330 @@
+// Non-affine fill: dedicated kernel for the reference's single-table model (gap_opening_cost == 0; pyx:225-252 case
+// list and scores, pyx:443-471 fill, pyx:513-531 traceback rule "first case in case order that reproduces the value").
+//
+// One value per cell, thirteen cases.  The affine kernel's lane = (row, band offset a) mapping would spend all its time
+// moving that single value between lanes; here a LANE OWNS A ROW i AND ALL ITS BAND OFFSETS a = k-i (W = 2s+1 cells per
+// iteration, statically unrolled), walks the linearised (j, b = l-j) axis, and lags the row above by ONE iteration:
+//      cell (i, j, a, b) is computed at iteration  q = i_in_block + j*P + (b+s)          (P = max(W, 2) cells per column)
+// so a column x = (x0,x1,x2,x3) reaches back  D(x) = x0 + (P-1)*x1 + x3  iterations, to band offset a + x0 - x2:
+//   x0 = 0 (seven cases)  sources are this lane's own cells: a register delay line of the last P+1 iterations
+//                         (x = 0010 is the neighbouring offset of the SAME iteration: offsets are swept in ascending order)
+//   x0 = 1 (six cases)    sources are the lane above, 1, 2, P or P+1 iterations ago: 4*W warp shuffles per iteration;
+//                         lane 0 takes them from an exchange block written by lane 31 of the warp above (or staged from
+//                         the boundary stream the previous row block left in global memory)
+// Band edges in a are compile-time (the case is simply not instantiated), band edges in b are a poison on the additive
+// constant, the range guard (pyx:133-138) is "cells outside the pair hold minus infinity".  With traceback every value is
+// value << 4 | (15 - case index): plain max is then (value desc, case order asc), the low nibble of the winner is the
+// code, and it is cleared before the value is handed on.  Codes: one nibble per cell, W nibbles = one uint32 per lane and
+// iteration, stored in computation order [row block][warp][iteration][lane] (128 contiguous bytes per warp).
+#include <utility>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace ba {
+namespace na {
+
+constexpr int PRE_MAX = 12;  // >= P + 2 for every instantiated band
+
+template <int S>
+struct Geo {
+    static constexpr int W = 2 * S + 1;
+    static constexpr int P = W < 2 ? 2 : W;   // S = 0 keeps one pad cell per column so that D(0100) = P-1 >= 1
+    static constexpr int NH = P + 1;          // own history depth (iterations)
+    static constexpr int RING = P + 3;        // exchange-block depth: reads reach back P+1 iterations, +1 write slot, +1 slack
+    static constexpr int XW = 8;              // ints per exchange record (W <= 7 values)
+    static constexpr int PRE = P + 1;         // iterations run before position 0 so that the staged row above is primed
+    static constexpr int LA = 8;              // cp.async look-ahead of the boundary staging (iterations)
+    static constexpr int PB = 16;             // landing-zone depth, power of two > LA
+};
+
+__device__ __forceinline__ int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); }
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int S, bool TRACE>
+__global__ void __launch_bounds__(256) fill_na_kernel(SysArgs A) {
+    using G_ = Geo<S>;
+    constexpr int W = G_::W, P = G_::P, NH = G_::NH, RING = G_::RING, XW = G_::XW, PRE = G_::PRE, LA = G_::LA, PB = G_::PB;
+    static_assert(W <= 7 && PRE <= PRE_MAX, "band too wide for this kernel");
+    extern __shared__ __align__(16) int smem[];
+    const int G = blockDim.x >> 5, RT = G * 32;
+    int* xs = smem;                                   // [(G+1)][RING][XW]   xs[0] = staged row above the block
+    int* pb = xs + (G + 1) * RING * XW;               // [PB][XW]
+    int* ssim = pb + PB * XW;                         // [(nsym+1)][nsym], last row zero
+    const int nsym = A.sc.nsym;
+    uint8_t* sresB = reinterpret_cast<uint8_t*>(ssim + (nsym + 1) * nsym);
+    const int bpad = A.bpad, boff = A.boff;
+    uint8_t* sclsB = sresB + bpad;
+    __shared__ int s_pair;
+
+    const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+    const int TB = TRACE ? 4 : 0;
+    const int NEGP = A.negp;
+    const int w_p = A.w_p, kG2 = A.k_2g, kGD = A.k_gd, kD = A.k_d;
+    constexpr int T_ = TRACE ? 1 : 0;
+
+    for (int q = tid; q < (G + 1) * RING * XW + PB * XW; q += blockDim.x) smem[q] = NEGP;
+    for (int q = tid; q < (nsym + 1) * nsym; q += blockDim.x) ssim[q] = (q < nsym * nsym) ? A.sim_p[q] : 0;
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) s_pair = atomicAdd(A.counter, 1);
+        __syncthreads();
+        const int pi = s_pair;
+        __syncthreads();
+        if (pi >= A.npairs) return;
+        const PairDesc d = A.pairs[pi];
+        const int n = d.n, m = d.m;
+        const uint8_t* ra = A.res + d.offA;
+        const uint8_t* ca = A.cls + d.offA;
+        for (int q = tid; q < bpad; q += blockDim.x) {
+            const int l = q - boff;
+            sresB[q] = (l >= 1 && l <= m) ? A.res[d.offB + l - 1] : 0;
+            sclsB[q] = (l >= 1 && l <= m) ? A.cls[d.offB + l - 1] : 255;
+        }
+        __syncthreads();
+
+        const int npass = (n + RT) / RT;
+        const int nit = (m + 1) * P + RT;                  // iterations 0 .. nit-1 cover every lane's last cell
+        const size_t bstride = (size_t)A.bnd_iters * XW;   // ints per boundary buffer
+        int* bnd_base = A.bnd + (size_t)blockIdx.x * 2 * bstride;
+
+        for (int pass = 0; pass < npass; ++pass) {
+            const int rr = g * 32 + lane, i = pass * RT + rr;
+            const bool has_in = pass > 0, has_out = pass + 1 < npass;
+            const int* bnd_in = bnd_base + (size_t)((pass + 1) & 1) * bstride;
+            int* bnd_out = bnd_base + (size_t)(pass & 1) * bstride;
+            const int Ai = (i >= 1 && i <= n) ? ra[i - 1] : nsym;  // zero row for i = 0 and rows outside the pair
+            const int* simrow = ssim + Ai * nsym;
+            int cA[W];       // structure class of A at k = i + a (254 never matches)
+            bool okA[W];     // band offset inside the pair: 0 <= k <= n, row inside the pair
+#pragma unroll
+            for (int aa = 0; aa < W; ++aa) {
+                const int k = i + aa - S;
+                okA[aa] = i <= n && k >= 0 && k <= n;
+                cA[aa] = (okA[aa] && k >= 1) ? ca[k - 1] : 254;
+            }
+            const int q_origin = (i == 0) ? S : (int)0x80000000;               // cell (0,0,0,0): j = 0, b = 0
+            const int q_end = (i == n) ? m * P + S + rr : (int)0x80000000;     // cell (n,m,n,m)
+            uint32_t* cw = nullptr;
+            if (TRACE) cw = reinterpret_cast<uint32_t*>(A.codes + d.code_off) + ((long long)pass * G + g) * (long long)(nit + PRE) * 32 + lane;
+
+            // position one iteration before the first one (q = -PRE)
+            int pos = -PRE - 1 - rr;
+            int j = -((-pos + P - 1) / P);
+            int bb = pos - j * P;
+            int slot = (((-PRE - 1) % RING) + RING) % RING;
+            int mu1 = 0;
+            int h[NH][W];  // h[d-1][aa]: this lane's value at band offset aa, d iterations ago
+#pragma unroll
+            for (int dd = 0; dd < NH; ++dd)
+#pragma unroll
+                for (int aa = 0; aa < W; ++aa) h[dd][aa] = NEGP;
+
+            // boundary I/O: thread e < W moves element e of the record of one iteration
+            const bool io = tid < W;
+            const int io_e = io ? tid : 0;
+            const bool do_flush = has_out && io, do_stage = has_in && io;
+            if (has_in) {  // prime: records of the producer's iterations q + RT for q = -PRE .. -PRE+LA-1
+                for (int t0 = -PRE; t0 < LA - PRE; ++t0) {
+                    const int rec = t0 + RT;
+                    if (io && rec < nit) {
+                        const unsigned dst = smem_u32(pb + ((t0 + 4 * PB) & (PB - 1)) * XW + io_e);
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(bnd_in + (size_t)(rec + PRE + 1) * XW + io_e) : "memory");
+                    }
+                    asm volatile("cp.async.commit_group;\n" ::: "memory");
+                }
+            }
+            __syncthreads();
+
+            for (int q = -PRE; q < nit; ++q) {
+                ++bb;
+                if (bb == P) { bb = 0; ++j; }
+                slot = (slot + 1 == RING) ? 0 : slot + 1;
+                const int l = j + bb - S;
+                const bool colok = (bb < W) && ((unsigned)j <= (unsigned)m) && ((unsigned)l <= (unsigned)m);
+                if (bb == 0) mu1 = simrow[sresB[j + boff]];
+                const int cB = sclsB[l + boff];
+
+                // ---- flush the record of iteration q-1 (exchange block xs[G], written before the last barrier)
+                if (do_flush) {
+                    const int ps = (slot == 0) ? RING - 1 : slot - 1;
+                    bnd_out[(size_t)(q + PRE) * XW + io_e] = xs[(G * RING + ps) * XW + io_e];
+                }
+
+                // ---- the row above, 1, 2, P and P+1 iterations ago
+                int U1[W], U2[W], UP[W], UQ[W];
+#pragma unroll
+                for (int aa = 0; aa < W; ++aa) {
+                    U1[aa] = __shfl_up_sync(0xffffffffu, h[0][aa], 1);
+                    U2[aa] = __shfl_up_sync(0xffffffffu, h[1][aa], 1);
+                    UP[aa] = __shfl_up_sync(0xffffffffu, h[P - 1][aa], 1);
+                    UQ[aa] = __shfl_up_sync(0xffffffffu, h[P][aa], 1);
+                }
+                if (lane == 0) {  // from the exchange block of the warp above (xs[0]: the staged boundary)
+                    int s1 = slot - 1, s2 = slot - 2, sp = slot - P, sq = slot - (P + 1);
+                    if (s1 < 0) s1 += RING;
+                    if (s2 < 0) s2 += RING;
+                    if (sp < 0) sp += RING;
+                    if (sq < 0) sq += RING;
+                    const int* xb = xs + g * RING * XW;
+#pragma unroll
+                    for (int aa = 0; aa < W; ++aa) {
+                        U1[aa] = xb[s1 * XW + aa];
+                        U2[aa] = xb[s2 * XW + aa];
+                        UP[aa] = xb[sp * XW + aa];
+                        UQ[aa] = xb[sq * XW + aa];
+                    }
+                }
+
+                // ---- additive constants shared by all band offsets of this iteration (scores of pyx:233-248; the low
+                // nibble carries 15 - case index when codes are wanted); pB0 / pB1: the source column b-1 / b+1 is outside the band
+                const int pB0 = (bb == 0) ? NEGP : 0, pB1 = (bb == W - 1) ? NEGP : 0;
+                const int c1 = kG2 + T_ * 14, c2 = kG2 + T_ * 13;
+                const int c3 = mu1 + kD + pB1 + T_ * 12;
+                const int c5 = kGD + T_ * 10, c6 = kGD + pB1 + T_ * 9, c7 = kGD + T_ * 8, c8 = kGD + pB0 + T_ * 7;
+                const int c11 = mu1 + kGD + pB1 + T_ * 4, c12 = mu1 + kGD + T_ * 3;
+                int M[W];
+                uint32_t code = 0;
+#pragma unroll
+                for (int aa = 0; aa < W; ++aa) {
+                    const int mu2 = (cB == cA[aa]) ? w_p : 0;
+                    int v = addmax(UQ[aa], mu1 + mu2 + T_ * 15, NEGP);              // 1111  case 0
+                    v = addmax(U1[aa], c1, v);                                       // 1010  case 1
+                    v = addmax(h[P - 1][aa], c2, v);                                 // 0101  case 2
+                    if (aa + 1 < W) v = addmax(UP[aa + 1], c3, v);                   // 1100  case 3
+                    if (aa >= 1) v = addmax(h[0][aa - 1], mu2 + kD + pB0 + T_ * 11, v);  // 0011  case 4
+                    if (aa + 1 < W) v = addmax(U1[aa + 1], c5, v);                   // 1000  case 5
+                    if (P >= 2) v = addmax(h[P - 2][aa], c6, v);                     // 0100  case 6
+                    if (aa >= 1) v = addmax(M[aa - 1], c7, v);                       // 0010  case 7 (same iteration)
+                    v = addmax(h[0][aa], c8, v);                                     // 0001  case 8
+                    v = addmax(U2[aa], mu2 + kGD + pB0 + T_ * 6, v);                 // 1011  case 9
+                    if (aa >= 1) v = addmax(h[P - 1][aa - 1], mu2 + kGD + T_ * 5, v);    // 0111  case 10
+                    v = addmax(UP[aa], c11, v);                                      // 1110  case 11
+                    if (aa + 1 < W) v = addmax(UQ[aa + 1], c12, v);                  // 1101  case 12
+                    v = (colok && okA[aa]) ? v : NEGP;
+                    if (aa == S && q == q_origin) v = 0;                             // M[0,0,0,0] = 0 (numpy zeros, pyx:27-35)
+                    if (TRACE) {
+                        // a cell no case reaches keeps nibble 15 ("none"): NEGP has a zero low nibble -> 15 - 0
+                        code |= (uint32_t)(15 - (v & 15)) << (4 * aa);
+                        v &= ~15;
+                    }
+                    M[aa] = v;
+                }
+                if (TRACE) { *cw = code; cw += 32; }
+
+                if (q == q_end) {
+                    const int best = M[S] >> TB;
+                    A.scores[d.orig] = (long long)best * A.gscale;
+                    A.start_state[d.orig] = 8;
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) A.end_values[(size_t)d.orig * 9 + t] = best * A.gscale;
+                }
+
+                // ---- publish: the last lane of every warp feeds lane 0 of the warp below / the next row block
+                if (lane == 31) {
+                    int* xo = xs + ((g + 1) * RING + slot) * XW;
+#pragma unroll
+                    for (int aa = 0; aa < W; ++aa) xo[aa] = M[aa];
+                }
+#pragma unroll
+                for (int dd = NH - 1; dd >= 1; --dd)
+#pragma unroll
+                    for (int aa = 0; aa < W; ++aa) h[dd][aa] = h[dd - 1][aa];
+#pragma unroll
+                for (int aa = 0; aa < W; ++aa) h[0][aa] = M[aa];
+
+                // ---- stage the row above this block for iteration q (what lane 0 of warp 0 reads from the next one on)
+                if (has_in) {
+                    asm volatile("cp.async.wait_group %0;\n" ::"n"(LA - 1) : "memory");
+                    if (do_stage) {
+                        int val = pb[((q + 4 * PB) & (PB - 1)) * XW + io_e];
+                        if (q + RT >= nit) val = NEGP;
+                        xs[slot * XW + io_e] = val;
+                        if (q + LA + RT < nit) {
+                            const unsigned dst = smem_u32(pb + ((q + LA + 4 * PB) & (PB - 1)) * XW + io_e);
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(bnd_in + (size_t)(q + LA + RT + PRE + 1) * XW + io_e) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;\n" ::: "memory");
+                }
+                __syncthreads();
+            }
+            if (has_out) {  // the record of the last iteration, then make the stream visible to the next row block
+                if (io) bnd_out[(size_t)(nit + PRE) * XW + io_e] = xs[(G * RING + slot) * XW + io_e];
+                __threadfence();
+            }
+            if (has_in) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            if (!has_out && has_in)  // leaving a multi-block pair: the staged row must read "minus infinity" again
+                for (int qq = tid; qq < RING * XW; qq += blockDim.x) xs[qq] = NEGP;
+            __syncthreads();
+        }
+    }
+}
+
+template <int S>
+size_t smem_bytes_t(int G, int nsym, int bpad) {
+    using G_ = Geo<S>;
+    const size_t ints = (size_t)(G + 1) * G_::RING * G_::XW + (size_t)G_::PB * G_::XW + (size_t)(nsym + 1) * nsym;
+    return ((ints * 4 + 2 * (size_t)bpad) + 15) & ~(size_t)15;
+}
+
+template <int S, bool TRACE>
+cudaError_t launch_t(const SysArgs& A, int grid, int G, size_t smem, cudaStream_t st) {
+    auto kern = fill_na_kernel<S, TRACE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, G * 32, smem, st>>>(A);
+    return cudaGetLastError();
+}
+template <int S, bool TRACE>
+int occ_t(int G, size_t smem) {
+    auto kern = fill_na_kernel<S, TRACE>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, G * 32, smem);
+    return nb;
+}
+
+}  // namespace na
+
+// ---- host-side geometry (mirrors na::Geo) and dispatch over max_shift
+static int na_P(int S) { return 2 * S + 1 < 2 ? 2 : 2 * S + 1; }
+int na_iters(int S, int G, int m) { return (m + 1) * na_P(S) + G * 32; }
+int na_pre(int S) { return na_P(S) + 1; }
+int na_boff(int S, int G) { return (G * 32 + 2 * na_P(S) + 16) / na_P(S) + 3 + S; }
+int na_bpad(int S, int G, int mmax) { return na_boff(S, G) + mmax + (G * 32 + 2 * na_P(S) + 16) / na_P(S) + S + 8; }
+size_t na_boundary_ints(int S, int G, int mmax) { return (size_t)(na_iters(S, G, mmax) + na_pre(S) + 8) * 8; }
+long long na_code_words(int S, int G, int n, int m) {  // uint64 units: one uint32 per lane and iteration
+    const int RT = G * 32;
+    return ((long long)((n + RT) / RT) * G * (na_iters(S, G, m) + na_pre(S)) * 32 + 1) / 2;
+}
+size_t na_smem_bytes(int S, int G, int nsym, int mmax) {
+    const int bpad = na_bpad(S, G, mmax);
+    switch (S) {
+        case 0: return na::smem_bytes_t<0>(G, nsym, bpad);
+        case 1: return na::smem_bytes_t<1>(G, nsym, bpad);
+        case 2: return na::smem_bytes_t<2>(G, nsym, bpad);
+        default: return na::smem_bytes_t<3>(G, nsym, bpad);
+    }
+}
+int na_occupancy(int S, bool trace, int G, size_t smem) {
+    switch (S) {
+        case 0: return trace ? na::occ_t<0, true>(G, smem) : na::occ_t<0, false>(G, smem);
+        case 1: return trace ? na::occ_t<1, true>(G, smem) : na::occ_t<1, false>(G, smem);
+        case 2: return trace ? na::occ_t<2, true>(G, smem) : na::occ_t<2, false>(G, smem);
+        case 3: return trace ? na::occ_t<3, true>(G, smem) : na::occ_t<3, false>(G, smem);
+    }
+    return 0;
+}
+cudaError_t launch_fill_na(const SysArgs& A, int grid, int G, size_t smem, bool trace, cudaStream_t st) {
+    switch (A.sc.s) {
+        case 0: return trace ? na::launch_t<0, true>(A, grid, G, smem, st) : na::launch_t<0, false>(A, grid, G, smem, st);
+        case 1: return trace ? na::launch_t<1, true>(A, grid, G, smem, st) : na::launch_t<1, false>(A, grid, G, smem, st);
+        case 2: return trace ? na::launch_t<2, true>(A, grid, G, smem, st) : na::launch_t<2, false>(A, grid, G, smem, st);
+        case 3: return trace ? na::launch_t<3, true>(A, grid, G, smem, st) : na::launch_t<3, false>(A, grid, G, smem, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace ba

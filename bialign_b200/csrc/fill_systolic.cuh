@@ -202,11 +202,18 @@ struct Geo {
     static constexpr int P = PAD ? 2 * S + 2 : (S == 0 ? 2 : 2 * S + 1);  // cells per column (S = 0 keeps its pad cell: D >= 1)
     static constexpr int R = 32 / LPR;                       // rows per warp
     static constexpr int RING = P + 3;                       // ring depth in iterations (max delay P+2; +1: reads never meet the write)
-    static constexpr int NV = 12;                            // ring values per lane per iteration
+    // Ring values per lane and iteration, ordered by who reads them:
+    //   0..2  Q[11][01,10,11]   3..5  L[11][01,10,11]      row below (x0 = 1): the only ones a boundary record carries
+    //   6, 7  Q[01][10], Q[01][11]                          next lane of the same row (x0 = 0, x2 = 1)
+    //   8     Q[01][01]         9..11 L[01][01,10,11]      the same lane (x0 = 0, x2 = 0), P resp. P-1 iterations later:
+    //                                                       kept in register delay lines instead when P is small (SELFREG)
+    static constexpr bool SELFREG = (P <= 5);
+    static constexpr int NV = SELFREG ? 8 : 12;
+    static constexpr int NVR = 6;                            // ring values in a boundary record
     static constexpr int NX = 6;                             // short-delay values crossing a warp boundary
     static constexpr int LA = RING;                          // cp.async look-ahead (iterations) of the boundary staging
     static constexpr int PB = 2 * RING;                      // prefetch-buffer depth (iterations): two ring periods
-    static constexpr int REAL = (NV + NX) * LPR;             // values per boundary record (one iteration of one row)
+    static constexpr int REAL = (NVR + NX) * LPR;            // values per boundary record (one iteration of one row)
     static constexpr int REC = (REAL + 3) & ~3;              // record stride in ints (16-byte multiple)
     static constexpr int RSLOT = NV * 32;
     // short-delay exchange block, per slot: recB [LPR+1][4] = {Q[10][01] of the iteration before, L[10][01,10,11]} then
@@ -255,7 +262,8 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
     static_assert(!P16 || (!TRACE && !PAD && BNEG && !LONG), "16-bit pair mode: score only, pad-free, beta < 0, batch mode");
     static_assert(!NA || (BNEG && !LONG && !P16), "non-affine flavour: batch mode, 32-bit");
     using G_ = Geo<S, PAD>;
-    constexpr int W = G_::W, P = G_::P, LPR = G_::LPR, R = G_::R, RING = G_::RING, NV = G_::NV, NX = G_::NX, PB = G_::PB;
+    constexpr int W = G_::W, P = G_::P, LPR = G_::LPR, R = G_::R, RING = G_::RING, NV = G_::NV, NVR = G_::NVR, PB = G_::PB;
+    constexpr bool SELFREG = G_::SELFREG;
     constexpr int RSLOT = G_::RSLOT, REC = G_::REC, REAL = G_::REAL, LA = G_::LA, XSLOT = G_::XSLOT, LQB = G_::LQB, XA = G_::XA;
     constexpr int RSLOTB = RSLOT * 4, XSLOTB = XSLOT * 4, RECB = REC * 4;
     constexpr bool PF = LONG && (P - 1) >= 2;       // ring inputs fetched one iteration ahead (pays off in the long-pair pipeline only)
@@ -396,10 +404,10 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
             // the fourth warp skipping the boundary I/O matters more than the divergence bookkeeping.)
             const int io_e = io_thread ? tid : 0;
             const int io_v = io_e / LPR, io_cs = io_e - io_v * LPR;
-            const bool io_ring = io_v < NV;
+            const bool io_ring = io_v < NVR;
             const int io_stride = io_ring ? RSLOT : XSLOT;
             // record elements beyond the ring values are the exchange block's 4*LPR recB ints, then its 2*LPR recA ints
-            const int io_x = io_e - NV * LPR;
+            const int io_x = io_e - NVR * LPR;
             const int io_col = io_ring ? io_v * 32 + (R - 1) * LPR + io_cs
                                        : (int)((G + 1) * RING * RSLOT) + (io_x < 4 * LPR ? io_x : XA + io_x - 4 * LPR);
             const int fl_src = io_col + (io_ring ? G * RING * RSLOT : G * RING * XSLOT);  // CTA output row
@@ -417,10 +425,10 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int e = 4 * tid + u, v = e / LPR, cs = e - v * LPR;
-                    const bool rg = v < NV;
+                    const bool rg = v < NVR;
                     lg_ring |= rg ? (1 << u) : 0;
                     lg_real |= (e < REAL) ? (1 << u) : 0;
-                    const int x = e - NV * LPR;
+                    const int x = e - NVR * LPR;
                     lg_dst[u] = smem_u32(smem + (rg ? v * 32 + (R - 1) * LPR + cs : (int)((G + 1) * RING * RSLOT) + (x < 4 * LPR ? x : XA + x - 4 * LPR)));
                 }
             }
@@ -474,7 +482,17 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                 for (int y = 0; y < 3; ++y) hR[x][y] = NEGP;
             int h2Q1010 = NEGP, h2Q1001 = NEGP, h2Q1011 = NEGP, h3Q1011 = NEGP;
             int h2R11[3] = {NEGP, NEGP, NEGP};
-            int pfF[6] = {NEGP, NEGP, NEGP, NEGP, NEGP, NEGP}, pfH[6] = {NEGP, NEGP, NEGP, NEGP, NEGP, NEGP};
+            int pf[12];  // PF: ring inputs of the next iteration, by ring id
+#pragma unroll
+            for (int v = 0; v < 12; ++v) pf[v] = NEGP;
+            // SELFREG: this lane's own Q[01][01] of the last P iterations and L[01][*] of the last P-1 (oldest first)
+            int dQ[P], dL[3][P > 1 ? P - 1 : 1];
+#pragma unroll
+            for (int k = 0; k < P; ++k) dQ[k] = NEGP;
+#pragma unroll
+            for (int y = 0; y < 3; ++y)
+#pragma unroll
+                for (int k = 0; k < P - 1; ++k) dL[y][k] = NEGP;
 
             if (LONG && has_in) {  // wait for the first records of the producer pass, then prime with 16-byte copies
                 if (tid == 0) {
@@ -547,37 +565,52 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                 // long-delay values from the rings (ids: 0..2 Q[11][01,10,11], 3..5 Q[01][..], 6..8 L[11][..], 9..11 L[01][..]).
                 // They are at least P-1 iterations old, so (when P-1 >= 2) they were fetched during the previous
                 // iteration: the loads overlap that iteration's tail and the barrier instead of stalling this one.
+                // ring id -> (source lane base, delay): 0:(U1,P+1) 1:(U0,P+1) 2:(U0,P+2) 3-5:(U1,P) 6:(W,P) 7:(W,P+1) 8:(S,P) 9-11:(S,P-1)
+                int rv[12];
                 if (PF) {
 #pragma unroll
-                    for (int y = 0; y < 3; ++y) { inH1[6 + y] = pfH[y]; inH1[y] = pfH[3 + y]; }
-                    inF[8] = pfF[0]; inF[7] = pfF[1]; inF[6] = pfF[2]; inF[2] = pfF[3]; inF[1] = pfF[4]; inF[0] = pfF[5];
+                    for (int v = 0; v < 12; ++v) rv[v] = pf[v];
                 } else if constexpr (ST) {
                     constexpr int oA = ((u + 2 * RING - (P + 2)) % RING) * RSLOTB, oB = ((u + 2 * RING - (P + 1)) % RING) * RSLOTB;
                     constexpr int oC = ((u + 2 * RING - P) % RING) * RSLOTB, oD = ((u + 2 * RING - (P - 1)) % RING) * RSLOTB;
-                    inF[8] = lds32o<oA + 2 * 128>(rU0);  // x=1111 Q[11][11]
-                    inF[7] = lds32o<oB + 1 * 128>(rU0);  // x=1110 Q[11][10]
-                    inF[6] = lds32o<oB + 0 * 128>(rU1);  // x=1101 Q[11][01]
-                    inF[2] = lds32o<oB + 5 * 128>(rW);   // x=0111 Q[01][11]
-                    inF[1] = lds32o<oC + 4 * 128>(rW);   // x=0110 Q[01][10]
-                    inF[0] = lds32o<oC + 3 * 128>(rS);   // x=0101 Q[01][01]
-                    inH1[6] = lds32o<oC + 6 * 128>(rU1); inH1[7] = lds32o<oC + 7 * 128>(rU1); inH1[8] = lds32o<oC + 8 * 128>(rU1);  // x=1100 L[11][*]
-                    inH1[0] = lds32o<oD + 9 * 128>(rS); inH1[1] = lds32o<oD + 10 * 128>(rS); inH1[2] = lds32o<oD + 11 * 128>(rS);   // x=0100 L[01][*]
+                    rv[2] = lds32o<oA + 2 * 128>(rU0);
+                    rv[1] = lds32o<oB + 1 * 128>(rU0);
+                    rv[0] = lds32o<oB + 0 * 128>(rU1);
+                    rv[7] = lds32o<oB + 7 * 128>(rW);
+                    rv[6] = lds32o<oC + 6 * 128>(rW);
+                    rv[3] = lds32o<oC + 3 * 128>(rU1); rv[4] = lds32o<oC + 4 * 128>(rU1); rv[5] = lds32o<oC + 5 * 128>(rU1);
+                    if constexpr (!SELFREG) {
+                        rv[8] = lds32o<oC + 8 * 128>(rS);
+                        rv[9] = lds32o<oD + 9 * 128>(rS); rv[10] = lds32o<oD + 10 * 128>(rS); rv[11] = lds32o<oD + 11 * 128>(rS);
+                    }
                 } else {
                     int rsA, rsB, rsC, rsD;  // ring slots written P+2, P+1, P, P-1 iterations ago
                     rsA = wslot - (P + 2); if (rsA < 0) rsA += RING;
                     rsB = wslot - (P + 1); if (rsB < 0) rsB += RING;
                     rsC = wslot - P;       if (rsC < 0) rsC += RING;
                     rsD = wslot - (P - 1); if (rsD < 0) rsD += RING;
-                    inF[8] = lds32o<(2) * 128>(rU0 + rsA * RSLOTB);  // x=1111 Q[11][11]
-                    inF[7] = lds32o<(1) * 128>(rU0 + rsB * RSLOTB);  // x=1110 Q[11][10]
-                    inF[6] = lds32o<(0) * 128>(rU1 + rsB * RSLOTB);  // x=1101 Q[11][01]
-                    inF[2] = lds32o<(5) * 128>(rW + rsB * RSLOTB);   // x=0111 Q[01][11]
-                    inF[1] = lds32o<(4) * 128>(rW + rsC * RSLOTB);   // x=0110 Q[01][10]
-                    inF[0] = lds32o<(3) * 128>(rS + rsC * RSLOTB);   // x=0101 Q[01][01]
-                    const unsigned aU1C = rU1 + rsC * RSLOTB, aSD = rS + rsD * RSLOTB;
-                    inH1[6] = lds32o<6 * 128>(aU1C); inH1[7] = lds32o<7 * 128>(aU1C); inH1[8] = lds32o<8 * 128>(aU1C);  // x=1100 L[11][*]
-                    inH1[0] = lds32o<9 * 128>(aSD); inH1[1] = lds32o<10 * 128>(aSD); inH1[2] = lds32o<11 * 128>(aSD);   // x=0100 L[01][*]
+                    rv[2] = lds32o<2 * 128>(rU0 + rsA * RSLOTB);
+                    rv[1] = lds32o<1 * 128>(rU0 + rsB * RSLOTB);
+                    rv[0] = lds32o<0 * 128>(rU1 + rsB * RSLOTB);
+                    rv[7] = lds32o<7 * 128>(rW + rsB * RSLOTB);
+                    rv[6] = lds32o<6 * 128>(rW + rsC * RSLOTB);
+                    const unsigned aU1C = rU1 + rsC * RSLOTB;
+                    rv[3] = lds32o<3 * 128>(aU1C); rv[4] = lds32o<4 * 128>(aU1C); rv[5] = lds32o<5 * 128>(aU1C);
+                    if constexpr (!SELFREG) {
+                        const unsigned aSD = rS + rsD * RSLOTB;
+                        rv[8] = lds32o<8 * 128>(rS + rsC * RSLOTB);
+                        rv[9] = lds32o<9 * 128>(aSD); rv[10] = lds32o<10 * 128>(aSD); rv[11] = lds32o<11 * 128>(aSD);
+                    }
                 }
+                if (SELFREG) {  // this lane's own values of P resp. P-1 iterations ago never left its registers
+                    rv[8] = dQ[0];
+#pragma unroll
+                    for (int y = 0; y < 3; ++y) rv[9 + y] = dL[y][0];
+                }
+                inF[6] = rv[0]; inF[7] = rv[1]; inF[8] = rv[2];     // x=1101, 1110, 1111   Q[11][*]
+                inF[1] = rv[6]; inF[2] = rv[7]; inF[0] = rv[8];     // x=0110, 0111, 0101   Q[01][*]
+#pragma unroll
+                for (int y = 0; y < 3; ++y) { inH1[6 + y] = rv[3 + y]; inH1[y] = rv[9 + y]; }  // x=1100 L[11][*], x=0100 L[01][*]
                 // short-delay values by shuffle
                 inF[5] = __shfl_up_sync(0xffffffffu, h3Q1011, LPR);      // x=1011 D=3
                 inF[4] = __shfl_up_sync(0xffffffffu, h2Q1010, LPR);      // x=1010 D=2
@@ -752,14 +785,16 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                     if constexpr (ST) {
                         constexpr int oA = ((u + 1 + 2 * RING - (P + 2)) % RING) * RSLOTB, oB = ((u + 1 + 2 * RING - (P + 1)) % RING) * RSLOTB;
                         constexpr int oC = ((u + 1 + 2 * RING - P) % RING) * RSLOTB, oD = ((u + 1 + 2 * RING - (P - 1)) % RING) * RSLOTB;
-                        pfF[0] = lds32o<oA + 2 * 128>(rU0);
-                        pfF[1] = lds32o<oB + 1 * 128>(rU0);
-                        pfF[2] = lds32o<oB + 0 * 128>(rU1);
-                        pfF[3] = lds32o<oB + 5 * 128>(rW);
-                        pfF[4] = lds32o<oC + 4 * 128>(rW);
-                        pfF[5] = lds32o<oC + 3 * 128>(rS);
-                        pfH[0] = lds32o<oC + 6 * 128>(rU1); pfH[1] = lds32o<oC + 7 * 128>(rU1); pfH[2] = lds32o<oC + 8 * 128>(rU1);
-                        pfH[3] = lds32o<oD + 9 * 128>(rS); pfH[4] = lds32o<oD + 10 * 128>(rS); pfH[5] = lds32o<oD + 11 * 128>(rS);
+                        pf[2] = lds32o<oA + 2 * 128>(rU0);
+                        pf[1] = lds32o<oB + 1 * 128>(rU0);
+                        pf[0] = lds32o<oB + 0 * 128>(rU1);
+                        pf[7] = lds32o<oB + 7 * 128>(rW);
+                        pf[6] = lds32o<oC + 6 * 128>(rW);
+                        pf[3] = lds32o<oC + 3 * 128>(rU1); pf[4] = lds32o<oC + 4 * 128>(rU1); pf[5] = lds32o<oC + 5 * 128>(rU1);
+                        if constexpr (!SELFREG) {
+                            pf[8] = lds32o<oC + 8 * 128>(rS);
+                            pf[9] = lds32o<oD + 9 * 128>(rS); pf[10] = lds32o<oD + 10 * 128>(rS); pf[11] = lds32o<oD + 11 * 128>(rS);
+                        }
                     } else {
                         const int ns = (wslot + 1 == RING) ? 0 : wslot + 1;
                         int rsA, rsB, rsC, rsD;
@@ -767,25 +802,29 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                         rsB = ns - (P + 1); if (rsB < 0) rsB += RING;
                         rsC = ns - P;       if (rsC < 0) rsC += RING;
                         rsD = ns - (P - 1); if (rsD < 0) rsD += RING;
-                        pfF[0] = lds32o<(2) * 128>(rU0 + rsA * RSLOTB);  // x=1111 Q[11][11]
-                        pfF[1] = lds32o<(1) * 128>(rU0 + rsB * RSLOTB);  // x=1110 Q[11][10]
-                        pfF[2] = lds32o<(0) * 128>(rU1 + rsB * RSLOTB);  // x=1101 Q[11][01]
-                        pfF[3] = lds32o<(5) * 128>(rW + rsB * RSLOTB);   // x=0111 Q[01][11]
-                        pfF[4] = lds32o<(4) * 128>(rW + rsC * RSLOTB);   // x=0110 Q[01][10]
-                        pfF[5] = lds32o<(3) * 128>(rS + rsC * RSLOTB);   // x=0101 Q[01][01]
-                        const unsigned aU1C = rU1 + rsC * RSLOTB, aSD = rS + rsD * RSLOTB;
-                        pfH[0] = lds32o<6 * 128>(aU1C); pfH[1] = lds32o<7 * 128>(aU1C); pfH[2] = lds32o<8 * 128>(aU1C);   // x=1100 L[11][*]
-                        pfH[3] = lds32o<9 * 128>(aSD); pfH[4] = lds32o<10 * 128>(aSD); pfH[5] = lds32o<11 * 128>(aSD);    // x=0100 L[01][*]
+                        pf[2] = lds32o<2 * 128>(rU0 + rsA * RSLOTB);
+                        pf[1] = lds32o<1 * 128>(rU0 + rsB * RSLOTB);
+                        pf[0] = lds32o<0 * 128>(rU1 + rsB * RSLOTB);
+                        pf[7] = lds32o<7 * 128>(rW + rsB * RSLOTB);
+                        pf[6] = lds32o<6 * 128>(rW + rsC * RSLOTB);
+                        const unsigned aU1C = rU1 + rsC * RSLOTB;
+                        pf[3] = lds32o<3 * 128>(aU1C); pf[4] = lds32o<4 * 128>(aU1C); pf[5] = lds32o<5 * 128>(aU1C);
+                        if constexpr (!SELFREG) {
+                            const unsigned aSD = rS + rsD * RSLOTB;
+                            pf[8] = lds32o<8 * 128>(rS + rsC * RSLOTB);
+                            pf[9] = lds32o<9 * 128>(aSD); pf[10] = lds32o<10 * 128>(aSD); pf[11] = lds32o<11 * 128>(aSD);
+                        }
                     }
                 }
 
                 // ring: long-delay values; short-delay values for the warp below / the next pass (only the last row's matter)
                 if constexpr (ST) {
-#pragma unroll
-                    for (int y = 0; y < 3; ++y) {
-                        if (y == 0) { sts32o<u * RSLOTB + 0 * 128>(wS, Qv[2][0]); sts32o<u * RSLOTB + 3 * 128>(wS, Qv[0][0]); sts32o<u * RSLOTB + 6 * 128>(wS, Lv[2][0]); sts32o<u * RSLOTB + 9 * 128>(wS, Lv[0][0]); }
-                        if (y == 1) { sts32o<u * RSLOTB + 1 * 128>(wS, Qv[2][1]); sts32o<u * RSLOTB + 4 * 128>(wS, Qv[0][1]); sts32o<u * RSLOTB + 7 * 128>(wS, Lv[2][1]); sts32o<u * RSLOTB + 10 * 128>(wS, Lv[0][1]); }
-                        if (y == 2) { sts32o<u * RSLOTB + 2 * 128>(wS, Qv[2][2]); sts32o<u * RSLOTB + 5 * 128>(wS, Qv[0][2]); sts32o<u * RSLOTB + 8 * 128>(wS, Lv[2][2]); sts32o<u * RSLOTB + 11 * 128>(wS, Lv[0][2]); }
+                    sts32o<u * RSLOTB + 0 * 128>(wS, Qv[2][0]); sts32o<u * RSLOTB + 1 * 128>(wS, Qv[2][1]); sts32o<u * RSLOTB + 2 * 128>(wS, Qv[2][2]);
+                    sts32o<u * RSLOTB + 3 * 128>(wS, Lv[2][0]); sts32o<u * RSLOTB + 4 * 128>(wS, Lv[2][1]); sts32o<u * RSLOTB + 5 * 128>(wS, Lv[2][2]);
+                    sts32o<u * RSLOTB + 6 * 128>(wS, Qv[0][1]); sts32o<u * RSLOTB + 7 * 128>(wS, Qv[0][2]);
+                    if constexpr (!SELFREG) {
+                        sts32o<u * RSLOTB + 8 * 128>(wS, Qv[0][0]);
+                        sts32o<u * RSLOTB + 9 * 128>(wS, Lv[0][0]); sts32o<u * RSLOTB + 10 * 128>(wS, Lv[0][1]); sts32o<u * RSLOTB + 11 * 128>(wS, Lv[0][2]);
                     }
                     sts128o_if<u * XSLOTB>(xso_b, hQ10[0], Lv[1][0], Lv[1][1], Lv[1][2], lastrow);
                     sts64o_if<u * XSLOTB + XA * 4>(xso_b - 8 * c, hQ10[2], Qv[1][1], lastrow);
@@ -794,14 +833,27 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
 #pragma unroll
                     for (int y = 0; y < 3; ++y) {
                         wr[(0 + y) * 32] = Qv[2][y];
-                        wr[(3 + y) * 32] = Qv[0][y];
-                        wr[(6 + y) * 32] = Lv[2][y];
-                        wr[(9 + y) * 32] = Lv[0][y];
+                        wr[(3 + y) * 32] = Lv[2][y];
+                        if (!SELFREG) wr[(9 + y) * 32] = Lv[0][y];
                     }
+                    wr[6 * 32] = Qv[0][1];
+                    wr[7 * 32] = Qv[0][2];
+                    if (!SELFREG) wr[8 * 32] = Qv[0][0];
                     sts128o_if<0>(xso_b + wslot * XSLOTB, hQ10[0], Lv[1][0], Lv[1][1], Lv[1][2], lastrow);
                     sts64o_if<XA * 4>(xso_b - 8 * c + wslot * XSLOTB, hQ10[2], Qv[1][1], lastrow);
                 }
                 // history shift
+                if (SELFREG) {
+#pragma unroll
+                    for (int k = 0; k + 1 < P; ++k) dQ[k] = dQ[k + 1];
+                    dQ[P - 1] = Qv[0][0];
+#pragma unroll
+                    for (int y = 0; y < 3; ++y) {
+#pragma unroll
+                        for (int k = 0; k + 2 < P; ++k) dL[y][k] = dL[y][k + 1];
+                        dL[y][P - 2] = Lv[0][y];
+                    }
+                }
                 h3Q1011 = h2Q1011;
                 h2Q1011 = hQ10[2]; h2Q1010 = hQ10[1]; h2Q1001 = hQ10[0];
 #pragma unroll
@@ -888,8 +940,8 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
             if (has_out) {  // last iteration's record, then make the stream visible to the next pass
                 for (int e = tid; e < REAL; e += blockDim.x) {
                     const int v = e / LPR, cs = e - v * LPR;
-                    const int val = (v < NV) ? ring[(G * RING + wslot) * RSLOT + v * 32 + (R - 1) * LPR + cs]
-                                             : xs[(G * RING + wslot) * XSLOT + (e - NV * LPR < 4 * LPR ? e - NV * LPR : XA + e - NV * LPR - 4 * LPR)];
+                    const int val = (v < NVR) ? ring[(G * RING + wslot) * RSLOT + v * 32 + (R - 1) * LPR + cs]
+                                              : xs[(G * RING + wslot) * XSLOT + (e - NVR * LPR < 4 * LPR ? e - NVR * LPR : XA + e - NVR * LPR - 4 * LPR)];
                     bnd_out[(size_t)(nit + PRE) * REC + e] = val;
                 }
                 __threadfence();

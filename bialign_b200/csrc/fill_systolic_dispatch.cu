@@ -24,7 +24,7 @@ SysGeo sys_geo(int S, bool pad) {
     g.P = pad ? 2 * S + 2 : (S == 0 ? 2 : 2 * S + 1);
     g.R = 32 / g.LPR;
     g.RING = g.P + 3;
-    g.REC = (18 * g.LPR + 3) & ~3;
+    g.REC = (12 * g.LPR + 3) & ~3;  // six ring values + six exchange values per lane of the row
     return g;
 }
 

@@ -55,6 +55,7 @@ struct TraceArgs {
     const uint64_t* codes;
     int fmt;                  // 0: nibble t = case id (generic kernel); 1: 5-bit tie fields (systolic kernel);
                               // 2: non-affine model, low nibble = case index 0..12
+                              // 3: non-affine model, dedicated kernel: uint32 per (row, j, b), nibble a+S = case index
     int sysG;                 // > 0: the table has the systolic kernel's layout (sys_code_index) with sysG warps per CTA
     int R, LPR, P, RING;      //      and this geometry
     const uint8_t* start_state;
@@ -90,6 +91,24 @@ int sys_bpad(int S, bool pad, int G, int mmax);
 cudaError_t launch_fill_systolic(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, bool bneg, cudaStream_t st);
 int sys_occupancy_na(int S, bool trace, bool pad, int G, size_t smem);
 cudaError_t launch_fill_systolic_na(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, cudaStream_t st);
+// Dedicated non-affine kernel (fill_na.cu): a lane owns a row and all its band offsets; max_shift <= BA_NA_MAX_SHIFT.
+constexpr int BA_NA_MAX_SHIFT = 3;
+int na_iters(int S, int G, int m);
+int na_pre(int S);
+int na_boff(int S, int G);
+int na_bpad(int S, int G, int mmax);
+size_t na_boundary_ints(int S, int G, int mmax);
+long long na_code_words(int S, int G, int n, int m);
+size_t na_smem_bytes(int S, int G, int nsym, int mmax);
+int na_occupancy(int S, bool trace, int G, size_t smem);
+cudaError_t launch_fill_na(const SysArgs& A, int grid, int G, size_t smem, bool trace, cudaStream_t st);
+// uint32 index of the code word holding cell (i, j, *, b) in that kernel's table (nibble a+S inside it)
+__host__ __device__ __forceinline__ long long na_code_index(int S, int G, int nit_all, int i, int j, int b) {
+    const int P = 2 * S + 1 < 2 ? 2 : 2 * S + 1, RT = G * 32;
+    const int pass = i / RT, rr = i - pass * RT, g = rr >> 5, lane = rr & 31;
+    const int qq = j * P + (b + S) + rr + P + 1 /* PRE */;
+    return (((long long)pass * G + g) * nit_all + qq) * 32 + lane;
+}
 int sys_occupancy_long(int S, bool trace, bool pad, int G, size_t smem);
 cudaError_t launch_fill_systolic_long(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, cudaStream_t st);
 

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(128) traceback_kernel(TraceArgs A) {
     const int s = A.s, n = d.n, m = d.m;
     // iterations per row block in the systolic kernel's table (fill_systolic.cuh: nit + PRE)
     const int nit_all = A.sysG ? (m + 1) * A.P + 2 * (A.sysG * A.R - 1) + A.LPR + A.RING + 4 : 0;
+    const int nit_na = A.fmt == 3 ? (m + 1) * (2 * s + 1 < 2 ? 2 : 2 * s + 1) + A.sysG * 32 + (2 * s + 1 < 2 ? 2 : 2 * s + 1) + 1 : 0;
     int i = n, j = m, k = n, l = m;
     int state = A.start_state[d.orig];
     uint8_t* out = A.trace + d.trace_off + d.trace_cap;  // one past the end of the slot
@@ -31,6 +32,17 @@ __global__ void __launch_bounds__(128) traceback_kernel(TraceArgs A) {
             break;
         }
         first = false;
+        if (A.fmt == 3) {  // dedicated non-affine kernel: one nibble per cell, walk ends at the first cell without a case
+            const uint32_t w32 = __ldg(reinterpret_cast<const uint32_t*>(codes) + na_code_index(s, A.sysG, nit_na, i, j, l - j));
+            const int cidx = (int)((w32 >> (4 * (k - i + s))) & 15);
+            if (cidx > 12) { ok = 1; break; }
+            const int xbn = NA_XBITS_TB[cidx];
+            *--out = (uint8_t)xbn;
+            ++len;
+            i -= (xbn >> 3) & 1; j -= (xbn >> 2) & 1; k -= (xbn >> 1) & 1; l -= xbn & 1;
+            if ((i | j | k | l) < 0 || abs(k - i) > s || abs(l - j) > s) { ok = 0; break; }
+            continue;
+        }
         const uint64_t wd = __ldg(codes + (A.sysG ? sys_code_index(A.R, A.LPR, A.P, s, A.sysG, nit_all, i, j, k - i, l - j)
                                                   : code_index(m, s, i, j, k - i, l - j)));
         int id;

@@ -47,20 +47,26 @@ def read_simmatrix(filename, scale=100):
         rows = blosum62_rows()
         return {a: {b: scale * rows[i][j] for j, b in enumerate(ALPHABET)} for i, a in enumerate(ALPHABET)}
     with open(filename, "r") as fh:
-        lines = fh.readlines()
-    keys, keys2, matrix = None, [], {}
-    for i, line in enumerate(lines):
-        if keys and i > len(keys):
+        return _parse_matrix_text(fh, scale)
+
+
+def _parse_matrix_text(lines, scale):
+    """Single pass over the text of a matrix file.  The header (first field '-') names the columns and fixes how many
+    lines can belong to the table: with c columns nothing beyond line index c is looked at.  Every other line is a row:
+    its symbol, then the values of the columns in header order (a short row simply defines fewer entries)."""
+    columns, row_order, table, last = None, [], {}, None
+    for index, text in enumerate(lines):
+        if last is not None and index > last:
             break
-        f = line.split()
-        if f[0] == "-":
-            keys = f[1:]
-        else:
-            keys2.append(f[0])
-            matrix[f[0]] = {k: scale * int(v) for k, v in zip(keys, f[1:])}
-    if keys != keys2:
-        print("ERROR while reading simmatrix {filename}.")  # sic: the reference prints this literally
-    return matrix
+        symbol, *values = text.split()
+        if symbol == "-":
+            columns, last = values, (len(values) or None)
+            continue
+        row_order.append(symbol)
+        table[symbol] = dict(zip(columns, (scale * int(v) for v in values)))
+    if columns != row_order:
+        print("ERROR while reading simmatrix {filename}.")  # the reference prints exactly this (no interpolation)
+    return table
 
 
 def simmatrix_table(matrix):

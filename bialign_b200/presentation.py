@@ -26,16 +26,10 @@ def highlight_sequence_identity(alistrA, alistrB):
 
 
 def parse_dotbracket(dbstr):
-    """0-based partner of every position, -1 for unpaired (pyx:911-922)."""
-    res = [-1] * len(dbstr)
-    stack = []
-    for i, sym in enumerate(dbstr):
-        if sym == "(":
-            stack.append(i)
-        elif sym == ")":
-            j = stack.pop()
-            res[i], res[j] = j, i
-    return res
+    """0-based partner of every position, -1 for unpaired (behaviour of pyx:911-922; IndexError on an unbalanced ')')."""
+    from .encoding import dotbracket_partners
+
+    return [int(p) - 1 for p in dotbracket_partners(dbstr)[1:]]
 
 
 def consensus_sbpp(alistrA, sbppA, alistrB, sbppB):
@@ -57,49 +51,48 @@ def consensus_sbpp(alistrA, sbppA, alistrB, sbppB):
 
 
 def mea(sbpp, gamma=3, *, brackets="()"):
-    """Maximum-expected-accuracy structure of a symmetric pair matrix with unpaired weights on the
-    diagonal; returns (structure string, score).  Same recursion, candidate lists, strict-improvement
-    updates and traceback order as pyx:836-886, so the emitted structure is identical -- including
-    that reference's quirks (e.g. candidates are only recorded when they strictly improve F)."""
+    """Maximum-expected-accuracy structure of a symmetric pair matrix with unpaired weights on the diagonal; returns
+    (structure string, score).  Spec (pyx:836-886): F[i][j] = best over "j unpaired" (weight sbpp[j][j]) and "j pairs
+    with k" (k < j - 3, weight 2*gamma*sbpp[k][j]) of F[i][k-1] + F[k+1][j-1] + weight, where only pairs (k, j) that
+    strictly beat every alternative for the interval [k, j] are ever considered, ties go to "j unpaired" and then to the
+    largest k, and an interval whose best value is 0 stays open.  Implementation: per end position j the admissible
+    splits are kept as two growing arrays (k and the value of closing at k), so one interval is a single vectorised
+    max over them; the structure is then read off the argmax table interval by interval."""
+    sbpp = np.asarray(sbpp, dtype=float)
     n = len(sbpp) - 1
     F = np.zeros((n + 2, n + 2), dtype=float)
-    T = np.zeros((n + 2, n + 2), dtype=int)
-    cands = [[] for _ in range(n + 1)]
+    arg = np.zeros((n + 2, n + 2), dtype=np.int64)      # 0 = nothing gained on this interval
+    split_at = [np.empty(0, dtype=np.int64) for _ in range(n + 1)]
+    split_val = [np.empty(0, dtype=float) for _ in range(n + 1)]
     for i in range(n, 0, -1):
-        cands[i].append((i, sbpp[i, i]))
+        split_at[i] = np.append(split_at[i], i)          # "i unpaired" is always admissible for intervals ending at i
+        split_val[i] = np.append(split_val[i], sbpp[i, i])
         for j in range(i, n + 1):
-            best, arg = F[i, j], T[i, j]
-            for k, C in cands[j]:
-                v = F[i, k - 1] + C
-                if best < v:
-                    best, arg = v, k
-            F[i, j], T[i, j] = best, arg
-            if i + 3 >= j:
-                continue
-            C = F[i + 1, j - 1] + 2 * gamma * sbpp[i, j]
-            if C > F[i, j]:
-                cands[j].append((i, C))
-                F[i, j] = C
-                T[i, j] = i
-    structure = ["."] * (n + 1)
-    stack = [(1, n)]
-    while stack:
-        i, j = stack.pop()
-        if i > n or j < 1:
+            totals = F[i, split_at[j] - 1] + split_val[j]
+            w = int(np.argmax(totals))                   # first maximum = order of admission: j itself, then larger k first
+            if totals[w] > 0.0:
+                F[i, j], arg[i, j] = totals[w], split_at[j][w]
+            if j - i > 3:
+                closed = F[i + 1, j - 1] + 2 * gamma * sbpp[i, j]
+                if closed > F[i, j]:                     # (i, j) strictly better than anything else: admit it for rows above
+                    split_at[j] = np.append(split_at[j], i)
+                    split_val[j] = np.append(split_val[j], closed)
+                    F[i, j], arg[i, j] = closed, i
+    opening, closing = brackets[0], brackets[1]
+    out = ["."] * (n + 1)
+    todo = [(1, n)] if n >= 1 else []
+    while todo:
+        i, j = todo.pop()
+        while j - i > 3 and arg[i, j] == j:               # trailing unpaired positions
+            j -= 1
+        k = int(arg[i, j]) if j - i > 3 else 0
+        if k == 0:
             continue
-        k = T[i, j]
-        if i + 3 >= j or k == 0:
-            continue
-        if k == j:
-            stack.append((i, j - 1))
-        elif k == i:
-            structure[k], structure[j] = brackets[0], brackets[1]
-            stack.append((k + 1, j - 1))
-        else:
-            stack.append((i, k - 1))
-            stack.append((k + 1, j - 1))
-            structure[k], structure[j] = brackets[0], brackets[1]
-    return "".join(structure[1:]), (F[1, n] if n >= 1 else 0.0)
+        out[k], out[j] = opening, closing
+        todo.append((k + 1, j - 1))
+        if k > i:
+            todo.append((i, k - 1))
+    return "".join(out[1:]), (F[1, n] if n >= 1 else 0.0)
 
 
 def read_molecule(content, type):

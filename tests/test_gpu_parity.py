@@ -535,3 +535,50 @@ def test_many_waves_with_a_tiny_code_arena():
         ia, ib = pairs[q]
         r = oracle.run(seqs[ia], seqs[ib], structs[ia], structs[ib], params, mode="codes")
         assert int(ref_scores[q]) == r["score"] and trace_hex(ref_cols, ref_off, q) == r["trace"]
+
+
+def test_fuzz_slice_vs_literal_oracle():
+    """100 rounds of scripts/fuzz_parity.py (random parameters incl. zero / positive costs, RNA and protein, max_shift 0..4,
+    every kernel / flavour / CTA width / long-pair mode) against the oracle's literal int64 restatement."""
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(root, "scripts", "fuzz_parity.py"))
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    bad, checked = fz.fuzz(seed=20261018, rounds=100, verbose=False)
+    assert checked > 200 and bad == 0
+
+
+def test_very_long_molecule_b_falls_back_instead_of_narrowing_the_cta():
+    """Molecule B is staged in shared memory by the systolic kernel; when it no longer fits next to the rings at the minimum
+    CTA width (one boundary-record element per thread) the engine must take the general level kernel -- never a narrower
+    CTA, which would drop boundary elements between the row blocks of a multi-pass pair."""
+    rng = np.random.default_rng(5)
+    aa = "ARNDCQEGHILKMFPSTWYV"
+    params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150, gap_cost=-50,
+                  shift_cost=-150, max_shift=1)
+    seqs, structs = [], []
+    for L in (150, 78000):  # 150 rows = several row blocks at any CTA width
+        seqs.append("".join(aa[i] for i in rng.integers(0, 20, L)))
+        structs.append("".join("HEC"[i] for i in rng.integers(0, 3, L)))
+    from bialign_b200.batch import BatchAligner
+
+    al = BatchAligner(**params)
+    s_auto, cols, offsets, complete = al.align(seqs, structs, [(0, 1)], want_trace=True)
+    kind_auto = al.engine.stats()["kernel_kind"]
+    t_auto = trace_hex_(cols, offsets, 0)
+    al.set_option("kernel", 0)
+    s_gen, cols, offsets, _ = al.align(seqs, structs, [(0, 1)], want_trace=True)
+    assert al.engine.stats()["kernel_kind"] == 0
+    assert int(s_auto[0]) == int(s_gen[0]) and t_auto == trace_hex_(cols, offsets, 0) and bool(complete[0])
+    v, end = oracle.eval_trace(seqs[0], seqs[1], structs[0], structs[1], params, t_auto)
+    assert v == int(s_auto[0]) and end == [150, 78000, 150, 78000]
+    assert kind_auto in (0, 1, 2, 3, 4)
+
+
+def trace_hex_(cols, offsets, p):
+    from bialign_b200.batch import trace_hex
+
+    return trace_hex(cols, offsets, p)

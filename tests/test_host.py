@@ -239,8 +239,11 @@ def test_bench_reference_arm_contract():
     cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
            "--pairs-per-gpu", "64"]
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
-    other = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    other = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, env=env, timeout=300)
     assert other.returncode == 0 and other.stdout.strip() == ""
+    # the GPU count on the command line must agree with the launcher's world size
+    bad = subprocess.run(cmd + ["--gpus", "4"], capture_output=True, text=True, env=env, timeout=300)
+    assert bad.returncode != 0 and "WORLD_SIZE" in bad.stderr
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-400:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
@@ -250,3 +253,55 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["value"] == line["value"] and "sample" in line["cpu_baseline"]
     assert line["e2e"] == {"value": line["value"], "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"].startswith("cfg3") and line["vs_baseline"] is None
+    assert line["config"]["reference_sample"]["pairs"] >= 1  # the bounded CPU sample is declared in the arm's own config
+
+
+def _write_matrix(path, symbols, rows, trailer=()):
+    with open(path, "w") as fh:
+        fh.write("-  " + "  ".join(symbols) + "\n")
+        for s, r in zip(symbols, rows):
+            fh.write(s + " " + " ".join("%2d" % v for v in r) + " \n")
+        for t in trailer:
+            fh.write(t + "\n")
+
+
+def test_read_simmatrix_file_format(tmp_path, capsys):
+    """File branch of read_simmatrix (nonpyx:33-58): header row starting with '-', one row per symbol, entries x 100,
+    anything after the last row ignored; a row/column order mismatch prints the reference's (literal) error line."""
+    from bialign_b200 import encoding
+
+    builtin = encoding.read_simmatrix("BLOSUM62")
+    syms = list(encoding.ALPHABET)
+    f = tmp_path / "b62.txt"
+    _write_matrix(f, syms, encoding.blosum62_rows(), trailer=["this line and the next are never parsed", "X Y Z"])
+    assert encoding.read_simmatrix(str(f)) == builtin
+    assert encoding.read_simmatrix(str(f), scale=1)["W"]["W"] == 11
+    assert capsys.readouterr().out == ""
+    ref_file = "/root/reference/Data/BLOSUM62.txt"
+    if os.path.exists(ref_file):  # build container only: the reference's own data file holds the same numbers
+        assert encoding.read_simmatrix(ref_file) == builtin
+    g = tmp_path / "swapped.txt"
+    _write_matrix(g, ["A", "C"], [[1, 2], [3, 4]])
+    text = open(g).read().replace("\nA ", "\nQ ", 1)
+    open(g, "w").write(text)
+    m = encoding.read_simmatrix(str(g))
+    assert m == {"Q": {"A": 100, "C": 200}, "C": {"A": 300, "C": 400}}
+    assert capsys.readouterr().out == "ERROR while reading simmatrix {filename}.\n"
+
+
+def test_batch_aligner_rejects_unknown_arguments_and_undefined_matrix_entries(tmp_path):
+    """A misspelled scoring argument must not silently run with defaults, and a residue pair the matrix does not define
+    raises KeyError like the reference's dict lookup (pyx:407) instead of scoring 0."""
+    from bialign_b200.batch import BatchAligner
+
+    with pytest.raises(TypeError):
+        BatchAligner(type="Protein", simmatrix="BLOSUM62", gap_costs=-50)
+    f = tmp_path / "holes.txt"
+    with open(f, "w") as fh:  # three columns, and the row of C is short: (C, D) is undefined
+        fh.write("- A C D\nA 4 0 1\nC 0 9\nD 1 2 6\n")
+    al = BatchAligner(type="Protein", simmatrix=str(f), gap_opening_cost=-10)
+    assert al.known is not None and not al.known.all()
+    res, cls, off = al.encode(["ADA", "AAD", "CC"], ["HHH", "HHH", "HH"])
+    al.check_known(res, off, [0], [1])  # A/D rows against A/D columns: all defined
+    with pytest.raises(KeyError):
+        al.check_known(res, off, [2], [1])  # C against D
