@@ -102,11 +102,12 @@ struct ba_engine {
     DevBuf<unsigned long long> d_progress;
     int opt_long = -1;                 // multi-CTA long-pair mode: -1 auto, 0 off, 1 force
     int opt_p16 = -1;                  // 16-bit pair mode for score-only batches: -1 auto, 0 off, 1 force
+    int opt_na = -1;                   // non-affine model: -1 / 1 dedicated kernel when applicable, 0 systolic NA flavour
     std::vector<int32_t> h_sim;
     int opt_warps = 0;                 // warps per CTA of the systolic kernel (0 = chosen per batch)
     int opt_pad = -1;                  // systolic flavour: -1 auto, 0 pad-free, 1 padded
     int last_fmt = 0, last_sysG = 0;   // code-table layout of the last run (debug fetch)
-    bool last_pad = false;
+    bool last_pad = false, last_na = false;
     DevBuf<long long> d_scores;
     DevBuf<uint8_t> d_start, d_complete, d_trace;
     DevBuf<int> d_endv, d_tlen;
@@ -327,6 +328,7 @@ int ba_set_option(ba_engine* e, const char* key, int64_t value) {
     else if (!strcmp(key, "pad")) return tri(&e->opt_pad);
     else if (!strcmp(key, "long")) return tri(&e->opt_long);
     else if (!strcmp(key, "p16")) return tri(&e->opt_p16);
+    else if (!strcmp(key, "na_kernel")) return tri(&e->opt_na);
     else if (!strcmp(key, "warps_per_cta")) {
         if (value < 0 || value > 8) return fail(e, BA_ERR_INVALID_ARG, "warps_per_cta must be in 0..8 (0 = auto)");
         e->opt_warps = (int)value;
@@ -483,17 +485,42 @@ int ba_run(ba_engine* e, int want_trace) {
     if (e->opt_kernel == 1 && !plan.ok)
         return fail(e, BA_ERR_SCORE_RANGE, "systolic kernel requested but its packed-integer range conditions do not hold");
     int kernel = plan.ok ? 1 : 0;
+    // non-affine model: the dedicated row-per-lane kernel (fill_na.cu) when the pad-free range conditions hold
+    bool na_ded = kernel == 1 && !affine && !plan.pad && s <= BA_NA_MAX_SHIFT && e->opt_na != 0;
+    if (e->opt_na == 1 && !affine && !na_ded && e->opt_kernel != 0)
+        return fail(e, BA_ERR_SCORE_RANGE, "dedicated non-affine kernel requested but not applicable (range or max_shift)");
     int max_grid = e->sm_count * 2;
     size_t scratch_stride = 0, sys_smem = 0;
     int sysG = e->opt_warps;
     SysArgs SA{};
     bool long_mode = false;
     int long_grid_max = 0, sys_occ = 0;
-    if (kernel == 1) {
+    if (na_ded) {
+        // CTA width: a row block is 32 rows per warp and lags 32 iterations per warp; estimate warp-iterations per pair
+        if (sysG == 0) {
+            double best = 0;
+            for (int G = 1; G <= 8; ++G) {
+                const size_t sm = na_smem_bytes(s, G, e->sc.nsym, mmax);
+                if (sm > kSysSmemLimit) continue;
+                const int occ = na_occupancy(s, want_trace != 0, G, sm);
+                if (occ < 1) continue;
+                double cost = 0;
+                const int64_t stride = std::max<int64_t>(1, N / 4096);
+                for (int64_t p = 0; p < N; p += stride) cost += (double)((ln[p] + 32 * G) / (32 * G)) * (na_iters(s, G, lm[p]) + na_pre(s)) * G;
+                cost /= std::min(occ * G, 16);
+                if (sysG == 0 || cost < best * 0.97) { best = cost; sysG = G; }
+            }
+            if (sysG == 0) sysG = 1;
+        }
+        sys_smem = na_smem_bytes(s, sysG, e->sc.nsym, mmax);
+        sys_occ = sys_smem > kSysSmemLimit ? 0 : na_occupancy(s, want_trace != 0, sysG, sys_smem);
+        if (sys_occ < 1) na_ded = false, sysG = e->opt_warps;  // molecule B too long for shared memory: systolic flavour / level kernel below
+    }
+    if (kernel == 1 && !na_ded) {
         if (sysG == 0) {
             // Pick the CTA width that minimises the estimated warp-iterations per resident warp:
-            // a pair costs passes(G) * iterations(G) on G warps; an SM runs occ(G) CTAs, and more than ~12
-            // resident warps do not add throughput (the ALU pipe is saturated).  Short pairs want a CTA that
+            // a pair costs passes(G) * iterations(G) on G warps; an SM runs occ(G) CTAs, and more than ~16
+            // resident warps do not add throughput.  Short pairs want a CTA that
             // covers all rows in one pass; long ones want few warps per CTA and several CTAs per SM.
             const SysGeo geo = sys_geo(s, plan.pad);
             double best = 0;
@@ -504,7 +531,7 @@ int ba_run(ba_engine* e, int want_trace) {
                                     : !affine ? sys_occupancy_na(s, want_trace != 0, plan.pad, G, sm)
                                               : sys_occupancy(s, want_trace != 0, plan.pad, plan.bneg, G, sm);
                 if (occ < 1) continue;
-                const double eff = std::min(occ * G, 12);
+                const double eff = std::min(occ * G, 16);
                 double cost = 0;
                 const int64_t stride = std::max<int64_t>(1, N / 4096);  // sample large batches
                 for (int64_t p = 0; p < N; p += stride) {
@@ -544,6 +571,7 @@ int ba_run(ba_engine* e, int want_trace) {
     // also holds the skewed pipeline's idle slots (about 10-15 % more memory, 15x fewer store transactions).
     auto pair_code_words = [&](int n, int m) -> int64_t {
         if (kernel != 1) return code_words(n, m, s);
+        if (na_ded) return na_code_words(s, sysG, n, m);
         return sys_code_words(s, plan.pad, sysG, n, m);
     };
     // code arena
@@ -634,7 +662,26 @@ int ba_run(ba_engine* e, int want_trace) {
     lap("result buffers");
     int64_t biggest_wave = 0;
     for (int w = 0; w < n_waves; ++w) biggest_wave = std::max(biggest_wave, wave_begin[w + 1] - wave_begin[w]);
-    if (kernel == 1) {
+    if (na_ded) {
+        max_grid = e->sm_count * sys_occ;
+        const int grid = (int)std::min<int64_t>(biggest_wave, max_grid);
+        CU(e->d_simp.ensure(plan.sim_p.size()));
+        CU(cudaMemcpyAsync(e->d_simp.p, plan.sim_p.data(), plan.sim_p.size() * 4, cudaMemcpyHostToDevice, e->stream));
+        if (nmax + 1 > sysG * 32) {  // pairs with several row blocks hand a boundary stream from block to block
+            cudaError_t ce = e->d_bnd.ensure((size_t)grid * 2 * na_boundary_ints(s, sysG, mmax));
+            if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "boundary streams: " + std::string(cudaGetErrorString(ce)));
+        }
+        const int64_t sh = (int64_t)1 << plan.tb;
+        SA.res = e->d_res.p; SA.cls = e->d_cls.p; SA.sim_p = e->d_simp.p; SA.sc = e->sc;
+        SA.w_p = (int)(e->sc.w / plan.g * sh);
+        SA.k_gd = (int)((e->sc.gamma + e->sc.delta) / plan.g * sh); SA.k_2g = (int)(2 * e->sc.gamma / plan.g * sh);
+        SA.k_d = (int)(e->sc.delta / plan.g * sh);
+        SA.negp = plan.negp; SA.tb_bits = plan.tb; SA.gscale = plan.g; SA.mmax = mmax;
+        SA.boff = na_boff(s, sysG); SA.bpad = na_bpad(s, sysG, mmax);
+        SA.bnd = e->d_bnd.p; SA.bnd_iters = (int)(na_boundary_ints(s, sysG, mmax) / 8);
+        SA.codes = want_trace ? e->d_codes.p : nullptr;
+        SA.scores = e->d_scores.p; SA.start_state = e->d_start.p; SA.end_values = e->d_endv.p;
+    } else if (kernel == 1) {
         max_grid = e->sm_count * sys_occ;
         const int grid = (int)std::min<int64_t>(biggest_wave, max_grid);
         const int rows_pass = sysG * sys_geo(s, plan.pad).R;
@@ -678,6 +725,13 @@ int ba_run(ba_engine* e, int want_trace) {
         SA.negp = plan.negp; SA.tb_bits = plan.tb; SA.gscale = plan.g; SA.mmax = mmax;
         SA.boff = sys_boff(s, plan.pad, sysG); SA.bpad = sys_bpad(s, plan.pad, sysG, mmax);
         SA.progress = e->d_progress.p;
+        {   // Flag period of the long-pair pipeline.  Many row blocks (a CTA per block, several per SM): a flag exchange costs an
+            // extra barrier and a spinning thread, so it is rare (default, ~32 iterations).  Few row blocks (one CTA per SM, the pair is
+            // latency-bound): every row block starts one flag period later than it could, so the period is one ring period.
+            const SysGeo geo = sys_geo(s, plan.pad);
+            const char* ov = getenv("BA_LONG_LQ");
+            SA.lq_iters = ov ? std::max(1, atoi(ov)) * geo.RING : (long_mode && npass_max <= e->sm_count ? geo.RING : 0);
+        }
         SA.bnd = e->d_bnd.p; SA.bnd_iters = biters + 8;  // matches sys_boundary_ints: slack records in front
         SA.codes = want_trace ? e->d_codes.p : nullptr;
         SA.scores = e->d_scores.p; SA.start_state = e->d_start.p; SA.end_values = e->d_endv.p;
@@ -727,6 +781,9 @@ int ba_run(ba_engine* e, int want_trace) {
         } else if (kernel == 1 && p16) {  // two pairs per work item (score only: a single wave)
             SA.pairs = e->d_desc.p; SA.npairs = (int)((N + 1) / 2); SA.counter = e->d_counter.p + w;
             CU(launch_fill_systolic_p16(SA, (int)std::min<int64_t>((N + 1) / 2, max_grid), sysG, sys_smem, e->stream));
+        } else if (na_ded) {
+            SA.pairs = e->d_desc.p + b; SA.npairs = (int)cnt; SA.counter = e->d_counter.p + w;
+            CU(launch_fill_na(SA, grid, sysG, sys_smem, want_trace != 0, e->stream));
         } else if (kernel == 1 && !affine) {
             SA.pairs = e->d_desc.p + b; SA.npairs = (int)cnt; SA.counter = e->d_counter.p + w;
             CU(launch_fill_systolic_na(SA, grid, sysG, sys_smem, want_trace != 0, plan.pad, e->stream));
@@ -745,7 +802,9 @@ int ba_run(ba_engine* e, int want_trace) {
             TraceArgs T{};
             T.pairs = e->d_desc.p + b; T.npairs = (int)cnt; T.s = s; T.codes = e->d_codes.p; T.fmt = affine ? kernel : 2;
             T.start_state = e->d_start.p; T.trace = e->d_trace.p; T.trace_len = e->d_tlen.p; T.complete = e->d_complete.p;
-            if (kernel == 1) {
+            if (na_ded) {
+                T.fmt = 3; T.sysG = sysG;
+            } else if (kernel == 1) {
                 const SysGeo geo = sys_geo(s, plan.pad);
                 T.sysG = sysG; T.R = geo.R; T.LPR = geo.LPR; T.P = geo.P; T.RING = geo.RING;
             }
@@ -778,10 +837,11 @@ int ba_run(ba_engine* e, int want_trace) {
         e->stats.code_bytes = cb;
     }
     e->stats.waves = n_waves;
-    e->stats.kernel_kind = kernel == 0 ? 0 : (p16 ? 5 : !affine ? (plan.pad ? 7 : 6) : (plan.pad ? 2 : 1) + (long_mode ? 2 : 0));
+    e->stats.kernel_kind = kernel == 0 ? 0 : na_ded ? 8 : (p16 ? 5 : !affine ? (plan.pad ? 7 : 6) : (plan.pad ? 2 : 1) + (long_mode ? 2 : 0));
     e->stats.warps_per_cta = kernel == 0 ? 0 : sysG;
     e->last_fmt = kernel;
     e->last_sysG = kernel == 1 ? sysG : 0;
+    e->last_na = na_ded;
     e->last_pad = kernel == 1 && plan.pad;
     e->ran = true;
     e->ran_trace = want_trace != 0;
@@ -902,6 +962,20 @@ int ba_debug_fetch_codes(ba_engine* e, int64_t pair, uint64_t* out, int64_t word
     if (e->last_sysG == 0) {
         CU(cudaMemcpyAsync(out, e->d_codes.p + e->h_last_code_off[pair], (size_t)need * 8, cudaMemcpyDeviceToHost, e->stream));
         CU(cudaStreamSynchronize(e->stream));
+        return BA_OK;
+    }
+    if (e->last_na) {  // dedicated non-affine kernel: a nibble per cell -> the cell-major table, case index in the low nibble
+        const int G = e->last_sysG, nit_all = na_iters(S, G, m) + na_pre(S);
+        const int64_t raw = na_code_words(S, G, n, m);
+        std::vector<uint64_t> tmp((size_t)raw);
+        CU(cudaMemcpyAsync(tmp.data(), e->d_codes.p + e->h_last_code_off[pair], (size_t)raw * 8, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(tmp.data());
+        for (int i = 0; i <= n; ++i)
+            for (int a = -S; a <= S; ++a)
+                for (int j = 0; j <= m; ++j)
+                    for (int b = -S; b <= S; ++b)
+                        out[code_index(m, S, i, j, a, b)] = (w32[na_code_index(S, G, nit_all, i, j, b)] >> (4 * (a + S))) & 15;
         return BA_OK;
     }
     // systolic layout -> the cell-major table this hook promises (cells the kernel never visits read as all-ones)

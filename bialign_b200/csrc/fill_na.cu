@@ -31,7 +31,8 @@ struct Geo {
     static constexpr int W = 2 * S + 1;
     static constexpr int P = W < 2 ? 2 : W;   // S = 0 keeps one pad cell per column so that D(0100) = P-1 >= 1
     static constexpr int NH = P + 1;          // own history depth (iterations)
-    static constexpr int RING = P + 3;        // exchange-block depth: reads reach back P+1 iterations, +1 write slot, +1 slack
+    static constexpr int RING = 2 * NH;       // exchange-block depth: two history periods (reads reach back P+1 = NH iterations),
+                                              // so a steady block that starts on a half boundary has compile-time slots
     static constexpr int XW = 8;              // ints per exchange record (W <= 7 values)
     static constexpr int PRE = P + 1;         // iterations run before position 0 so that the staged row above is primed
     static constexpr int LA = 8;              // cp.async look-ahead of the boundary staging (iterations)
@@ -41,8 +42,42 @@ struct Geo {
 __device__ __forceinline__ int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); }
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+template <bool V> struct BC_ { static constexpr bool value = V; };
+template <int V> struct IC_ { static constexpr int value = V; };
+template <class F, int... U>
+__device__ __forceinline__ void steady_block(F& f, const int q, std::integer_sequence<int, U...>) {
+    ((f(BC_<true>{}, IC_<U>{}, q + U), __syncthreads()), ...);
+}
+// One exchange record (8 ints, W of them used): predicated loads into / stores from exactly W registers
+template <int W>
+__device__ __forceinline__ void lds_rec(int (&v)[W], unsigned addr, bool c) {
+    static_assert(W == 1 || W == 3 || W == 5 || W == 7, "odd band widths only");
+    if constexpr (W == 1)
+        asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %2, 0;\n @pp ld.shared.s32 %0, [%1];\n}\n" : "+r"(v[0]) : "r"(addr), "r"((int)c) : "memory");
+    else if constexpr (W == 3)
+        asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %4, 0;\n @pp ld.shared.v2.s32 {%0, %1}, [%3];\n @pp ld.shared.s32 %2, [%3+8];\n}\n"
+                     : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]) : "r"(addr), "r"((int)c) : "memory");
+    else if constexpr (W == 5)
+        asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %6, 0;\n @pp ld.shared.v4.s32 {%0, %1, %2, %3}, [%5];\n @pp ld.shared.s32 %4, [%5+16];\n}\n"
+                     : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]) : "r"(addr), "r"((int)c) : "memory");
+    else
+        asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %8, 0;\n @pp ld.shared.v4.s32 {%0, %1, %2, %3}, [%7];\n @pp ld.shared.v2.s32 {%4, %5}, [%7+16];\n @pp ld.shared.s32 %6, [%7+24];\n}\n"
+                     : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]) : "r"(addr), "r"((int)c) : "memory");
+}
+template <int W>
+__device__ __forceinline__ void sts_rec(unsigned addr, const int (&v)[W], bool c) {
+    if constexpr (W == 1)
+        asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %2, 0;\n @pp st.shared.s32 [%0], %1;\n}\n" ::"r"(addr), "r"(v[0]), "r"((int)c) : "memory");
+    else if constexpr (W == 3)
+        asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %4, 0;\n @pp st.shared.v2.s32 [%0], {%1, %2};\n @pp st.shared.s32 [%0+8], %3;\n}\n" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"((int)c) : "memory");
+    else if constexpr (W == 5)
+        asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %6, 0;\n @pp st.shared.v4.s32 [%0], {%1, %2, %3, %4};\n @pp st.shared.s32 [%0+16], %5;\n}\n" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"((int)c) : "memory");
+    else
+        asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %8, 0;\n @pp st.shared.v4.s32 [%0], {%1, %2, %3, %4};\n @pp st.shared.v2.s32 [%0+16], {%5, %6};\n @pp st.shared.s32 [%0+24], %7;\n}\n" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"((int)c) : "memory");
+}
+
 template <int S, bool TRACE>
-__global__ void __launch_bounds__(256) fill_na_kernel(SysArgs A) {
+__global__ void __launch_bounds__(256, 1) fill_na_kernel(SysArgs A) {
     using G_ = Geo<S>;
     constexpr int W = G_::W, P = G_::P, NH = G_::NH, RING = G_::RING, XW = G_::XW, PRE = G_::PRE, LA = G_::LA, PB = G_::PB;
     static_assert(W <= 7 && PRE <= PRE_MAX, "band too wide for this kernel");
@@ -63,6 +98,7 @@ __global__ void __launch_bounds__(256) fill_na_kernel(SysArgs A) {
     const int w_p = A.w_p, kG2 = A.k_2g, kGD = A.k_gd, kD = A.k_d;
     constexpr int T_ = TRACE ? 1 : 0;
 
+    const unsigned xin_b = smem_u32(xs + g * RING * XW), xout_b = smem_u32(xs + (g + 1) * RING * XW);
     for (int q = tid; q < (G + 1) * RING * XW + PB * XW; q += blockDim.x) smem[q] = NEGP;
     for (int q = tid; q < (nsym + 1) * nsym; q += blockDim.x) ssim[q] = (q < nsym * nsym) ? A.sim_p[q] : 0;
     __syncthreads();
@@ -137,22 +173,35 @@ __global__ void __launch_bounds__(256) fill_na_kernel(SysArgs A) {
             }
             __syncthreads();
 
-            for (int q = -PRE; q < nit; ++q) {
+            // Steady range of this warp [st_lo, st_hi): every lane has S < j <= m - max(S, 1) throughout (all column range
+            // tests true, no origin / end cell) and every staged record exists.
+            const int st_lo = (S + 1) * P + g * 32 + 31;
+            int st_hi = (m - (S > 0 ? S : 1) + 1) * P + g * 32;
+            if (has_in) st_hi = min(st_hi, nit - RT - LA);
+
+            // ---- one iteration: W cells of this lane's row.  ST: steady form (no column tests, no end / origin).
+            unsigned xin_cur = 0, xin_oth = 0, xout_cur = 0;  // steady blocks: the two halves of the exchange ring
+            bool half = false;
+            auto iteration = [&](auto st_, auto u_, const int q) __attribute__((always_inline)) {
+                constexpr bool ST = decltype(st_)::value;
+                constexpr int u = decltype(u_)::value;  // ST: position inside the block = slot inside the current half
                 ++bb;
                 if (bb == P) { bb = 0; ++j; }
-                slot = (slot + 1 == RING) ? 0 : slot + 1;
+                if (!ST) slot = (slot + 1 == RING) ? 0 : slot + 1;
                 const int l = j + bb - S;
-                const bool colok = (bb < W) && ((unsigned)j <= (unsigned)m) && ((unsigned)l <= (unsigned)m);
+                const bool colok = ST || ((bb < W) && ((unsigned)j <= (unsigned)m) && ((unsigned)l <= (unsigned)m));
                 if (bb == 0) mu1 = simrow[sresB[j + boff]];
                 const int cB = sclsB[l + boff];
 
                 // ---- flush the record of iteration q-1 (exchange block xs[G], written before the last barrier)
-                if (do_flush) {
-                    const int ps = (slot == 0) ? RING - 1 : slot - 1;
-                    bnd_out[(size_t)(q + PRE) * XW + io_e] = xs[(G * RING + ps) * XW + io_e];
+                {
+                    const int ps = ST ? ((half ? NH : 0) + u + RING - 1) % RING : ((slot == 0) ? RING - 1 : slot - 1);
+                    const int val = xs[(G * RING + ps) * XW + io_e];
+                    if (do_flush) bnd_out[(size_t)(q + PRE) * XW + io_e] = val;
                 }
 
-                // ---- the row above, 1, 2, P and P+1 iterations ago
+                // ---- the row above, 1, 2, P and P+1 iterations ago: shuffles; lane 0 reads the exchange block of the warp
+                // above (xs[0]: the staged boundary) with predicated vector loads that overwrite the shuffle results
                 int U1[W], U2[W], UP[W], UQ[W];
 #pragma unroll
                 for (int aa = 0; aa < W; ++aa) {
@@ -161,20 +210,22 @@ __global__ void __launch_bounds__(256) fill_na_kernel(SysArgs A) {
                     UP[aa] = __shfl_up_sync(0xffffffffu, h[P - 1][aa], 1);
                     UQ[aa] = __shfl_up_sync(0xffffffffu, h[P][aa], 1);
                 }
-                if (lane == 0) {  // from the exchange block of the warp above (xs[0]: the staged boundary)
+                if constexpr (ST) {
+                    // slot u of the current half; d iterations back: the same half when u >= d, else the other one
+                    lds_rec<W>(U1, (u >= 1 ? xin_cur : xin_oth) + ((u - 1 + NH) % NH) * (XW * 4), lane == 0);
+                    lds_rec<W>(U2, (u >= 2 ? xin_cur : xin_oth) + ((u - 2 + NH) % NH) * (XW * 4), lane == 0);
+                    lds_rec<W>(UP, (u >= P ? xin_cur : xin_oth) + ((u - P + NH) % NH) * (XW * 4), lane == 0);
+                    lds_rec<W>(UQ, xin_oth + u * (XW * 4), lane == 0);
+                } else {
                     int s1 = slot - 1, s2 = slot - 2, sp = slot - P, sq = slot - (P + 1);
                     if (s1 < 0) s1 += RING;
                     if (s2 < 0) s2 += RING;
                     if (sp < 0) sp += RING;
                     if (sq < 0) sq += RING;
-                    const int* xb = xs + g * RING * XW;
-#pragma unroll
-                    for (int aa = 0; aa < W; ++aa) {
-                        U1[aa] = xb[s1 * XW + aa];
-                        U2[aa] = xb[s2 * XW + aa];
-                        UP[aa] = xb[sp * XW + aa];
-                        UQ[aa] = xb[sq * XW + aa];
-                    }
+                    lds_rec<W>(U1, xin_b + s1 * (XW * 4), lane == 0);
+                    lds_rec<W>(U2, xin_b + s2 * (XW * 4), lane == 0);
+                    lds_rec<W>(UP, xin_b + sp * (XW * 4), lane == 0);
+                    lds_rec<W>(UQ, xin_b + sq * (XW * 4), lane == 0);
                 }
 
                 // ---- additive constants shared by all band offsets of this iteration (scores of pyx:233-248; the low
@@ -195,7 +246,7 @@ __global__ void __launch_bounds__(256) fill_na_kernel(SysArgs A) {
                     if (aa + 1 < W) v = addmax(UP[aa + 1], c3, v);                   // 1100  case 3
                     if (aa >= 1) v = addmax(h[0][aa - 1], mu2 + kD + pB0 + T_ * 11, v);  // 0011  case 4
                     if (aa + 1 < W) v = addmax(U1[aa + 1], c5, v);                   // 1000  case 5
-                    if (P >= 2) v = addmax(h[P - 2][aa], c6, v);                     // 0100  case 6
+                    v = addmax(h[P - 2][aa], c6, v);                                 // 0100  case 6
                     if (aa >= 1) v = addmax(M[aa - 1], c7, v);                       // 0010  case 7 (same iteration)
                     v = addmax(h[0][aa], c8, v);                                     // 0001  case 8
                     v = addmax(U2[aa], mu2 + kGD + pB0 + T_ * 6, v);                 // 1011  case 9
@@ -203,17 +254,17 @@ __global__ void __launch_bounds__(256) fill_na_kernel(SysArgs A) {
                     v = addmax(UP[aa], c11, v);                                      // 1110  case 11
                     if (aa + 1 < W) v = addmax(UQ[aa + 1], c12, v);                  // 1101  case 12
                     v = (colok && okA[aa]) ? v : NEGP;
-                    if (aa == S && q == q_origin) v = 0;                             // M[0,0,0,0] = 0 (numpy zeros, pyx:27-35)
+                    if (!ST && aa == S && q == q_origin) v = 0;                      // M[0,0,0,0] = 0 (numpy zeros, pyx:27-35)
                     if (TRACE) {
-                        // a cell no case reaches keeps nibble 15 ("none"): NEGP has a zero low nibble -> 15 - 0
-                        code |= (uint32_t)(15 - (v & 15)) << (4 * aa);
+                        code = __funnelshift_r(code, (uint32_t)v, 4);  // low nibble (15 - case index) in at the top
                         v &= ~15;
                     }
                     M[aa] = v;
                 }
-                if (TRACE) { *cw = code; cw += 32; }
+                // nibble aa = case index of band offset aa; a cell no case reaches reads 15 ("none": NEGP has a zero low nibble)
+                if (TRACE) { *cw = (~code) >> (32 - 4 * W); cw += 32; }
 
-                if (q == q_end) {
+                if (!ST && q == q_end) {
                     const int best = M[S] >> TB;
                     A.scores[d.orig] = (long long)best * A.gscale;
                     A.start_state[d.orig] = 8;
@@ -222,11 +273,8 @@ __global__ void __launch_bounds__(256) fill_na_kernel(SysArgs A) {
                 }
 
                 // ---- publish: the last lane of every warp feeds lane 0 of the warp below / the next row block
-                if (lane == 31) {
-                    int* xo = xs + ((g + 1) * RING + slot) * XW;
-#pragma unroll
-                    for (int aa = 0; aa < W; ++aa) xo[aa] = M[aa];
-                }
+                if constexpr (ST) sts_rec<W>(xout_cur + u * (XW * 4), M, lane == 31);
+                else sts_rec<W>(xout_b + slot * (XW * 4), M, lane == 31);
 #pragma unroll
                 for (int dd = NH - 1; dd >= 1; --dd)
 #pragma unroll
@@ -239,16 +287,33 @@ __global__ void __launch_bounds__(256) fill_na_kernel(SysArgs A) {
                     asm volatile("cp.async.wait_group %0;\n" ::"n"(LA - 1) : "memory");
                     if (do_stage) {
                         int val = pb[((q + 4 * PB) & (PB - 1)) * XW + io_e];
-                        if (q + RT >= nit) val = NEGP;
-                        xs[slot * XW + io_e] = val;
-                        if (q + LA + RT < nit) {
+                        if (!ST && q + RT >= nit) val = NEGP;
+                        xs[(ST ? (half ? NH : 0) + u : slot) * XW + io_e] = val;
+                        if (ST || q + LA + RT < nit) {
                             const unsigned dst = smem_u32(pb + ((q + LA + 4 * PB) & (PB - 1)) * XW + io_e);
                             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(bnd_in + (size_t)(q + LA + RT + PRE + 1) * XW + io_e) : "memory");
                         }
                     }
                     asm volatile("cp.async.commit_group;\n" ::: "memory");
                 }
-                __syncthreads();
+            };
+
+            // whole history periods (NH iterations, statically unrolled: the delay-line registers are renamed, not moved)
+            for (int q = -PRE; q < nit;) {
+                const bool aligned = (slot == NH - 1) || (slot == RING - 1);  // the next slot starts a half of the exchange ring
+                if (aligned && q >= st_lo && q + NH <= st_hi) {  // warp-uniform
+                    half = (slot == NH - 1);                     // the block writes the second half
+                    xin_cur = xin_b + (half ? NH : 0) * (XW * 4);
+                    xin_oth = xin_b + (half ? 0 : NH) * (XW * 4);
+                    xout_cur = xout_b + (half ? NH : 0) * (XW * 4);
+                    steady_block(iteration, q, std::make_integer_sequence<int, NH>{});
+                    q += NH;
+                    slot = half ? RING - 1 : NH - 1;
+                } else {
+                    iteration(BC_<false>{}, IC_<0>{}, q);
+                    __syncthreads();
+                    ++q;
+                }
             }
             if (has_out) {  // the record of the last iteration, then make the stream visible to the next row block
                 if (io) bnd_out[(size_t)(nit + PRE) * XW + io_e] = xs[(G * RING + slot) * XW + io_e];

@@ -186,8 +186,14 @@ __device__ __forceinline__ void open3(int i0, int i1, int i2, int beta, int& o0,
     }
 }
 
+// Register caps: narrow bands in batch mode fit 128 registers without spills, which (with 54 KB of shared memory per
+// 4-warp CTA) allows four CTAs = 16 warps per SM (measured on config 3: +3.6 % over three CTAs at 142 registers);
+// wider bands and the long-pair flavour keep 168 (three CTAs of 128 threads: 65536 / 384 = 170).
 #ifndef BA_SYS_MAXNREG
-#define BA_SYS_MAXNREG 168  // 3 CTAs of 128 threads per SM: 65536 / 384 = 170
+#define BA_SYS_MAXNREG 168
+#endif
+#ifndef BA_SYS_MAXNREG_NARROW
+#define BA_SYS_MAXNREG_NARROW 128
 #endif
 constexpr int LQ = 32;   // long-pair mode: progress flags are published / polled about every LQ iterations (rounded up to whole
                         // ring periods); measured on the 8192 x 8192 pair: 4 -> 158 ms (the extra barrier and the spinning
@@ -258,11 +264,11 @@ struct Geo {
 // pyx:233-248": with TRACE the low 4 bits carry 15 - case index, attached at the target through the additive constants;
 // the code word of a cell is the case index of its best state (what the traceback of pyx:521-528 would pick).
 template <int S, bool TRACE, bool PAD, bool BNEG, bool LONG, bool P16 = false, bool NA = false>
-__global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
+__global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
     static_assert(!P16 || (!TRACE && !PAD && BNEG && !LONG), "16-bit pair mode: score only, pad-free, beta < 0, batch mode");
     static_assert(!NA || (BNEG && !LONG && !P16), "non-affine flavour: batch mode, 32-bit");
     using G_ = Geo<S, PAD>;
-    constexpr int W = G_::W, P = G_::P, LPR = G_::LPR, R = G_::R, RING = G_::RING, NV = G_::NV, NVR = G_::NVR, PB = G_::PB;
+    constexpr int W = G_::W, P = G_::P, LPR = G_::LPR, R = G_::R, RING = G_::RING, NVR = G_::NVR, PB = G_::PB;
     constexpr bool SELFREG = G_::SELFREG;
     constexpr int RSLOT = G_::RSLOT, REC = G_::REC, REAL = G_::REAL, LA = G_::LA, XSLOT = G_::XSLOT, LQB = G_::LQB, XA = G_::XA;
     constexpr int RSLOTB = RSLOT * 4, XSLOTB = XSLOT * 4, RECB = REC * 4;
@@ -572,7 +578,8 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                     for (int v = 0; v < 12; ++v) rv[v] = pf[v];
                 } else if constexpr (ST) {
                     constexpr int oA = ((u + 2 * RING - (P + 2)) % RING) * RSLOTB, oB = ((u + 2 * RING - (P + 1)) % RING) * RSLOTB;
-                    constexpr int oC = ((u + 2 * RING - P) % RING) * RSLOTB, oD = ((u + 2 * RING - (P - 1)) % RING) * RSLOTB;
+                    constexpr int oC = ((u + 2 * RING - P) % RING) * RSLOTB;
+                    [[maybe_unused]] constexpr int oD = ((u + 2 * RING - (P - 1)) % RING) * RSLOTB;
                     rv[2] = lds32o<oA + 2 * 128>(rU0);
                     rv[1] = lds32o<oB + 1 * 128>(rU0);
                     rv[0] = lds32o<oB + 0 * 128>(rU1);
@@ -784,7 +791,8 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                 if (PF) {
                     if constexpr (ST) {
                         constexpr int oA = ((u + 1 + 2 * RING - (P + 2)) % RING) * RSLOTB, oB = ((u + 1 + 2 * RING - (P + 1)) % RING) * RSLOTB;
-                        constexpr int oC = ((u + 1 + 2 * RING - P) % RING) * RSLOTB, oD = ((u + 1 + 2 * RING - (P - 1)) % RING) * RSLOTB;
+                        constexpr int oC = ((u + 1 + 2 * RING - P) % RING) * RSLOTB;
+                        [[maybe_unused]] constexpr int oD = ((u + 1 + 2 * RING - (P - 1)) % RING) * RSLOTB;
                         pf[2] = lds32o<oA + 2 * 128>(rU0);
                         pf[1] = lds32o<oB + 1 * 128>(rU0);
                         pf[0] = lds32o<oB + 0 * 128>(rU1);
@@ -905,6 +913,7 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
             };
 
             int next_flag = 0;  // LONG: next iteration (a multiple of RING) at which progress is published / awaited
+            const int lqb = (LONG && A.lq_iters > 0) ? A.lq_iters : LQB;
             for (int q = -PRE; q < nit;) {
                 const bool aligned = (wslot == RING - 1);  // q is a multiple of RING
                 if (LONG && aligned && q >= next_flag) {
@@ -914,11 +923,11 @@ __global__ void __maxnreg__(BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
                             st_release_u64(prog_out, tag_out | (unsigned long long)(q - 1));
                         }
                         if (has_in) {  // the iterations up to the next flag point prefetch records up to q + LQB - 1 + LA + 2RT
-                            const unsigned long long want = tag_in | (unsigned long long)min(q + LQB + LA + 2 * RT, nit);
+                            const unsigned long long want = tag_in | (unsigned long long)min(q + lqb + LA + 2 * RT, nit);
                             while (ld_acquire_u64(prog_in) < want) __nanosleep(100);
                         }
                     }
-                    next_flag = q + LQB;
+                    next_flag = q + lqb;
                     __syncthreads();
                 }
                 if (STEADY_OK && aligned && q >= st_lo && q + RING <= st_hi) {  // warp-uniform

@@ -42,6 +42,7 @@ struct SysArgs {
     unsigned long long* progress;  // LONG flavour: one progress flag per boundary stream (2 * grid)
     int* bnd;                 // per CTA: two boundary streams of bnd_iters records
     int bnd_iters;
+    int lq_iters;             // LONG flavour: iterations between progress-flag exchanges (a multiple of the ring period; 0 = default)
     uint64_t* codes;
     long long* scores;
     uint8_t* start_state;

@@ -56,6 +56,14 @@ def main():
         res, cls, off, pa, pb = workloads.protein_pairs(12500, seed=3)
         run("cfg3 12.5k protein pairs 200-500 s=2 trace", al, res, cls, off, pa, pb, True)
         run("cfg3 12.5k protein pairs 200-500 s=2 score-only", al, res, cls, off, pa, pb, False)
+    if "3s" in which:  # small slice (profiler captures)
+        al = BatchAligner(max_shift=2, **prot)
+        res, cls, off, pa, pb = workloads.protein_pairs(3552, seed=3)
+        run("cfg3 3552 protein pairs 200-500 s=2 trace", al, res, cls, off, pa, pb, True, reps=1)
+    if "4s" in which:
+        al = BatchAligner(max_shift=2, **workloads.RNA_PARAMS)
+        res, cls, off, pa, pb = workloads.rna_pairs(30000, seed=4)
+        run("cfg4 30k RNA pairs len 120 s=2 score-only", al, res, cls, off, pa, pb, False, reps=1)
     if "4" in which:
         al = BatchAligner(max_shift=2, **workloads.RNA_PARAMS)
         res, cls, off, pa, pb = workloads.rna_pairs(125000, seed=4)

@@ -480,11 +480,12 @@ def test_tie_storms_at_multipass_sizes(variant):
         _unselect(al)
 
 
-@pytest.mark.parametrize("kernel", [0, 1, 2])
+@pytest.mark.parametrize("kernel", [0, 1, 2, 3])
 @pytest.mark.parametrize("s", [0, 1, 2, 3, 4])
 def test_nonaffine_model_vs_oracle(s, kernel):
-    """gap_opening_cost == 0 (the CLI default): level kernel and both systolic flavours against the oracle's literal
-    restatement of pyx:443-471 / 513-531 -- scores and first-case-wins traces, ragged multi-pass batch."""
+    """gap_opening_cost == 0 (the CLI default): level kernel (0), both non-affine flavours of the systolic kernel (1, 2) and
+    the dedicated row-per-lane kernel (3, max_shift <= 3) against the oracle's literal restatement of pyx:443-471 /
+    513-531 -- scores and first-case-wins traces, ragged multi-block batch."""
     from bialign_b200.batch import trace_hex
 
     rng = np.random.default_rng(2300 + s)
@@ -494,11 +495,14 @@ def test_nonaffine_model_vs_oracle(s, kernel):
         params.update(var)
         seqs, structs, pairs = _random_protein_batch(rng, 8, 1, 110)
         al = _aligner(params)
-        _select(al, kernel)
+        _select(al, min(kernel, 1) if kernel == 3 else kernel)
+        al.set_option("na_kernel", 1 if kernel == 3 and s <= 3 else 0)
+        if kernel == 3:
+            al.set_option("warps_per_cta", int(rng.choice([1, 2, 3])))  # 32, 64, 96 rows per block: one to four blocks per pair
         try:
             scores, cols, offsets, complete = al.align(seqs, structs, pairs, want_trace=True)
             kind = al.engine.stats()["kernel_kind"]
-            assert kind == (0 if kernel == 0 else 5 + kernel)
+            assert kind == (0 if kernel == 0 else (8 if s <= 3 else 6) if kernel == 3 else 5 + kernel)
             for q, (ia, ib) in enumerate(pairs):
                 r = oracle.run(seqs[ia], seqs[ib], structs[ia], structs[ib], params)
                 assert int(scores[q]) == r["score"], (q, var)
