@@ -77,6 +77,8 @@ __device__ __forceinline__ void sts_rec(unsigned addr, const int (&v)[W], bool c
 }
 
 template <int S, bool TRACE>
+// (no register cap: a 96-register cap compiles without spills for max_shift <= 2 and gives 20 resident warps per SM instead
+// of 12, but measured 236 instead of 356 G cells/s on the config-3 shape: not adopted)
 __global__ void __launch_bounds__(256, 1) fill_na_kernel(SysArgs A) {
     using G_ = Geo<S>;
     constexpr int W = G_::W, P = G_::P, NH = G_::NH, RING = G_::RING, XW = G_::XW, PRE = G_::PRE, LA = G_::LA, PB = G_::PB;

@@ -771,10 +771,12 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
                     else { stg64o<0>(cw, lo, hi); cw += 32; }
                     // table layout [source state][b][lane column]: for one source state the lanes of a warp read
                     // (at most P*LPR <= 32) consecutive words -> no bank conflicts
-                    const unsigned tp = tb_b + bb * (LPR * 4);
                     const int msk = ~((1 << TB) - 1);
+                    {
+                        const unsigned tp = tb_b + bb * (LPR * 4);
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) M[t] = (M[t] & msk) | lds32(tp + t * (P * LPR * 4));
+                        for (int t = 0; t < 9; ++t) M[t] = (M[t] & msk) | lds32(tp + t * (P * LPR * 4));
+                    }
                 }
 
                 // ---- publish: R (second alignment decided), L (first decided), Q (both)
