@@ -219,10 +219,12 @@ def gather_traces(mine, cols, offsets, complete, n_total, device=None, dst=None)
     meta_h = meta.cpu().numpy()
     goff = np.concatenate([[0], np.cumsum(meta_h[0])]).astype(np.int64)
     total_local = int(offsets[-1] - offsets[0])
-    place = np.repeat(goff[mine] - offsets[:-1], lens) + np.arange(offsets[0], offsets[0] + total_local)
     flat = torch.zeros(int(goff[-1]), dtype=torch.uint8, device=device)
     if total_local:
-        flat[torch.as_tensor(place, device=device)] = torch.as_tensor(np.asarray(cols[offsets[0]:offsets[-1]]), device=device)
+        # byte k of local pair p goes to goff[mine[p]] + k: per-pair shifts expanded on the device (no per-byte host index)
+        shift = torch.as_tensor(goff[mine] - (offsets[:-1] - offsets[0]), device=device)
+        place = torch.repeat_interleave(shift, torch.as_tensor(lens, device=device)) + torch.arange(total_local, device=device)
+        flat[place] = torch.as_tensor(np.ascontiguousarray(cols[offsets[0]:offsets[-1]]), device=device)
     if multi:
         if dst is None:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM)
