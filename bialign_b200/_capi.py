@@ -13,7 +13,7 @@ BA_OK, BA_ERR_INVALID_ARG, BA_ERR_NO_DEVICE, BA_ERR_CUDA, BA_ERR_OOM, BA_ERR_SCO
 SYMBOLS = ["ba_engine_create", "ba_engine_destroy", "ba_last_error", "ba_set_scoring", "ba_load_sequences",
            "ba_load_pairs", "ba_run", "ba_fetch_scores", "ba_trace_bytes", "ba_fetch_traces", "ba_align_batch",
            "ba_get_stats", "ba_set_option", "ba_debug_fetch_codes", "ba_debug_fetch_end_values", "ba_microbench_int",
-           "ba_version", "ba_engine_create_multi", "ba_engine_device_count"]
+           "ba_version", "ba_engine_create_multi", "ba_engine_device_count", "ba_set_pair_mu2"]
 
 
 ENGINE_OPTIONS = {"kernel": -1, "pad": -1, "long": -1, "p16": -1, "na_kernel": -1, "warps_per_cta": 0, "code_arena_bytes": 0}
@@ -55,6 +55,7 @@ def load_library():
     L.ba_set_scoring.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32]
     L.ba_load_sequences.argtypes = [vp, vp, vp, vp, i64]
     L.ba_load_pairs.argtypes = [vp, vp, vp, i64]
+    L.ba_set_pair_mu2.argtypes = [vp, vp, vp]
     L.ba_run.argtypes = [vp, i32]
     L.ba_fetch_scores.argtypes = [vp, vp]
     L.ba_trace_bytes.argtypes = [vp, ctypes.POINTER(i64)]
@@ -137,6 +138,18 @@ class Engine:
         assert a.shape == b.shape
         self._npairs = int(a.size)
         self._check(self._L.ba_load_pairs(self._h, _ptr(a), _ptr(b), a.size))
+
+    def set_pair_mu2(self, matrices):
+        """Per-pair mu2 matrices (list of int arrays of shape len(A) x len(B), in pair order), or None to drop them."""
+        if matrices is None:
+            self._check(self._L.ba_set_pair_mu2(self._h, None, None))
+            return
+        flat = [np.ascontiguousarray(m, dtype=np.int32).reshape(-1) for m in matrices]
+        off = np.concatenate([[0], np.cumsum([f.size for f in flat])]).astype(np.int64)
+        buf = np.concatenate(flat).astype(np.int32) if flat else np.zeros(1, dtype=np.int32)
+        if buf.size == 0:
+            buf = np.zeros(1, dtype=np.int32)
+        self._check(self._L.ba_set_pair_mu2(self._h, _ptr(buf), _ptr(off)))
 
     def run(self, want_trace=False):
         self._check(self._L.ba_run(self._h, 1 if want_trace else 0))

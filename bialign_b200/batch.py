@@ -139,10 +139,23 @@ class BatchAligner:
         eng.set_scoring(self.table, p["structure_weight"], p["gap_opening_cost"], p["gap_cost"],
                         p["shift_cost"], p["max_shift"])
 
-    def align_encoded(self, res, cls, off, pair_a, pair_b, want_trace=False):
-        """End-to-end on host arrays.  Returns scores, or (scores, cols, offsets, complete)."""
+    def align_encoded(self, res, cls, off, pair_a, pair_b, want_trace=False, mu2=None):
+        """End-to-end on host arrays.  Returns scores, or (scores, cols, offsets, complete).
+        `mu2`: optional list of per-pair int matrices len(A) x len(B) replacing the class-equality structure similarity
+        (probabilistic RNA profiles, pyx:414-423); such batches run on the general level kernel."""
         self.check_known(res, off, pair_a, pair_b)
         self.configure()
+        if mu2 is not None:
+            eng = self.engine
+            eng.load_sequences(res, cls, off)
+            eng.load_pairs(pair_a, pair_b)
+            eng.set_pair_mu2(mu2)
+            eng.run(want_trace=want_trace)
+            scores = eng.fetch_scores()
+            if not want_trace:
+                return scores
+            cols, offsets, complete = eng.fetch_traces()
+            return scores, cols, offsets, complete
         scores = self.engine.align_batch(res, cls, off, pair_a, pair_b, want_trace=want_trace)
         if not want_trace:
             return scores

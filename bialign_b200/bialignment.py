@@ -51,6 +51,33 @@ def _column_score_affine(state, x, mu1, mu2, beta, gamma, Delta):
     return score
 
 
+def _symmetric_pair_matrix(bpp):
+    """1-based symmetric pair-probability matrix from ViennaRNA's upper-triangular `bpp`, diagonal = probability of being
+    unpaired (behaviour of pyx:327-338; row sums accumulated left to right like the reference's Python sums)."""
+    n = len(bpp) - 1
+    upper = np.triu(np.asarray(bpp, dtype=float)[: n + 1, : n + 1], k=1)
+    upper[0, :] = 0.0
+    sb = upper + upper.T
+    for i in range(1, n + 1):
+        sb[i, i] = 1.0 - (np.cumsum(sb[i, 1:])[-1] if n else 0.0)
+    return sb
+
+
+def _pairing_profile(mol):
+    """(up, down, unp) lists over positions 0..n (pyx:366-374): probability of pairing upstream (partner at most i-2),
+    downstream, or not at all; sums run left to right like the reference's."""
+    n = mol["len"]
+    if "sbpp" not in mol:  # supplied dot-bracket string: one-hot profile from the structure classes
+        cls = np.concatenate([[encoding.UNP], mol["cls"]])
+        return ([float(c == encoding.UP) for c in cls], [float(c == encoding.DOWN) for c in cls],
+                [float(c == encoding.UNP) for c in cls])
+    sb = mol["sbpp"]
+    up = [float(np.cumsum(sb[i, 1:i - 1])[-1]) if i - 1 > 1 else 0.0 for i in range(n + 1)]
+    down = [float(np.cumsum(sb[i, i + 1:n + 1])[-1]) if i + 1 <= n else 0.0 for i in range(n + 1)]
+    unp = [1.0 - up[i] - down[i] for i in range(n + 1)]
+    return up, down, unp
+
+
 class BiAligner:
     nl = 14
     outmodes = {
@@ -97,10 +124,18 @@ class BiAligner:
         x["len"] = len(x["seq"])
         if structure is None:
             if self._is_rna:
-                # The reference predicts base-pair probabilities with ViennaRNA here (pyx:345-353).
-                # That dependency is outside the scope of this engine: supply dot-bracket structures.
-                import RNA  # noqa: F401  (raises ModuleNotFoundError exactly like the reference without ViennaRNA)
-                raise NotImplementedError("predicted RNA structures are not supported; pass strA/strB")
+                # No structure: base-pair probabilities from ViennaRNA, exactly the calls of pyx:345-353 (ModuleNotFoundError
+                # when the module is absent, like the reference).  The probabilistic structure similarity is evaluated on the
+                # host with the reference's floating-point formula and handed to the engine as an integer matrix.
+                import RNA
+
+                fc = RNA.fold_compound(str(sequence))
+                x["mfe"] = fc.mfe()
+                x["pf"] = fc.pf()
+                x["sbpp"] = _symmetric_pair_matrix(fc.bpp())
+                x["mea"] = mea(x["sbpp"])
+                x["structure"] = x["pf"][0]
+                x["predicted"] = True
             else:
                 self.error("Structures have to be provided when aligning proteins")
         else:
@@ -110,6 +145,8 @@ class BiAligner:
             if self._is_rna:
                 x["partner"] = encoding.dotbracket_partners(structure)
                 x["cls"] = encoding.rna_structure_classes(structure)
+        if self._is_rna:
+            x["up"], x["down"], x["unp"] = _pairing_profile(x)
         return x
 
     # scoring functions, 1-based like the reference (pyx:405-440); used by eval_trace
@@ -123,13 +160,26 @@ class BiAligner:
 
     def mu2(self, i, j):
         if self._is_rna:
-            ca = self.molA["cls"][i - 1] if i >= 1 else encoding.UNP
-            cb = self.molB["cls"][j - 1] if j >= 1 else encoding.UNP
-            # int(w * (sqrt(upA*upB) + sqrt(downA*downB) + sqrt(unpA*unpB))) with one-hot profiles
-            return int(self._params["structure_weight"] * (1.0 if ca == cb else 0.0))
+            # pyx:416-423; with supplied structures the profiles are 0/1 and this is w * [class_A(i) == class_B(j)]
+            A, B = self.molA, self.molB
+            return int(self._params["structure_weight"] * (sqrt(A["up"][i] * B["up"][j]) + sqrt(A["down"][i] * B["down"][j]) +
+                                                           sqrt(A["unp"][i] * B["unp"][j])))
         if self.molA["structure"][i - 1] == self.molB["structure"][j - 1]:
             return self._params["structure_weight"]
         return 0
+
+    def _mu2_matrix(self):
+        """int32 matrix mu2(k, l), k = 1..n, l = 1..m, when a molecule has a predicted (probabilistic) profile, else None."""
+        if not (self._is_rna and (self.molA.get("predicted") or self.molB.get("predicted"))):
+            return None
+        A, B = self.molA, self.molB
+        total = 0.0
+        for key in ("up", "down", "unp"):
+            prod = np.outer(np.asarray(A[key][1:], dtype=float), np.asarray(B[key][1:], dtype=float))
+            if (prod < 0).any():
+                raise ValueError("math domain error")  # math.sqrt of a negative product (pyx:419-421)
+            total = total + np.sqrt(prod)
+        return (self._params["structure_weight"] * total).astype(np.int64).astype(np.int32)
 
     # ------------------------------------------------------------------ the hot path (GPU)
     def _encoded(self):
@@ -158,7 +208,9 @@ class BiAligner:
             table = encoding.match_table(self._params["sequence_match_similarity"],
                                          self._params["sequence_mismatch_similarity"], nsym=max(len(used), 1))
         if self._is_rna:
-            ca, cb = self.molA["cls"], self.molB["cls"]
+            # (a molecule with a predicted profile has no classes: its mu2 comes from the uploaded matrix)
+            ca = self.molA.get("cls", np.zeros(self.molA["len"], dtype=np.uint8))
+            cb = self.molB.get("cls", np.zeros(self.molB["len"], dtype=np.uint8))
         else:
             ca, cb = encoding.encode_bytes(self.molA["structure"]), encoding.encode_bytes(self.molB["structure"])
         return ra, rb, ca, cb, table
@@ -177,6 +229,9 @@ class BiAligner:
         off = np.array([0, n, n + m], dtype=np.int64)
         eng.load_sequences(res, cls, off)
         eng.load_pairs(np.array([0], dtype=np.int32), np.array([1], dtype=np.int32))
+        mu2 = self._mu2_matrix()
+        if mu2 is not None:
+            eng.set_pair_mu2([mu2])
         eng.run(want_trace=True)
         self._score = np.int64(eng.fetch_scores()[0])
         cols, offsets, complete = eng.fetch_traces()
@@ -211,6 +266,8 @@ class BiAligner:
     def _sbpp(self, mol):
         """Symmetric pair matrix with unpaired probability on the diagonal for a fixed structure
         (what pyx:378-392 builds); only needed for the RNA consensus-structure rows."""
+        if "sbpp" in mol:
+            return mol["sbpp"]
         n = mol["len"]
         m = np.zeros((n + 1, n + 1), dtype=float)
         partner = mol["partner"]

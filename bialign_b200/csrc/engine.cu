@@ -89,6 +89,10 @@ struct ba_engine {
 
     std::vector<int32_t> h_pa, h_pb;
     int64_t n_pairs = 0;
+    bool have_mu2 = false;             // per-pair mu2 matrices loaded (ba_set_pair_mu2): general level kernel only
+    int64_t max_abs_mu2 = 0;
+    DevBuf<int> d_mu2;
+    DevBuf<long long> d_mu2_off;
 
     std::vector<PairDesc> h_desc;          // sorted order
     std::vector<int64_t> h_slot_off;       // caller order
@@ -257,6 +261,7 @@ int set_option(ba_engine* e, const char* key, int64_t value);
 int set_scoring(ba_engine* e, const int32_t* sim, int nsym, int w, int beta, int gamma, int delta, int s);
 int load_sequences(ba_engine* e, const uint8_t* residues, const uint8_t* classes, const int64_t* offsets, int64_t n_seq);
 int load_pairs(ba_engine* e, const int32_t* seq_a, const int32_t* seq_b, int64_t n_pairs);
+int set_pair_mu2(ba_engine* e, const int32_t* mu2, const int64_t* offsets);
 int run(ba_engine* e, int want_trace);
 int fetch_scores(ba_engine* e, int64_t* scores);
 int trace_bytes(ba_engine* e, int64_t* total);
@@ -306,6 +311,7 @@ void ba_engine_destroy(ba_engine* e) {
     e->d_scratch.release(); e->d_counter.release(); e->d_scores.release(); e->d_start.release();
     e->d_complete.release(); e->d_trace.release(); e->d_endv.release(); e->d_tlen.release(); e->h_stage.release();
     e->d_simp.release(); e->d_tbtab.release(); e->d_bnd.release(); e->d_progress.release();
+    e->d_mu2.release(); e->d_mu2_off.release();
     cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -404,7 +410,38 @@ int ba_load_pairs(ba_engine* e, const int32_t* seq_a, const int32_t* seq_b, int6
     e->h_pb.assign(seq_b, seq_b + n_pairs);
     e->n_pairs = n_pairs;
     e->have_pairs = true;
+    e->have_mu2 = false;
     e->ran = false;
+    return BA_OK;
+}
+
+int ba_set_pair_mu2(ba_engine* e, const int32_t* mu2, const int64_t* offsets) {
+    if (!e) return BA_ERR_INVALID_ARG;
+    if (!e->kids.empty()) return multi::set_pair_mu2(e, mu2, offsets);
+    if (!e->have_pairs) return fail(e, BA_ERR_STATE, "ba_load_pairs first");
+    e->have_mu2 = false;
+    e->ran = false;
+    if (!mu2 && !offsets) return BA_OK;  // back to class-equality scoring
+    if (!offsets) return fail(e, BA_ERR_INVALID_ARG, "offsets is NULL");
+    const int64_t N = e->n_pairs;
+    for (int64_t p = 0; p < N; ++p) {
+        const int64_t n = e->h_off[e->h_pa[p] + 1] - e->h_off[e->h_pa[p]], m = e->h_off[e->h_pb[p] + 1] - e->h_off[e->h_pb[p]];
+        if (offsets[p + 1] - offsets[p] != n * m)
+            return fail(e, BA_ERR_INVALID_ARG, "mu2 matrix of pair " + std::to_string(p) + " must hold len(A) x len(B) entries");
+    }
+    const int64_t total = N ? offsets[N] - offsets[0] : 0;
+    if (total > 0 && !mu2) return fail(e, BA_ERR_INVALID_ARG, "mu2 is NULL");
+    CU(cudaSetDevice(e->device));
+    e->max_abs_mu2 = 0;
+    for (int64_t q = 0; q < total; ++q) e->max_abs_mu2 = std::max<int64_t>(e->max_abs_mu2, std::llabs((long long)mu2[offsets[0] + q]));
+    std::vector<long long> off((size_t)N + 1);
+    for (int64_t p = 0; p <= N; ++p) off[p] = offsets[p] - offsets[0];
+    CU(e->d_mu2.ensure((size_t)std::max<int64_t>(total, 1)));
+    CU(e->d_mu2_off.ensure((size_t)N + 1));
+    if (total) CU(cudaMemcpyAsync(e->d_mu2.p, mu2 + offsets[0], sizeof(int) * total, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->d_mu2_off.p, off.data(), sizeof(long long) * (N + 1), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->have_mu2 = true;
     return BA_OK;
 }
 
@@ -448,11 +485,18 @@ int ba_run(ba_engine* e, int want_trace) {
         cs += (affine ? 9 : 1) * band_cells(ln[p], lm[p], s);
     }
     e->stats.cell_states = cs;
+    bool wide = false;  // values need the reference's int64 tables (pyx:27-35): general level kernel, 64-bit instantiation
     {   // int32 exactness bound of SURVEY 8a-6
-        const int64_t col = e->max_abs_sim + std::llabs((long long)e->sc.w) + 2 * std::llabs((long long)e->sc.beta) +
+        const int64_t col = e->max_abs_sim + std::max<int64_t>(std::llabs((long long)e->sc.w), e->have_mu2 ? e->max_abs_mu2 : 0) +
+                            2 * std::llabs((long long)e->sc.beta) +
                             2 * std::llabs((long long)e->sc.gamma) + 2 * std::llabs((long long)e->sc.delta);
-        if ((int64_t)(nmax + mmax + 2) * col >= ((int64_t)1 << 30))
-            return fail(e, BA_ERR_SCORE_RANGE, "score bound exceeds int32 range (needs the reference's int64 tables)");
+        if ((int64_t)(nmax + mmax + 2) * col >= ((int64_t)1 << 30)) {
+            if (e->opt_kernel == 1)
+                return fail(e, BA_ERR_SCORE_RANGE, "score bound exceeds int32 range: only the general level kernel has a 64-bit instantiation (kernel = 1 requested)");
+            if ((double)(nmax + mmax + 2) * (double)col >= 4.0e18)
+                return fail(e, BA_ERR_SCORE_RANGE, "score bound exceeds int64 range");
+            wide = true;
+        }
     }
     lap("lengths + range check");
     std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
@@ -475,12 +519,21 @@ int ba_run(ba_engine* e, int want_trace) {
     // ---- kernel choice: systolic when its exactness conditions hold, else the generic level kernel
     SysPlan plan;
     bool p16 = false;
-    if (e->opt_kernel != 0 && affine && !want_trace && e->opt_p16 != 0 && e->opt_pad != 1 && N >= 2) {
+    if (e->opt_kernel != 0 && affine && !want_trace && e->opt_p16 != 0 && e->opt_pad != 1 && N >= 2 && !e->have_mu2 && !wide) {
         plan = plan_systolic(e, nmax, mmax, false, true);  // do the scores provably fit 16 bits?
         p16 = plan.ok;
     }
     if (e->opt_p16 == 1 && !p16 && !want_trace && affine && N >= 2)
         return fail(e, BA_ERR_SCORE_RANGE, "16-bit pair mode requested but the score range does not fit");
+    if (wide) {
+        p16 = false;
+        plan = SysPlan{};
+    } else
+    if (e->have_mu2) {  // per-pair mu2 matrices: only the general level kernel reads them
+        if (e->opt_kernel == 1) return fail(e, BA_ERR_INVALID_ARG, "per-pair mu2 matrices run on the general level kernel (kernel = 1 requested)");
+        p16 = false;
+        plan = SysPlan{};
+    } else
     if (!p16 && e->opt_kernel != 0) plan = plan_systolic(e, nmax, mmax, want_trace != 0, false, !affine);
     if (e->opt_kernel == 1 && !plan.ok)
         return fail(e, BA_ERR_SCORE_RANGE, "systolic kernel requested but its packed-integer range conditions do not hold");
@@ -739,7 +792,7 @@ int ba_run(ba_engine* e, int want_trace) {
     } else {
         scratch_stride = generic_scratch_ints(nmax, s);  // sized for nine states; the non-affine kernel uses a ninth
         const int grid = (int)std::min<int64_t>(biggest_wave, max_grid);
-        cudaError_t ce = e->d_scratch.ensure(scratch_stride * grid);
+        cudaError_t ce = e->d_scratch.ensure(scratch_stride * grid * (wide ? 2 : 1));
         if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "fill scratch: " + std::string(cudaGetErrorString(ce)));
     }
     lap("kernel plan + scratch");
@@ -768,6 +821,7 @@ int ba_run(ba_engine* e, int want_trace) {
         A.scratch = e->d_scratch.p; A.scratch_stride = scratch_stride;
         A.codes = want_trace ? e->d_codes.p : nullptr;
         A.scores = e->d_scores.p; A.start_state = e->d_start.p; A.end_values = e->d_endv.p;
+        A.mu2 = e->have_mu2 ? e->d_mu2.p : nullptr; A.mu2_off = e->d_mu2_off.p;
         const int grid = (int)std::min<int64_t>(cnt, max_grid);
         if (kernel == 1 && long_mode) {
             const int rows_pass = sysG * sys_geo(s, plan.pad).R;
@@ -792,9 +846,9 @@ int ba_run(ba_engine* e, int want_trace) {
             SA.pairs = e->d_desc.p + b; SA.npairs = (int)cnt; SA.counter = e->d_counter.p + w;
             CU(launch_fill_systolic(SA, grid, sysG, sys_smem, want_trace != 0, plan.pad, plan.bneg, e->stream));
         } else if (affine) {
-            launch_fill_generic(A, grid, want_trace != 0, e->stream);
+            launch_fill_generic(A, grid, want_trace != 0, wide, e->stream);
         } else {
-            launch_fill_nonaffine(A, grid, want_trace != 0, e->stream);
+            launch_fill_nonaffine(A, grid, want_trace != 0, wide, e->stream);
         }
         e->stats.kernel_launches++;
         CU(cudaGetLastError());
@@ -838,7 +892,7 @@ int ba_run(ba_engine* e, int want_trace) {
         e->stats.code_bytes = cb;
     }
     e->stats.waves = n_waves;
-    e->stats.kernel_kind = kernel == 0 ? 0 : na_ded ? 8 : (p16 ? 5 : !affine ? (plan.pad ? 7 : 6) : (plan.pad ? 2 : 1) + (long_mode ? 2 : 0));
+    e->stats.kernel_kind = kernel == 0 ? (wide ? 9 : 0) : na_ded ? 8 : (p16 ? 5 : !affine ? (plan.pad ? 7 : 6) : (plan.pad ? 2 : 1) + (long_mode ? 2 : 0));
     e->stats.warps_per_cta = kernel == 0 ? 0 : sysG;
     e->last_fmt = kernel;
     e->last_sysG = kernel == 1 ? sysG : 0;
@@ -1114,6 +1168,21 @@ int load_pairs(ba_engine* e, const int32_t* seq_a, const int32_t* seq_b, int64_t
     e->have_pairs = true;
     e->ran = false;
     return BA_OK;
+}
+
+int set_pair_mu2(ba_engine* e, const int32_t* mu2, const int64_t* offsets) {
+    if (!e->have_pairs) return fail(e, BA_ERR_STATE, "ba_load_pairs first");
+    if (!mu2 && !offsets) return for_each_kid(e, [&](size_t, ba_engine* kid) { return ba_set_pair_mu2(kid, nullptr, nullptr); });
+    if (!mu2 || !offsets) return fail(e, BA_ERR_INVALID_ARG, "mu2 / offsets NULL");
+    return for_each_kid(e, [&](size_t k, ba_engine* kid) {  // every device gets the matrices of its own pairs
+        const auto& sh = e->shard[k];
+        std::vector<int64_t> off(sh.size() + 1, 0);
+        for (size_t q = 0; q < sh.size(); ++q) off[q + 1] = off[q] + (offsets[sh[q] + 1] - offsets[sh[q]]);
+        std::vector<int32_t> buf((size_t)std::max<int64_t>(off.back(), 1));
+        for (size_t q = 0; q < sh.size(); ++q)
+            std::copy(mu2 + offsets[sh[q]], mu2 + offsets[sh[q] + 1], buf.begin() + off[q]);
+        return ba_set_pair_mu2(kid, buf.data(), off.data());
+    });
 }
 
 int run(ba_engine* e, int want_trace) {

@@ -17,7 +17,9 @@ __device__ __forceinline__ int half_score(int src_r, int x_r, int mu, int beta, 
     return gamma + (src_r == x_r ? 0 : beta);
 }
 
-template <bool TRACE>
+// V = int (default) or long long: the reference's tables are int64 (pyx:27-35); the wide instantiation is used when the
+// int32 bound (n+m) * (one column's largest magnitude) >= 2^30 does not hold.
+template <bool TRACE, class V>
 __global__ void __launch_bounds__(256) fill_level_kernel(FillArgs A) {
     __shared__ int s_pair;
     const int s = A.sc.s, W = 2 * s + 1;
@@ -35,12 +37,12 @@ __global__ void __launch_bounds__(256) fill_level_kernel(FillArgs A) {
         const uint8_t* cb = A.cls + d.offB;
         const int n = d.n, m = d.m;
         const int items = (n + 1) * W * W;
-        int* lv = A.scratch + (size_t)blockIdx.x * A.scratch_stride;
+        V* lv = reinterpret_cast<V*>(A.scratch) + (size_t)blockIdx.x * A.scratch_stride;
         const size_t lstride = (size_t)items * 9;
         uint64_t* codes = TRACE ? A.codes + d.code_off : nullptr;
 
         for (int tau = 0; tau <= 2 * (n + m); ++tau) {
-            int* cur = lv + (size_t)(tau % 5) * lstride;
+            V* cur = lv + (size_t)(tau % 5) * lstride;
             for (int it = threadIdx.x; it < items; it += blockDim.x) {
                 const int bb = it % W, aa = (it / W) % W, i = it / (W * W);
                 const int a = aa - s, b = bb - s;
@@ -55,12 +57,14 @@ __global__ void __launch_bounds__(256) fill_level_kernel(FillArgs A) {
                     continue;
                 }
                 const int mu1 = (i > 0 && j > 0) ? A.sim[(int)ra[i - 1] * A.sc.nsym + rb[j - 1]] : 0;
-                const int mu2 = (k > 0 && l > 0 && ca[k - 1] == cb[l - 1]) ? A.sc.w : 0;
+                const int mu2 = A.mu2 ? ((k > 0 && l > 0) ? A.mu2[A.mu2_off[d.orig] + (long long)(k - 1) * m + (l - 1)] : 0)
+                                      : ((k > 0 && l > 0 && ca[k - 1] == cb[l - 1]) ? A.sc.w : 0);
                 uint64_t word = 0;
                 for (int t = 0; t < 9; ++t) {
                     const int r01 = t / 3, r23 = t % 3;
                     const int t0 = hb0(r01), t1 = hb1(r01), t2 = hb0(r23), t3 = hb1(r23);
-                    int best = NEG, bid = 15, bk0 = 0, bk1 = 0;
+                    V best = NEG;
+                    int bid = 15, bk0 = 0, bk1 = 0;
                     // the three groups of pyx:275-296: (x0,x1,x2,x3), first case id
                     for (int g = 0; g < 3; ++g) {
                         const int x0 = (g == 1) ? 0 : t0, x1 = (g == 1) ? 0 : t1;
@@ -70,7 +74,7 @@ __global__ void __launch_bounds__(256) fill_level_kernel(FillArgs A) {
                         const int pa = p2 - p0, pb = p3 - p1;
                         if (pa > s || pa < -s || pb > s || pb < -s) continue;
                         const int nx = x0 + x1 + x2 + x3;
-                        const int* src = lv + (size_t)((tau - nx) % 5) * lstride +
+                        const V* src = lv + (size_t)((tau - nx) % 5) * lstride +
                                          ((size_t)(p0 * W + (pa + s)) * W + (pb + s)) * 9;
                         const int shift = Delta * ((x0 != x2) + (x1 != x3));
                         const int ncase = (g == 0) ? 9 : 3;
@@ -82,7 +86,7 @@ __global__ void __launch_bounds__(256) fill_level_kernel(FillArgs A) {
                             int sc = shift;
                             if (g != 1) sc += half_score(s01, r01, mu1, beta, gamma);
                             if (g != 2) sc += half_score(s23, r23, mu2, beta, gamma);
-                            const int v = src[3 * s01 + s23] + sc;
+                            const V v = src[3 * s01 + s23] + sc;
                             // tie key, a function of (predecessor cell, source state): pyx:541-545
                             const int T0 = pa + hb0(s01) - hb0(s23), T1 = pb + hb1(s01) - hb1(s23);
                             const int k1 = abs(T1), k0 = abs(T0) + k1;
@@ -99,8 +103,8 @@ __global__ void __launch_bounds__(256) fill_level_kernel(FillArgs A) {
             __syncthreads();
         }
         if (threadIdx.x == 0) {
-            const int* fin = lv + (size_t)((2 * (n + m)) % 5) * lstride + ((size_t)(n * W + s) * W + s) * 9;
-            int best = fin[0];
+            const V* fin = lv + (size_t)((2 * (n + m)) % 5) * lstride + ((size_t)(n * W + s) * W + s) * 9;
+            V best = fin[0];
             for (int t = 1; t < 9; ++t) best = max(best, fin[t]);
             // start state: first best state with the fewest shifts (pyx:573-582)
             int st = 0, bsh = 99;
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(256) fill_level_kernel(FillArgs A) {
                 }
             A.scores[d.orig] = best;
             A.start_state[d.orig] = (uint8_t)st;
-            for (int t = 0; t < 9; ++t) A.end_values[(size_t)d.orig * 9 + t] = fin[t];
+            for (int t = 0; t < 9; ++t) A.end_values[(size_t)d.orig * 9 + t] = (int)fin[t];  // (debug hook: truncated when wide)
         }
         __syncthreads();
     }
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(256) fill_level_kernel(FillArgs A) {
 // ---------------------------------------------------------------------------------------------
 __constant__ int NA_XBITS[13] = {15, 10, 5, 12, 3, 8, 4, 2, 1, 11, 7, 14, 13};
 
-template <bool TRACE>
+template <bool TRACE, class V>
 __global__ void __launch_bounds__(256) fill_level_nonaffine_kernel(FillArgs A) {
     __shared__ int s_pair;
     const int s = A.sc.s, W = 2 * s + 1;
@@ -143,10 +147,10 @@ __global__ void __launch_bounds__(256) fill_level_nonaffine_kernel(FillArgs A) {
         const uint8_t* cb = A.cls + d.offB;
         const int n = d.n, m = d.m;
         const int items = (n + 1) * W * W;
-        int* lv = A.scratch + (size_t)blockIdx.x * A.scratch_stride;
+        V* lv = reinterpret_cast<V*>(A.scratch) + (size_t)blockIdx.x * A.scratch_stride;
         uint64_t* codes = TRACE ? A.codes + d.code_off : nullptr;
         for (int tau = 0; tau <= 2 * (n + m); ++tau) {
-            int* cur = lv + (size_t)(tau % 5) * items;
+            V* cur = lv + (size_t)(tau % 5) * items;
             for (int it = threadIdx.x; it < items; it += blockDim.x) {
                 const int bb = it % W, aa = (it / W) % W, i = it / (W * W);
                 const int a = aa - s, b = bb - s;
@@ -161,8 +165,10 @@ __global__ void __launch_bounds__(256) fill_level_nonaffine_kernel(FillArgs A) {
                     continue;
                 }
                 const int mu1 = (i > 0 && j > 0) ? A.sim[(int)ra[i - 1] * A.sc.nsym + rb[j - 1]] : 0;
-                const int mu2 = (k > 0 && l > 0 && ca[k - 1] == cb[l - 1]) ? A.sc.w : 0;
-                int best = NEG, bid = 15;
+                const int mu2 = A.mu2 ? ((k > 0 && l > 0) ? A.mu2[A.mu2_off[d.orig] + (long long)(k - 1) * m + (l - 1)] : 0)
+                                      : ((k > 0 && l > 0 && ca[k - 1] == cb[l - 1]) ? A.sc.w : 0);
+                V best = NEG;
+                int bid = 15;
                 for (int c = 0; c < 13; ++c) {
                     const int xb = NA_XBITS[c];
                     const int x0 = (xb >> 3) & 1, x1 = (xb >> 2) & 1, x2 = (xb >> 1) & 1, x3 = xb & 1;
@@ -178,7 +184,7 @@ __global__ void __launch_bounds__(256) fill_level_nonaffine_kernel(FillArgs A) {
                     else if (c <= 8) sc = gamma + Delta;
                     else if (c <= 10) sc = gamma + mu2 + Delta;
                     else sc = gamma + mu1 + Delta;
-                    const int v = lv[(size_t)((tau - (x0 + x1 + x2 + x3)) % 5) * items + (p0 * W + (pa + s)) * W + (pb + s)] + sc;
+                    const V v = lv[(size_t)((tau - (x0 + x1 + x2 + x3)) % 5) * items + (p0 * W + (pa + s)) * W + (pb + s)] + sc;
                     if (bid == 15 || v > best) { best = v; bid = c; }
                 }
                 cur[it] = best;
@@ -187,23 +193,33 @@ __global__ void __launch_bounds__(256) fill_level_nonaffine_kernel(FillArgs A) {
             __syncthreads();
         }
         if (threadIdx.x == 0) {
-            const int fin = lv[(size_t)((2 * (n + m)) % 5) * items + (n * W + s) * W + s];
+            const V fin = lv[(size_t)((2 * (n + m)) % 5) * items + (n * W + s) * W + s];
             A.scores[d.orig] = fin;
             A.start_state[d.orig] = 0;
-            for (int t = 0; t < 9; ++t) A.end_values[(size_t)d.orig * 9 + t] = fin;
+            for (int t = 0; t < 9; ++t) A.end_values[(size_t)d.orig * 9 + t] = (int)fin;
         }
         __syncthreads();
     }
 }
 
-void launch_fill_nonaffine(const FillArgs& A, int grid, bool trace, cudaStream_t st) {
-    if (trace) fill_level_nonaffine_kernel<true><<<grid, 256, 0, st>>>(A);
-    else fill_level_nonaffine_kernel<false><<<grid, 256, 0, st>>>(A);
+void launch_fill_nonaffine(const FillArgs& A, int grid, bool trace, bool wide, cudaStream_t st) {
+    if (wide) {
+        if (trace) fill_level_nonaffine_kernel<true, long long><<<grid, 256, 0, st>>>(A);
+        else fill_level_nonaffine_kernel<false, long long><<<grid, 256, 0, st>>>(A);
+    } else {
+        if (trace) fill_level_nonaffine_kernel<true, int><<<grid, 256, 0, st>>>(A);
+        else fill_level_nonaffine_kernel<false, int><<<grid, 256, 0, st>>>(A);
+    }
 }
 
-void launch_fill_generic(const FillArgs& A, int grid, bool trace, cudaStream_t st) {
-    if (trace) fill_level_kernel<true><<<grid, 256, 0, st>>>(A);
-    else fill_level_kernel<false><<<grid, 256, 0, st>>>(A);
+void launch_fill_generic(const FillArgs& A, int grid, bool trace, bool wide, cudaStream_t st) {
+    if (wide) {
+        if (trace) fill_level_kernel<true, long long><<<grid, 256, 0, st>>>(A);
+        else fill_level_kernel<false, long long><<<grid, 256, 0, st>>>(A);
+    } else {
+        if (trace) fill_level_kernel<true, int><<<grid, 256, 0, st>>>(A);
+        else fill_level_kernel<false, int><<<grid, 256, 0, st>>>(A);
+    }
 }
 
 size_t generic_scratch_ints(int nmax, int s) {

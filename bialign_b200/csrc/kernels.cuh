@@ -13,11 +13,13 @@ struct FillArgs {
     int npairs;
     int* counter;             // work-queue head (zeroed before launch)
     int* scratch;             // per-CTA scratch (generic kernel: rolling levels; systolic: strip boundaries)
-    size_t scratch_stride;    // ints per CTA
+    size_t scratch_stride;    // values (int, or long long in the wide instantiation) per CTA
     uint64_t* codes;          // traceback-code arena (nullptr when score-only)
     long long* scores;        // [n_pairs] in caller order
     uint8_t* start_state;     // [n_pairs] traceback start state
     int* end_values;          // [n_pairs][9]  M[t][n,m,n,m]
+    const int* mu2;           // optional per-pair structure-similarity matrices (probabilistic RNA profiles, pyx:414-423):
+    const long long* mu2_off; //   pair p (caller order) owns n x m ints at mu2 + mu2_off[p], entry (k-1)*m + (l-1) = mu2(k, l)
 };
 
 // Systolic kernel (fill_systolic.cu).  All score constants are divided by the gcd of the scoring
@@ -65,8 +67,8 @@ struct TraceArgs {
     uint8_t* complete;        // [n_pairs]
 };
 
-void launch_fill_generic(const FillArgs& A, int grid, bool trace, cudaStream_t st);
-void launch_fill_nonaffine(const FillArgs& A, int grid, bool trace, cudaStream_t st);
+void launch_fill_generic(const FillArgs& A, int grid, bool trace, bool wide, cudaStream_t st);    // wide: int64 values
+void launch_fill_nonaffine(const FillArgs& A, int grid, bool trace, bool wide, cudaStream_t st);
 size_t generic_scratch_ints(int nmax, int s);
 void launch_traceback(const TraceArgs& A, cudaStream_t st);
 

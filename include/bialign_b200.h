@@ -33,8 +33,10 @@ extern "C" {
 #define BA_ERR_NO_DEVICE 2   /* no CUDA device / not sm_100: the product has no CPU fallback       */
 #define BA_ERR_CUDA 3        /* a CUDA call failed; ba_last_error has the text                    */
 #define BA_ERR_OOM 4         /* device (or pinned host) allocation failed                         */
-#define BA_ERR_SCORE_RANGE 5 /* |score| bound (n+m)*(max|mu1|+|w|+2|beta|+2|gamma|+2|Delta|) >= 2^30:
-                                the reference's int64 tables (pyx:27-35) would be needed            */
+#define BA_ERR_SCORE_RANGE 5 /* a fast kernel was forced ("kernel" = 1) although its integer range conditions do not hold,
+                                or the score bound exceeds even int64.  In automatic mode batches whose bound
+                                (n+m)*(max|mu1|+|w|+2|beta|+2|gamma|+2|Delta|) reaches 2^30 run on the 64-bit
+                                instantiation of the general level kernel (the reference's int64 tables, pyx:27-35) */
 #define BA_ERR_ALPHABET 6    /* a residue code >= nsym (the reference raises KeyError, pyx:407)    */
 #define BA_ERR_STATE 7       /* call order: scoring / sequences / pairs not set, nothing run yet   */
 
@@ -63,7 +65,8 @@ typedef struct ba_stats {
                                  3 / 4 = the same two in multi-CTA long-pair mode,
                                  5 = systolic pad-free, two pairs per lane in packed 16-bit halves,
                                  6 / 7 = systolic pad-free / padded running the non-affine model,
-                                 8 = dedicated non-affine kernel (a lane owns a row and all its band offsets) */
+                                 8 = dedicated non-affine kernel (a lane owns a row and all its band offsets),
+                                 9 = general level kernel, 64-bit values (score bound >= 2^30)               */
     int32_t device;
     int32_t warps_per_cta;    /* CTA width the systolic kernel ran with (0 for the general kernel)      */
     int32_t reserved;
@@ -97,6 +100,14 @@ BA_API int ba_load_sequences(ba_engine* e, const uint8_t* residues, const uint8_
                       int64_t n_seq);
 /* Pair list: pair p aligns sequence seq_a[p] (molecule A) with seq_b[p] (molecule B). */
 BA_API int ba_load_pairs(ba_engine* e, const int32_t* seq_a, const int32_t* seq_b, int64_t n_pairs);
+
+/* Optional per-pair structure-similarity matrices: pair p of the loaded pair list (caller order) owns len(A) x len(B)
+ * int32 entries at mu2 + offsets[p], entry (k-1)*len(B) + (l-1) = mu2(k, l).  Replaces the probabilistic branch of
+ * _structure_similarity (pyx:414-423: int(w * (sqrt(upA*upB) + sqrt(downA*downB) + sqrt(unpA*unpB))) for base-pair
+ * probability profiles, e.g. ViennaRNA's when no structure is supplied, pyx:345-353): the host evaluates that formula, the
+ * device reads the integers.  Pairs with matrices run on the general level kernel (small batches; not the fast path).
+ * ba_load_pairs drops the matrices; ba_set_pair_mu2(e, NULL, NULL) returns to class-equality scoring. */
+BA_API int ba_set_pair_mu2(ba_engine* e, const int32_t* mu2, const int64_t* offsets);
 
 /* Forward fill (+ traceback when want_trace) of every loaded pair on device-resident inputs.
  * Replaces optimize() (pyx:443-509) and traceback() (pyx:513-586).  Blocks until the device is done. */

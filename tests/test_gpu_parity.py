@@ -337,11 +337,24 @@ def test_error_codes_range_and_alphabet():
     from bialign_b200 import _capi
     from bialign_b200.batch import BatchAligner
 
-    big = BatchAligner(type="Protein", simmatrix="BLOSUM62", structure_weight=1 << 27, gap_opening_cost=-150, gap_cost=-50,
-                       shift_cost=-150, max_shift=1)
-    with pytest.raises(_capi.BialignError) as ei:
-        big.align(["ACD" * 20, "ACD" * 20], ["HHH" * 20, "HHH" * 20], [(0, 1)])
-    assert ei.value.code == _capi.BA_ERR_SCORE_RANGE
+    # a score bound beyond int32: the reference's tables are int64 (pyx:27-35) -> 64-bit level kernel in automatic mode,
+    # BA_ERR_SCORE_RANGE only when a fast kernel is forced
+    from bialign_b200.batch import trace_hex
+
+    for gap_open in (-150, 0):
+        wide = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=1 << 27, gap_opening_cost=gap_open, gap_cost=-50,
+                    shift_cost=-(1 << 24), max_shift=1)
+        big = BatchAligner(**wide)
+        sa, sb, ta, tb = "ACDEFGHIKL" * 6, "ACDFGHIKLM" * 6 + "AC", "HHHEEECCCH" * 6, "HHEEECCCHH" * 6 + "EE"
+        scores, cols, offsets, complete = big.align([sa, sb], [ta, tb], [(0, 1)], want_trace=True)
+        assert big.engine.stats()["kernel_kind"] == 9
+        r = oracle.run(sa, sb, ta, tb, wide, mode="literal")
+        assert int(scores[0]) == r["score"] and abs(r["score"]) > (1 << 31) and trace_hex(cols, offsets, 0) == r["trace"]
+        assert int(big.align([sa, sb], [ta, tb], [(0, 1)])[0]) == r["score"]
+        big.set_option("kernel", 1)
+        with pytest.raises(_capi.BialignError) as ei:
+            big.align([sa, sb], [ta, tb], [(0, 1)])
+        assert ei.value.code == _capi.BA_ERR_SCORE_RANGE
     ok = BatchAligner(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150, gap_cost=-50,
                       shift_cost=-150, max_shift=1)
     res = np.array([0, 1, 200, 3], dtype=np.uint8)  # 200 >= nsym (24): the reference would raise KeyError (pyx:407)
@@ -586,3 +599,28 @@ def trace_hex_(cols, offsets, p):
     from bialign_b200.batch import trace_hex
 
     return trace_hex(cols, offsets, p)
+
+
+def test_probabilistic_structure_similarity_matches_reference(monkeypatch):
+    """No structure supplied for an RNA: base-pair probabilities come from the `RNA` module (here tests/fake_rna, the same
+    stand-in the goldens were generated with from the unmodified reference), mu2 = int(w * (sqrt(upA upB) + ...)) is
+    evaluated on the host and uploaded per pair (ba_set_pair_mu2), the level kernel fills.  Scores, traces, the 14 decoded
+    rows (MEA consensus structures of the probability matrices) and eval_trace must equal the reference's."""
+    import json
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.syspath_prepend(os.path.join(root, "tests", "fake_rna"))
+    monkeypatch.delitem(sys.modules, "RNA", raising=False)
+    from bialign_b200 import bialignment as ba
+
+    cases = json.load(open(os.path.join(root, "tests", "golden", "rna_prob_cases.json")))
+    assert len(cases) >= 10
+    for c in cases:
+        b = ba.BiAligner(c["seqA"], c["seqB"], c["strA"], c["strB"], nameA="A", nameB="B", **c["params"])
+        assert int(b.optimize()) == c["score"], (c["seqA"], c["params"])
+        tr = b.traceback()
+        assert "".join("%x" % (8 * x[0] + 4 * x[1] + 2 * x[2] + x[3]) for x in tr) == c["trace"]
+        assert [[n, r] for n, r in b.decode_trace_full(tr)] == c["full"]
+        assert list(b.eval_trace(tr))[-2:] == c["eval_tail"]

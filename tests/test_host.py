@@ -305,3 +305,45 @@ def test_batch_aligner_rejects_unknown_arguments_and_undefined_matrix_entries(tm
     al.check_known(res, off, [0], [1])  # A/D rows against A/D columns: all defined
     with pytest.raises(KeyError):
         al.check_known(res, off, [2], [1])  # C against D
+
+
+def test_probabilistic_profile_host_arithmetic(monkeypatch):
+    """Host side of the probabilistic RNA path (no GPU): the profile of a predicted structure (tests/fake_rna stands in for
+    ViennaRNA), the uploaded integer matrix and the scalar mu2() agree, and a supplied structure gives the one-hot profile."""
+    import sys
+
+    monkeypatch.syspath_prepend(os.path.join(ROOT, "tests", "fake_rna"))
+    monkeypatch.delitem(sys.modules, "RNA", raising=False)
+    from bialign_b200 import bialignment as ba
+
+    params = dict(type="RNA", simmatrix=None, structure_weight=333, gap_opening_cost=-200, gap_cost=-50, shift_cost=-150,
+                  max_shift=1, sequence_match_similarity=100, sequence_mismatch_similarity=0)
+    b = ba.BiAligner("GGGAAAUCCCGAUUAGCUAGC", "GGCAUAUGCCGAUCG", None, "((..)).........", **params)
+    assert b.molA.get("predicted") and not b.molB.get("predicted")
+    n, m = b.molA["len"], b.molB["len"]
+    for key in ("up", "down", "unp"):
+        assert len(b.molA[key]) == n + 1 and len(b.molB[key]) == m + 1
+    assert all(abs(u + d + p - 1.0) < 1e-12 for u, d, p in zip(b.molA["up"], b.molA["down"], b.molA["unp"]))
+    assert b.molB["down"][1:3] == [1.0, 1.0] and b.molB["up"][5:7] == [1.0, 1.0] and b.molB["unp"][0] == 1.0
+    mat = b._mu2_matrix()
+    assert mat.shape == (n, m) and mat.dtype == np.int32
+    assert all(mat[k - 1, l - 1] == b.mu2(k, l) for k in range(1, n + 1) for l in range(1, m + 1))
+    assert 0 < mat.max() <= 333 and (mat % 333 != 0).any()  # genuinely fractional similarities, truncated
+    sb = b.molA["sbpp"]
+    assert np.allclose(sb, sb.T) and np.allclose(sb[1:, 1:].sum(axis=1), 1.0)
+    # supplied structures only: no matrix, the class path is used
+    assert ba.BiAligner("GGGAAACCC", "GGAAACC", "(((...)))", "((...))", **params)._mu2_matrix() is None
+
+
+def test_rna_without_structure_needs_the_rna_module(monkeypatch):
+    """Like the reference (pyx:347), an RNA without a supplied structure imports ViennaRNA's `RNA` module and fails with
+    ImportError when it is not installed; proteins without structures print the reference's error and exit."""
+    import sys
+
+    monkeypatch.setitem(sys.modules, "RNA", None)
+    from bialign_b200 import bialignment as ba
+
+    params = dict(type="RNA", simmatrix=None, structure_weight=400, gap_opening_cost=-200, gap_cost=-50, shift_cost=-150,
+                  max_shift=1, sequence_match_similarity=100, sequence_mismatch_similarity=0)
+    with pytest.raises(ImportError):
+        ba.BiAligner("GGGAAACCC", "GGAAACC", None, None, **params)
