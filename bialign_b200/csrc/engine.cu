@@ -107,6 +107,8 @@ struct ba_engine {
     int opt_long = -1;                 // multi-CTA long-pair mode: -1 auto, 0 off, 1 force
     int opt_p16 = -1;                  // 16-bit pair mode for score-only batches: -1 auto, 0 off, 1 force
     int opt_na = -1;                   // non-affine model: -1 / 1 dedicated kernel when applicable, 0 systolic NA flavour
+    int opt_chain = -1;                // short pairs chained along j: -1 auto, 0 off, 1 force
+    DevBuf<int> d_chains;
     std::vector<int32_t> h_sim;
     int opt_warps = 0;                 // warps per CTA of the systolic kernel (0 = chosen per batch)
     int opt_pad = -1;                  // systolic flavour: -1 auto, 0 pad-free, 1 padded
@@ -311,7 +313,7 @@ void ba_engine_destroy(ba_engine* e) {
     e->d_scratch.release(); e->d_counter.release(); e->d_scores.release(); e->d_start.release();
     e->d_complete.release(); e->d_trace.release(); e->d_endv.release(); e->d_tlen.release(); e->h_stage.release();
     e->d_simp.release(); e->d_tbtab.release(); e->d_bnd.release(); e->d_progress.release();
-    e->d_mu2.release(); e->d_mu2_off.release();
+    e->d_mu2.release(); e->d_mu2_off.release(); e->d_chains.release();
     cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -335,6 +337,7 @@ int ba_set_option(ba_engine* e, const char* key, int64_t value) {
     else if (!strcmp(key, "long")) return tri(&e->opt_long);
     else if (!strcmp(key, "p16")) return tri(&e->opt_p16);
     else if (!strcmp(key, "na_kernel")) return tri(&e->opt_na);
+    else if (!strcmp(key, "chain")) return tri(&e->opt_chain);
     else if (!strcmp(key, "warps_per_cta")) {
         if (value < 0 || value > 8) return fail(e, BA_ERR_INVALID_ARG, "warps_per_cta must be in 0..8 (0 = auto)");
         e->opt_warps = (int)value;
@@ -519,7 +522,8 @@ int ba_run(ba_engine* e, int want_trace) {
     // ---- kernel choice: systolic when its exactness conditions hold, else the generic level kernel
     SysPlan plan;
     bool p16 = false;
-    if (e->opt_kernel != 0 && affine && !want_trace && e->opt_p16 != 0 && e->opt_pad != 1 && N >= 2 && !e->have_mu2 && !wide) {
+    if (e->opt_kernel != 0 && affine && !want_trace && e->opt_p16 != 0 && e->opt_pad != 1 && N >= 2 && !e->have_mu2 && !wide &&
+        !(e->opt_chain == 1 && e->opt_p16 != 1)) {  // a forced chained flavour keeps the 32-bit kernel
         plan = plan_systolic(e, nmax, mmax, false, true);  // do the scores provably fit 16 bits?
         p16 = plan.ok;
     }
@@ -619,6 +623,28 @@ int ba_run(ba_engine* e, int want_trace) {
             p16 = false;
         }
     }
+    // Short pairs: when every pair fits ONE row block of a CTA of at most 8 warps, chains of pairs run back to back through
+    // the systolic array (CHAIN flavour): the pipeline skew is paid per chain, not per pair.
+    bool chain_mode = false;
+    constexpr int kChainBudget = 3072;  // staged-B bytes of one chain (sum of m + 2s + 6 over its pairs)
+    if (kernel == 1 && !na_ded && affine && !p16 && !plan.pad && plan.bneg && e->opt_chain != 0 && e->opt_long != 1 && N >= 2 &&
+        mmax + 2 * s + 6 <= kChainBudget) {
+        const SysGeo geo = sys_geo(s, false);
+        const int minG = (12 * geo.LPR + 31) / 32;
+        const int Gc = std::max({(nmax + geo.R) / geo.R, minG, e->opt_warps});  // ceil((nmax+1)/R) rows in one block
+        if (Gc <= 8) {
+            const size_t sm = sys_smem_bytes_chain(s, Gc, e->sc.nsym, sys_bpad(s, false, Gc, kChainBudget));
+            const int occ = sm > kSysSmemLimit ? 0 : sys_occupancy_chain(s, want_trace != 0, Gc, sm);
+            if (occ >= 1) {
+                chain_mode = true;
+                sysG = Gc;
+                sys_smem = sm;
+                sys_occ = occ;
+            }
+        }
+    }
+    if (e->opt_chain == 1 && !chain_mode && N >= 2)
+        return fail(e, BA_ERR_INVALID_ARG, "chained short-pair mode requested but not applicable (a pair needs several row blocks, or another flavour is forced)");
     // Code words of one pair: the level kernel uses the cell-major table of common.cuh; the systolic kernel writes in the
     // order it computes -- [row block][warp][iteration][lane], 256 contiguous bytes per warp and iteration -- so its table
     // also holds the skewed pipeline's idle slots (about 10-15 % more memory, 15x fewer store transactions).
@@ -694,6 +720,26 @@ int ba_run(ba_engine* e, int want_trace) {
         wave_begin.push_back(N);
     }
     const int n_waves = (int)wave_begin.size() - 1;
+    std::vector<int> h_chains;          // per wave: chain start indices (relative to the wave's first pair), one extra end entry
+    std::vector<int64_t> chain_begin;   // per wave: offset of its entries in h_chains
+    if (chain_mode) {
+        for (int w = 0; w < n_waves; ++w) {
+            chain_begin.push_back((int64_t)h_chains.size());
+            const int64_t b = wave_begin[w], cnt = wave_begin[w + 1] - b;
+            int64_t q = 0;
+            while (q < cnt) {
+                h_chains.push_back((int)q);
+                int used = 0, len = 0;
+                while (q < cnt && len < BA_KCHAIN && used + e->h_desc[b + q].m + 2 * s + 6 <= kChainBudget) {
+                    used += e->h_desc[b + q].m + 2 * s + 6;
+                    ++len;
+                    ++q;
+                }
+            }
+            h_chains.push_back((int)cnt);
+        }
+        chain_begin.push_back((int64_t)h_chains.size());
+    }
     lap("arena + waves");
 
     // ---- buffers
@@ -748,7 +794,7 @@ int ba_run(ba_engine* e, int want_trace) {
         }
         // Few, long pairs: spread the row blocks of each pair over the whole grid (LONG flavour, cooperative launch)
         const int npass_max = (nmax + rows_pass) / rows_pass;
-        if (!p16 && affine && plan.bneg && e->opt_long != 0 && npass_max >= 2 && sysG >= 2 &&
+        if (!chain_mode && !p16 && affine && plan.bneg && e->opt_long != 0 && npass_max >= 2 && sysG >= 2 &&
             (e->opt_long == 1 || (N <= 4 && npass_max >= 8))) {
             const int occl = sys_occupancy_long(s, want_trace != 0, plan.pad, sysG, sys_smem);
             int coop = 0;
@@ -776,7 +822,11 @@ int ba_run(ba_engine* e, int want_trace) {
         SA.k_2g2d = (int)((2 * e->sc.gamma + 2 * e->sc.delta) / plan.g * sh); SA.k_2d = (int)(2 * e->sc.delta / plan.g * sh);
         SA.k_d = (int)(e->sc.delta / plan.g * sh);
         SA.negp = plan.negp; SA.tb_bits = plan.tb; SA.gscale = plan.g; SA.mmax = mmax;
-        SA.boff = sys_boff(s, plan.pad, sysG); SA.bpad = sys_bpad(s, plan.pad, sysG, mmax);
+        SA.boff = sys_boff(s, plan.pad, sysG); SA.bpad = sys_bpad(s, plan.pad, sysG, chain_mode ? kChainBudget : mmax);
+        if (chain_mode) {
+            CU(e->d_chains.ensure(h_chains.size()));
+            CU(cudaMemcpyAsync(e->d_chains.p, h_chains.data(), sizeof(int) * h_chains.size(), cudaMemcpyHostToDevice, e->stream));
+        }
         SA.progress = e->d_progress.p;
         {   // Flag period of the long-pair pipeline.  Many row blocks (a CTA per block, several per SM): a flag exchange costs an
             // extra barrier and a spinning thread, so it is rare (default, ~32 iterations).  Few row blocks (one CTA per SM, the pair is
@@ -842,6 +892,10 @@ int ba_run(ba_engine* e, int want_trace) {
         } else if (kernel == 1 && !affine) {
             SA.pairs = e->d_desc.p + b; SA.npairs = (int)cnt; SA.counter = e->d_counter.p + w;
             CU(launch_fill_systolic_na(SA, grid, sysG, sys_smem, want_trace != 0, plan.pad, e->stream));
+        } else if (kernel == 1 && chain_mode) {
+            const int nch = (int)(chain_begin[w + 1] - chain_begin[w]) - 1;
+            SA.pairs = e->d_desc.p + b; SA.npairs = nch; SA.chains = e->d_chains.p + chain_begin[w]; SA.counter = e->d_counter.p + w;
+            CU(launch_fill_systolic_chain(SA, std::min(nch, max_grid), sysG, sys_smem, want_trace != 0, e->stream));
         } else if (kernel == 1) {
             SA.pairs = e->d_desc.p + b; SA.npairs = (int)cnt; SA.counter = e->d_counter.p + w;
             CU(launch_fill_systolic(SA, grid, sysG, sys_smem, want_trace != 0, plan.pad, plan.bneg, e->stream));
@@ -892,7 +946,7 @@ int ba_run(ba_engine* e, int want_trace) {
         e->stats.code_bytes = cb;
     }
     e->stats.waves = n_waves;
-    e->stats.kernel_kind = kernel == 0 ? (wide ? 9 : 0) : na_ded ? 8 : (p16 ? 5 : !affine ? (plan.pad ? 7 : 6) : (plan.pad ? 2 : 1) + (long_mode ? 2 : 0));
+    e->stats.kernel_kind = kernel == 0 ? (wide ? 9 : 0) : na_ded ? 8 : chain_mode ? 10 : (p16 ? 5 : !affine ? (plan.pad ? 7 : 6) : (plan.pad ? 2 : 1) + (long_mode ? 2 : 0));
     e->stats.warps_per_cta = kernel == 0 ? 0 : sysG;
     e->last_fmt = kernel;
     e->last_sysG = kernel == 1 ? sysG : 0;

@@ -263,10 +263,17 @@ struct Geo {
 // the double-shift columns 0110 / 1001 do not exist, pyx:250-252), and the tie-break is "first case in the order of
 // pyx:233-248": with TRACE the low 4 bits carry 15 - case index, attached at the target through the additive constants;
 // the code word of a cell is the case index of its best state (what the traceback of pyx:521-528 would pick).
-template <int S, bool TRACE, bool PAD, bool BNEG, bool LONG, bool P16 = false, bool NA = false>
+//
+// CHAIN = short pairs (every pair fits one row block): a work item is a CHAIN of up to KCHAIN pairs that run back to back through
+// the systolic array along the j axis, separated by one dead column, so the 2-iterations-per-row pipeline skew is paid once per
+// chain instead of once per pair.  Every lane switches to the next pair of the chain on its own when it passes the dead column
+// (its row of A, its validity, its slice of the staged B molecules, its code stream); steady blocks are agreed by a warp vote.
+constexpr int KCHAIN = BA_KCHAIN;
+template <int S, bool TRACE, bool PAD, bool BNEG, bool LONG, bool P16 = false, bool NA = false, bool CHAIN = false>
 __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
     static_assert(!P16 || (!TRACE && !PAD && BNEG && !LONG), "16-bit pair mode: score only, pad-free, beta < 0, batch mode");
     static_assert(!NA || (BNEG && !LONG && !P16), "non-affine flavour: batch mode, 32-bit");
+    static_assert(!CHAIN || (!PAD && BNEG && !LONG && !P16 && !NA), "chained short pairs: plain pad-free affine flavour");
     using G_ = Geo<S, PAD>;
     constexpr int W = G_::W, P = G_::P, LPR = G_::LPR, R = G_::R, RING = G_::RING, NVR = G_::NVR, PB = G_::PB;
     constexpr bool SELFREG = G_::SELFREG;
@@ -293,6 +300,8 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
     uint8_t* sresB_hi = sclsB + bpad;   // P16 only: molecule B of the second pair
     uint8_t* sclsB_hi = sresB_hi + bpad;
     __shared__ int s_pair;
+    __shared__ PairDesc s_cd[CHAIN ? KCHAIN : 1];  // CHAIN: the pairs of the current chain
+    __shared__ int s_seg[CHAIN ? KCHAIN + 1 : 1];  //        and where position l = 0 of each one's molecule B sits in sresB / sclsB
 
     const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
     const int r = lane / LPR, c = lane - r * LPR;
@@ -353,9 +362,22 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
             if (pi >= A.npairs) return;
         }
         PairDesc d, dh;  // dh: second pair of a P16 work item (dh.orig < 0: none, the first pair is computed twice)
+        int K = 1;       // CHAIN: pairs in this chain
         if (P16) {
             d = A.pairs[2 * pi];
             dh = A.pairs[2 * pi + 1];
+        } else if (CHAIN) {
+            const int first = A.chains[pi];
+            K = A.chains[pi + 1] - first;
+            if (tid < K) s_cd[tid] = A.pairs[first + tid];
+            __syncthreads();
+            if (tid == 0) {  // B segments: front slack, then per pair its columns with a guard of S + 3 on either side
+                int at = boff;
+                for (int kk = 0; kk < K; ++kk) { s_seg[kk] = at; at += s_cd[kk].m + 2 * S + 6; }
+                s_seg[K] = at;  // the "no more pairs" state of a lane reads the tail slack
+            }
+            d = s_cd[0];
+            dh = d;
         } else {
             d = A.pairs[pi];
             dh = d;
@@ -366,6 +388,15 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
         const uint8_t* ra_hi = A.res + dh.offA;
         const uint8_t* ca_hi = A.cls + dh.offA;
         // stage molecule B (bytes); 1-based position l -> sclsB[l + boff]; 255 (B) / 254 (A) never match
+        if (CHAIN) {
+            for (int q = tid; q < bpad; q += blockDim.x) { sresB[q] = 0; sclsB[q] = 255; }
+            __syncthreads();
+            for (int kk = 0; kk < K; ++kk)
+                for (int l = 1 + tid; l <= s_cd[kk].m; l += blockDim.x) {
+                    sresB[s_seg[kk] + l] = A.res[s_cd[kk].offB + l - 1];
+                    sclsB[s_seg[kk] + l] = A.cls[s_cd[kk].offB + l - 1];
+                }
+        } else
         for (int q = tid; q < bpad; q += blockDim.x) {
             const int l = q - boff;
             sresB[q] = (l >= 1 && l <= d.m) ? A.res[d.offB + l - 1] : 0;
@@ -377,8 +408,12 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
         }
         __syncthreads();
 
-        const int npass = (n + RT) / RT;  // ceil((n+1)/RT)
-        const int nit = (m + 1) * P + 2 * (RT - 1) + LPR + RING;
+        const int npass = CHAIN ? 1 : (n + RT) / RT;  // ceil((n+1)/RT)
+        int nit = (m + 1) * P + 2 * (RT - 1) + LPR + RING;
+        if (CHAIN) {  // all pairs of the chain back to back, one dead column after each
+            nit = 2 * (RT - 1) + LPR + RING;
+            for (int kk = 0; kk < K; ++kk) nit += (s_cd[kk].m + 2) * P;
+        }
         const size_t bstride = (size_t)A.bnd_iters * REC;  // ints per boundary buffer
         int* bnd_base = A.bnd + (LONG ? (size_t)0 : (size_t)blockIdx.x * 2 * bstride);
         const int NC = gridDim.x;
@@ -386,9 +421,11 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
         for (int pass = LONG ? (int)blockIdx.x : 0; pass < npass; pass += LONG ? NC : 1) {
             const int i = pass * RT + g * R + r;
             const int k = i + a;
-            const bool lane_ok = lane_real && i <= d.n && k >= 0 && k <= d.n;
+            // per-pair lane state (constant over a pass, except in CHAIN mode where a lane moves from pair to pair)
+            int cur_n = d.n, cur_m = d.m, cur_orig = d.orig, kidx = 0, bofs = boff;
+            bool lane_ok = lane_real && i <= d.n && k >= 0 && k <= d.n;
             const int Ai = (lane_ok && i >= 1) ? ra[i - 1] : nsym;  // zero row for i = 0
-            const int Ak = (lane_ok && k >= 1) ? ca[k - 1] : 254;
+            int Ak = (lane_ok && k >= 1) ? ca[k - 1] : 254;
             const int* simrow = ssim + Ai * nsym;
             const bool lane_ok_hi = P16 && lane_real && i <= dh.n && k >= 0 && k <= dh.n;
             const int Ak_hi = (lane_ok_hi && k >= 1) ? ca_hi[k - 1] : 254;
@@ -456,8 +493,14 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
             // cell-major layout costs one 32-byte sector per lane).  Every lane stores in every iteration: slots of lanes
             // or iterations outside the pair are simply never read (sys_code_index, kernels.cuh).
             uint64_t* cw = nullptr;  // this lane's slot of the current iteration
-            if (TRACE) cw = A.codes + d.code_off + ((long long)pass * G + g) * (long long)(nit + PRE) * 32 + lane;
+            if (TRACE) cw = A.codes + d.code_off + ((long long)pass * G + g) * (long long)((m + 1) * P + 2 * (RT - 1) + LPR + RING + PRE) * 32 + lane;
 
+            // plain affine flavour: a lane at k = 0 poisons its x2 = 1 cases itself (their sources sit at k = -1, lanes that
+            // are outside the pair and, in steady blocks, not masked), so the first rows of a pair can run steady blocks too
+            constexpr bool K0FIX = !P16 && !NA && !PAD;
+            const int pK0 = (K0FIX && k == 0) ? NEGP : 0;
+            const int pWk = K0FIX ? ((c == 0 || k == 0) ? NEGP : 0) : pW;
+            const int k2Gk = k2G + pK0, kGDk = kGD + pK0;
             // Steady range of this warp [st_lo, st_hi): every lane of the warp has S < j <= m - max(S,1) throughout
             // (all range tests true, no origin / end cell), the staged records exist, and no lane of the warp
             // is a band offset below row 0 (k < 0, first rows of the first pass: their cells ARE read, as "minus infinity").
@@ -468,7 +511,7 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
                 st_lo = (S + 1) * P + sig_hi;
                 st_hi = (m_eff - (S > 0 ? S : 1) + 1) * P + sig_lo;
                 if (has_in) st_hi = min(st_hi, q_rec_lim - LA);
-                if (pass == 0 && g * R < S) st_hi = st_lo;
+                if (!K0FIX && pass == 0 && g * R < S) st_hi = st_lo;
             }
 
             // position of this lane one iteration before the first one (q = -PRE)
@@ -535,8 +578,25 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
                     wslot = (wslot + 1 == RING) ? 0 : wslot + 1;
                     pslot = (pslot + 1 == PB) ? 0 : pslot + 1;
                 }
+                if constexpr (CHAIN && !ST) {
+                    if (bb == 0 && j >= cur_m + 2) {  // past the dead column: this lane enters the next pair of the chain
+                        ++kidx;
+                        j = 0;
+                        if (kidx < K) {
+                            const PairDesc& dn = s_cd[kidx];
+                            cur_n = dn.n; cur_m = dn.m; cur_orig = dn.orig;
+                            lane_ok = lane_real && i <= dn.n && k >= 0 && k <= dn.n;
+                            simrow = ssim + ((lane_ok && i >= 1) ? A.res[dn.offA + i - 1] : nsym) * nsym;
+                            Ak = (lane_ok && k >= 1) ? A.cls[dn.offA + k - 1] : 254;
+                            if (TRACE) cw = A.codes + dn.code_off + ((long long)g * ((dn.m + 1) * P + 2 * (RT - 1) + LPR + RING + PRE) + sigma + PRE) * 32 + lane;
+                        } else {  // no more pairs: idle until the array has drained
+                            cur_n = -1; cur_m = 0x3fffffff; lane_ok = false; simrow = ssim + nsym * nsym; Ak = 254;
+                        }
+                        bofs = s_seg[kidx < K ? kidx : K];
+                    }
+                }
                 const int l = j + bb - S;
-                const bool valid = ST || (lane_ok && (bb < W) && ((unsigned)j <= (unsigned)d.m) && ((unsigned)l <= (unsigned)d.m));
+                const bool valid = ST || (lane_ok && (bb < W) && ((unsigned)j <= (unsigned)cur_m) && ((unsigned)l <= (unsigned)cur_m));
                 int vmask = 0, nmask = 0;  // P16: per-half validity
                 if (P16 && !ST) {
                     const bool valid_hi = lane_ok_hi && (bb < W) && ((unsigned)j <= (unsigned)dh.m) && ((unsigned)l <= (unsigned)dh.m);
@@ -545,14 +605,14 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
                 }
 
                 // ---- similarity inputs of the target cell (mu1 changes once per column)
-                const int cB = sclsB[l + boff];
+                const int cB = sclsB[l + bofs];
                 int mu2;
                 if (P16) {
                     const int cBh = sclsB_hi[l + boff];
                     if (bb == 0) mu1 = (simrow[sresB[j + boff]] & 0xffff) | (simrow_hi[sresB_hi[j + boff]] << 16);
                     mu2 = ((cB == Ak) ? wlo : 0) | ((cBh == Ak_hi) ? whi : 0);
                 } else {
-                    if (bb == 0) mu1 = simrow[sresB[j + boff]];
+                    if (bb == 0) mu1 = simrow[sresB[j + bofs]];
                     mu2 = (cB == Ak) ? A.w_p : 0;
                 }
 
@@ -643,7 +703,8 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
                     lds64o_if<XA * 4>(inF[5], inF[4], xsi_b - 8 * c + s2 * XSLOTB, row0);
                     lds128o_if<16>(inF[3], inH1[3], inH1[4], inH1[5], xsi_b + s1 * XSLOTB, row0);
                     // origin: M[1111][0,0,0,0] = 0 (pyx:485) enters as the F input of state 1111 (mu1 = mu2 = 0 there)
-                    if (q == q_origin) inF[8] = 0;
+                    // (the origin lane sits at k = 0, whose x2 = 1 cases carry the poison pK0: cancel it for this one input)
+                    if (CHAIN ? (i == 0 && a == 0 && j == 0 && bb == S) : (q == q_origin)) inF[8] = -pK0;
                 }
 
                 // ---- additive constants per case (affine_score minus its gap-opening part), with the poisons
@@ -691,21 +752,21 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
                     kh1[2] = mu1 + A.k_d + pU1 + pB1 + T_ * (15 - 3);  // x=1100  case 3: mu1 + Delta
                 } else {
                     kF[0] = k2G;                       // x=0101
-                    kF[1] = k2G2D + pW + pB1;          // x=0110
-                    kF[2] = mu2 + kGD + pW;            // x=0111
+                    kF[1] = k2G2D + pWk + pB1;         // x=0110
+                    kF[2] = mu2 + kGD + pWk;           // x=0111
                     kF[3] = k2G2D + pU1 + pB0;         // x=1001
-                    kF[4] = k2G;                       // x=1010
-                    kF[5] = mu2 + kGD + pB0;           // x=1011
+                    kF[4] = k2Gk;                      // x=1010   (x0 = x2 = 1: source at k - 1)
+                    kF[5] = mu2 + kGDk + pB0;          // x=1011
                     kF[6] = mu1 + kGD + pU1;           // x=1101
-                    kF[7] = mu1 + kGD + pB1;           // x=1110
-                    kF[8] = mu1 + mu2;                 // x=1111
+                    kF[7] = mu1 + kGDk + pB1;          // x=1110
+                    kF[8] = mu1 + mu2 + pK0;           // x=1111
                     // half-column cases also re-base the id field of the winner they carry (TRACE): a full-column
                     // source has field 27 - src (19..27); -10 maps the (t01, h) sources of x=(0,0,t2,t3) to 9..17 and
                     // -19 the (h, t23) sources of x=(t0,t1,0,0) to 0..8, so on equal tie keys the three groups keep the
                     // reference's case order (ids 0-8 < 9-11 < 12-14) and the source stays decodable.
                     kh2[0] = kGD + ADJ2 + pB0;             // x=0001
-                    kh2[1] = kGD + ADJ2 + pW;              // x=0010
-                    kh2[2] = mu2 + k2D + ADJ2 + pW + pB0;  // x=0011
+                    kh2[1] = kGD + ADJ2 + pWk;             // x=0010
+                    kh2[2] = mu2 + k2D + ADJ2 + pWk + pB0; // x=0011
                     kh1[0] = kGD + ADJ1 + pB1;             // x=0100
                     kh1[1] = kGD + ADJ1 + pU1;             // x=1000
                     kh1[2] = mu1 + k2D + ADJ1 + pU1 + pB1; // x=1100
@@ -721,7 +782,7 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
                 }
 
                 // ---- results at the end cell
-                if (!ST && q == q_end) {
+                if (!ST && (CHAIN ? (lane_ok && i == cur_n && a == 0 && j == cur_m && bb == S) : (q == q_end))) {
                     int Mv[9];  // plain values of the nine states (low half in 16-bit pair mode)
 #pragma unroll
                     for (int t = 0; t < 9; ++t) Mv[t] = P16 ? (int)(short)(M[t] & 0xffff) : (M[t] >> TB);
@@ -734,10 +795,10 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
                         const int t01 = t / 3, t23 = t % 3;
                         const int sh = (hb0(t01) != hb0(t23)) + (hb1(t01) != hb1(t23));
                         if (Mv[t] == best && sh < bsh) { bsh = sh; st = t; }
-                        A.end_values[(size_t)d.orig * 9 + t] = Mv[t] * A.gscale;
+                        A.end_values[(size_t)cur_orig * 9 + t] = Mv[t] * A.gscale;
                     }
-                    A.scores[d.orig] = (long long)best * A.gscale;
-                    A.start_state[d.orig] = (uint8_t)st;
+                    A.scores[cur_orig] = (long long)best * A.gscale;
+                    A.start_state[cur_orig] = (uint8_t)st;
                 }
 
                 if (P16 && !ST && q == q_end_hi) {  // the second pair of the work item ends at its own cell
@@ -768,7 +829,7 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
 #pragma unroll
                     for (int t = 6; t < 9; ++t) hi = __funnelshift_r(hi, (unsigned)M[t], 5);
                     if constexpr (ST) stg64o<u * 256>(cw, lo, hi);
-                    else { stg64o<0>(cw, lo, hi); cw += 32; }
+                    else { if (!CHAIN || kidx < K) stg64o<0>(cw, lo, hi); cw += 32; }
                     // table layout [source state][b][lane column]: for one source state the lanes of a warp read
                     // (at most P*LPR <= 32) consecutive words -> no bank conflicts
                     const int msk = ~((1 << TB) - 1);
@@ -932,7 +993,15 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
                     next_flag = q + lqb;
                     __syncthreads();
                 }
-                if (STEADY_OK && aligned && q >= st_lo && q + RING <= st_hi) {  // warp-uniform
+                bool steady = STEADY_OK && aligned && q >= st_lo && q + RING <= st_hi;  // warp-uniform
+                if (CHAIN && STEADY_OK && aligned) {
+                    // every lane of the warp stays strictly inside its current pair for the whole block (lanes are in
+                    // different pairs around a chain boundary, so the range cannot be precomputed per warp)
+                    const int posn = j * P + bb;  // position of the previous iteration
+                    const bool mine = kidx < K && posn + 1 >= (S + 1) * P && posn + RING <= (cur_m - (S > 0 ? S : 1) + 1) * P - 1;
+                    steady = __all_sync(0xffffffffu, mine);
+                }
+                if (steady) {
                     const int ph = (pslot + 1 == PB) ? 0 : pslot + 1;           // 0 or RING
                     pb_cur = pb_s + ph * RECB;
                     pb_oth = pb_s + (ph ? 0 : LA) * RECB;
@@ -1038,6 +1107,24 @@ template <int S>
 int occ_na_s(bool trace, bool pad, int G, size_t smem) {
     if (pad) return trace ? occ_na_t<S, true, true>(G, smem) : occ_na_t<S, false, true>(G, smem);
     return trace ? occ_na_t<S, true, false>(G, smem) : occ_na_t<S, false, false>(G, smem);
+}
+
+// CHAIN flavour: short pairs chained along j (pad-free, beta < 0)
+template <int S, bool TRACE>
+cudaError_t launch_chain_t(const SysArgs& A, int grid, int G, size_t smem, cudaStream_t st) {
+    auto kern = fill_systolic_kernel<S, TRACE, false, true, false, false, false, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, G * 32, smem, st>>>(A);
+    return cudaGetLastError();
+}
+template <int S, bool TRACE>
+int occ_chain_t(int G, size_t smem) {
+    auto kern = fill_systolic_kernel<S, TRACE, false, true, false, false, false, true>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, G * 32, smem);
+    return nb;
 }
 
 // LONG flavour: cooperative launch (all CTAs must be co-resident: they wait on one another)

@@ -13,7 +13,9 @@ namespace ba {
     cudaError_t launch_fill_systolic_p16_s##s(const SysArgs&, int, int, size_t, cudaStream_t);                          \
     int sys_occupancy_p16_s##s(int, size_t);                                                                            \
     cudaError_t launch_fill_systolic_na_s##s(const SysArgs&, int, int, size_t, bool, bool, cudaStream_t);               \
-    int sys_occupancy_na_s##s(bool, bool, int, size_t);
+    int sys_occupancy_na_s##s(bool, bool, int, size_t);                                                                 \
+    cudaError_t launch_fill_systolic_chain_s##s(const SysArgs&, int, int, size_t, bool, cudaStream_t);                  \
+    int sys_occupancy_chain_s##s(bool, int, size_t);
 DECL(0) DECL(1) DECL(2) DECL(3) DECL(4)
 #undef DECL
 
@@ -142,6 +144,38 @@ cudaError_t launch_fill_systolic_long(const SysArgs& A, int grid, int G, size_t 
         case 2: return launch_fill_systolic_long_s2(A, grid, G, smem, trace, pad, st);
         case 3: return launch_fill_systolic_long_s3(A, grid, G, smem, trace, pad, st);
         case 4: return launch_fill_systolic_long_s4(A, grid, G, smem, trace, pad, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+int sys_occupancy_chain(int S, bool trace, int G, size_t smem) {
+    switch (S) {
+        case 0: return sys_occupancy_chain_s0(trace, G, smem);
+        case 1: return sys_occupancy_chain_s1(trace, G, smem);
+        case 2: return sys_occupancy_chain_s2(trace, G, smem);
+        case 3: return sys_occupancy_chain_s3(trace, G, smem);
+        default: return sys_occupancy_chain_s4(trace, G, smem);
+    }
+}
+
+// shared memory of the chained flavour: the ordinary carve-up with one staged-B array of bpad_total bytes per kind
+size_t sys_smem_bytes_chain(int S, int G, int nsym, int bpad_total) {
+    switch (S) {
+        case 0: return sys_smem_bytes_s0(false, G, nsym, bpad_total, false);
+        case 1: return sys_smem_bytes_s1(false, G, nsym, bpad_total, false);
+        case 2: return sys_smem_bytes_s2(false, G, nsym, bpad_total, false);
+        case 3: return sys_smem_bytes_s3(false, G, nsym, bpad_total, false);
+        default: return sys_smem_bytes_s4(false, G, nsym, bpad_total, false);
+    }
+}
+
+cudaError_t launch_fill_systolic_chain(const SysArgs& A, int grid, int G, size_t smem, bool trace, cudaStream_t st) {
+    switch (A.sc.s) {
+        case 0: return launch_fill_systolic_chain_s0(A, grid, G, smem, trace, st);
+        case 1: return launch_fill_systolic_chain_s1(A, grid, G, smem, trace, st);
+        case 2: return launch_fill_systolic_chain_s2(A, grid, G, smem, trace, st);
+        case 3: return launch_fill_systolic_chain_s3(A, grid, G, smem, trace, st);
+        case 4: return launch_fill_systolic_chain_s4(A, grid, G, smem, trace, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -20,4 +20,8 @@ cudaError_t launch_fill_systolic_na_s2(const SysArgs& A, int grid, int G, size_t
     return sys::launch_na_s<2>(A, grid, G, smem, trace, pad, st);
 }
 int sys_occupancy_na_s2(bool trace, bool pad, int G, size_t smem) { return sys::occ_na_s<2>(trace, pad, G, smem); }
+cudaError_t launch_fill_systolic_chain_s2(const SysArgs& A, int grid, int G, size_t smem, bool trace, cudaStream_t st) {
+    return trace ? sys::launch_chain_t<2, true>(A, grid, G, smem, st) : sys::launch_chain_t<2, false>(A, grid, G, smem, st);
+}
+int sys_occupancy_chain_s2(bool trace, int G, size_t smem) { return trace ? sys::occ_chain_t<2, true>(G, smem) : sys::occ_chain_t<2, false>(G, smem); }
 }  // namespace ba

@@ -20,4 +20,8 @@ cudaError_t launch_fill_systolic_na_s3(const SysArgs& A, int grid, int G, size_t
     return sys::launch_na_s<3>(A, grid, G, smem, trace, pad, st);
 }
 int sys_occupancy_na_s3(bool trace, bool pad, int G, size_t smem) { return sys::occ_na_s<3>(trace, pad, G, smem); }
+cudaError_t launch_fill_systolic_chain_s3(const SysArgs& A, int grid, int G, size_t smem, bool trace, cudaStream_t st) {
+    return trace ? sys::launch_chain_t<3, true>(A, grid, G, smem, st) : sys::launch_chain_t<3, false>(A, grid, G, smem, st);
+}
+int sys_occupancy_chain_s3(bool trace, int G, size_t smem) { return trace ? sys::occ_chain_t<3, true>(G, smem) : sys::occ_chain_t<3, false>(G, smem); }
 }  // namespace ba

@@ -39,7 +39,8 @@ struct SysArgs {
     int mmax;                 // longest molecule B of the wave
     int boff, bpad;           // front offset / total size of the staged molecule-B arrays
     const PairDesc* pairs;
-    int npairs;
+    int npairs;               // work items: pairs, or chains of pairs (CHAIN flavour)
+    const int* chains;        // CHAIN flavour: chain c = pairs[chains[c] .. chains[c+1])
     int* counter;
     unsigned long long* progress;  // LONG flavour: one progress flag per boundary stream (2 * grid)
     int* bnd;                 // per CTA: two boundary streams of bnd_iters records
@@ -113,6 +114,11 @@ __host__ __device__ __forceinline__ long long na_code_index(int S, int G, int ni
     return (((long long)pass * G + g) * nit_all + qq) * 32 + lane;
 }
 int sys_occupancy_long(int S, bool trace, bool pad, int G, size_t smem);
+// chained short pairs (pad-free affine flavour); bpad_total = bytes of one staged-B array incl. all slack
+constexpr int BA_KCHAIN = 16;
+int sys_occupancy_chain(int S, bool trace, int G, size_t smem);
+size_t sys_smem_bytes_chain(int S, int G, int nsym, int bpad_total);
+cudaError_t launch_fill_systolic_chain(const SysArgs& A, int grid, int G, size_t smem, bool trace, cudaStream_t st);
 cudaError_t launch_fill_systolic_long(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, cudaStream_t st);
 
 }  // namespace ba

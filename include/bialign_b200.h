@@ -66,7 +66,8 @@ typedef struct ba_stats {
                                  5 = systolic pad-free, two pairs per lane in packed 16-bit halves,
                                  6 / 7 = systolic pad-free / padded running the non-affine model,
                                  8 = dedicated non-affine kernel (a lane owns a row and all its band offsets),
-                                 9 = general level kernel, 64-bit values (score bound >= 2^30)               */
+                                 9 = general level kernel, 64-bit values (score bound >= 2^30),
+                                 10 = systolic pad-free, short pairs chained along j (every pair fits one row block) */
     int32_t device;
     int32_t warps_per_cta;    /* CTA width the systolic kernel ran with (0 for the general kernel)      */
     int32_t reserved;
@@ -132,7 +133,8 @@ BA_API int ba_get_stats(const ba_engine* e, ba_stats* out);
  * "kernel" (0 generic, 1 systolic, -1 auto), "pad" (systolic flavour: 0 pad-free, 1 padded, -1 auto),
  * "warps_per_cta" (1..8, 0 = chosen per batch), "long" (multi-CTA long-pair mode: 0 off, 1 force, -1 auto),
  * "p16" (16-bit pair mode for score-only batches: 0 off, 1 force, -1 auto),
- * "na_kernel" (non-affine model: 0 = systolic kernel's non-affine flavour, 1 / -1 = dedicated kernel when applicable). */
+ * "na_kernel" (non-affine model: 0 = systolic kernel's non-affine flavour, 1 / -1 = dedicated kernel when applicable),
+ * "chain" (batches of short pairs run as chains through the systolic array: 0 off, 1 force, -1 auto). */
 BA_API int ba_set_option(ba_engine* e, const char* key, int64_t value);
 
 /* Test hook: copy the raw 4-bit code table of pair p of the last wave (uint64 per cell, index

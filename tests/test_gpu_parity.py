@@ -142,6 +142,7 @@ def _select(al, kind):
     """kind 0 = generic level kernel, 1 = systolic pad-free, 2 = systolic padded."""
     al.set_option("kernel", 0 if kind == 0 else 1)
     al.set_option("pad", -1 if kind == 0 else kind - 1)
+    al.set_option("chain", 0)  # the chained short-pair flavour has its own test
 
 
 def _unselect(al):
@@ -408,7 +409,7 @@ def test_score_only_16bit_pair_mode(s):
             assert al.engine.stats()["kernel_kind"] == 5
             al.set_option("p16", 0)
             s32 = al.align(seqs, structs, pairs, want_trace=False)
-            assert al.engine.stats()["kernel_kind"] in (1, 2)
+            assert al.engine.stats()["kernel_kind"] in (1, 2, 10)
         finally:
             _unselect(al)
         assert (s16 == s32).all()
@@ -624,3 +625,33 @@ def test_probabilistic_structure_similarity_matches_reference(monkeypatch):
         assert "".join("%x" % (8 * x[0] + 4 * x[1] + 2 * x[2] + x[3]) for x in tr) == c["trace"]
         assert [[n, r] for n, r in b.decode_trace_full(tr)] == c["full"]
         assert list(b.eval_trace(tr))[-2:] == c["eval_tail"]
+
+
+@pytest.mark.parametrize("s", [0, 1, 2, 3])
+def test_chained_short_pairs_vs_oracle(s):
+    """Batches of pairs that each fit one row block run as chains through the systolic array (kernel_kind 10): every lane
+    moves from pair to pair on its own.  Ragged lengths incl. empty molecules, more pairs than one chain holds, tie storms;
+    scores, traces, end values and the code table of every reachable cell-state against the oracle, and against chain = 0."""
+    rng = np.random.default_rng(4100 + s)
+    hi = {0: 30, 1: 60, 2: 40, 3: 28}[s]
+    for var in ({}, {"shift_cost": 0, "gap_cost": 0}, {"structure_weight": 0}):
+        params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150, gap_cost=-50,
+                      shift_cost=-150, max_shift=s)
+        params.update(var)
+        seqs, structs, pairs = _random_protein_batch(rng, 70, 1, hi)
+        for q in (3, 11):  # empty molecules inside a chain
+            seqs[2 * q] = ""
+            structs[2 * q] = ""
+        seqs[2 * 20 + 1] = ""
+        structs[2 * 20 + 1] = ""
+        pairs = [p for p in pairs if len(seqs[p[0]]) or len(seqs[p[1]])]  # (both empty: the reference raises, pyx:407)
+        al = _aligner(params)
+        al.set_option("chain", 1)
+        kind = _check_batch(al, seqs, structs, pairs, params, table_pairs=len(pairs))
+        assert kind == 10
+        chained = al.align(seqs, structs, pairs, want_trace=True)
+        al.set_option("chain", 0)
+        plain = al.align(seqs, structs, pairs, want_trace=True)
+        assert al.engine.stats()["kernel_kind"] in (1, 2)
+        for x, y in zip(chained, plain):
+            assert (x == y).all()
