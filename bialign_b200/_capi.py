@@ -16,14 +16,14 @@ SYMBOLS = ["ba_engine_create", "ba_engine_destroy", "ba_last_error", "ba_set_sco
            "ba_version", "ba_engine_create_multi", "ba_engine_device_count", "ba_set_pair_mu2"]
 
 
-ENGINE_OPTIONS = {"kernel": -1, "pad": -1, "long": -1, "p16": -1, "na_kernel": -1, "chain": -1, "warps_per_cta": 0, "code_arena_bytes": 0}
+ENGINE_OPTIONS = {"kernel": -1, "pad": -1, "long": -1, "p16": -1, "na_kernel": -1, "chain": -1, "rebase": -1, "rebase_window": 0, "warps_per_cta": 0, "code_arena_bytes": 0}
 
 
 class BaStats(ctypes.Structure):
     _fields_ = [("pairs", ctypes.c_int64), ("cell_states", ctypes.c_int64), ("kernel_launches", ctypes.c_int64),
                 ("waves", ctypes.c_int64), ("fill_ms", ctypes.c_double), ("traceback_ms", ctypes.c_double),
                 ("total_ms", ctypes.c_double), ("code_bytes", ctypes.c_int64), ("kernel_kind", ctypes.c_int32),
-                ("device", ctypes.c_int32), ("warps_per_cta", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("device", ctypes.c_int32), ("warps_per_cta", ctypes.c_int32), ("fallback_pairs", ctypes.c_int32)]
 
 
 class BialignError(RuntimeError):

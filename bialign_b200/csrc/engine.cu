@@ -109,6 +109,12 @@ struct ba_engine {
     int opt_na = -1;                   // non-affine model: -1 / 1 dedicated kernel when applicable, 0 systolic NA flavour
     int opt_chain = -1;                // short pairs chained along j: -1 auto, 0 off, 1 force
     DevBuf<int> d_chains;
+    int opt_rebase = -1;               // rebased wide-range trace runs: -1 auto (when the packed plan fails), 0 off, 1 force
+    int64_t opt_rebase_window = 0;     // test hook: cap on the rebased window (scaled score units below a row's maximum), 0 = none
+    DevBuf<int> d_rowmax, d_simp1;
+    DevBuf<long long> d_row_off;
+    DevBuf<uint8_t> d_suspect;
+    DevBuf<PairDesc> d_desc2;          // pairs recomputed by the level kernel after a rebased run
     std::vector<int32_t> h_sim;
     int opt_warps = 0;                 // warps per CTA of the systolic kernel (0 = chosen per batch)
     int opt_pad = -1;                  // systolic flavour: -1 auto, 0 pad-free, 1 padded
@@ -168,6 +174,8 @@ struct SysPlan {
     bool ok = false;
     bool pad = true, bneg = false;   // kernel flavour (fill_systolic.cuh)
     int g = 1, tb = 0, negp = 0;
+    int64_t colabs = 0;              // bound on what one column (plus tie adjustments) adds, scaled units
+    int df_max = 0;                  // rebased plan: bound on the row-potential steps it allows for
     std::vector<int> sim_p, tbtab;
 };
 
@@ -204,6 +212,7 @@ SysPlan plan_systolic(const ba_engine* e, int nmax, int mmax, bool trace, bool b
     const int64_t Fn = len * (c1n + c2n + 2 * dn) / g + 2;
     const int64_t colabs = (c1p + c2p + c1n + c2n + 2 * dp + 2 * dn + 2 * std::llabs((long long)sc.beta)) / g + 64;  // one column + tie adjustments
     (void)c1p; (void)c2p;
+    pl.colabs = colabs;
     int kb = 0;
     while ((1 << kb) < (S + 2) * (S + 2)) ++kb;
     pl.tb = trace ? (nonaffine ? 4 : kb + 5) : 0;  // non-affine: 15 - case index of pyx:233-248
@@ -252,6 +261,28 @@ SysPlan plan_systolic(const ba_engine* e, int nmax, int mmax, bool trace, bool b
     }
     pl.ok = true;
     return pl;
+}
+
+// Plans of a rebased wide-range trace run (fill_systolic.cuh, REBASE): p1 = the ordinary score-only plan (exact values, no tie
+// bits), p2 = the TRACE launch in coordinates relative to the row maxima of the first: its values only need the window
+// [negv, 0] plus the usual slack, whatever the lengths.  False when either does not exist or the window would be too small
+// to be useful (fewer than 64 worst-case columns below a row's maximum).
+bool plan_rebase(const ba_engine* e, int nmax, int mmax, SysPlan& p1, SysPlan& p2) {
+    if (e->sc.beta >= 0 || e->opt_pad == 1) return false;
+    p1 = plan_systolic(e, nmax, mmax, false);
+    if (!p1.ok || p1.pad || !p1.bneg) return false;
+    // tie-break tables, scaled similarity table and bit budget: those of a trace plan for a pair short enough to have one
+    p2 = plan_systolic(e, 1, 1, true);
+    if (!p2.ok || p2.pad || !p2.bneg || p2.g != p1.g) return false;
+    const int64_t lim = (int64_t)1 << (31 - p2.tb);
+    const int64_t dfm = (2 * e->sc.s + 4) * p1.colabs;
+    int64_t negv = -((lim - 2 * p1.colabs - dfm - 64) / 3);
+    if (-negv < 64 * p1.colabs) return false;
+    if (e->opt_rebase_window > 0) negv = std::max<int64_t>(negv, -e->opt_rebase_window);
+    p2.negp = (int)(negv * ((int64_t)1 << p2.tb));
+    p2.colabs = p1.colabs;
+    p2.df_max = (int)std::min<int64_t>(dfm, 1 << 28);
+    return true;
 }
 
 }  // namespace
@@ -314,6 +345,7 @@ void ba_engine_destroy(ba_engine* e) {
     e->d_complete.release(); e->d_trace.release(); e->d_endv.release(); e->d_tlen.release(); e->h_stage.release();
     e->d_simp.release(); e->d_tbtab.release(); e->d_bnd.release(); e->d_progress.release();
     e->d_mu2.release(); e->d_mu2_off.release(); e->d_chains.release();
+    e->d_rowmax.release(); e->d_simp1.release(); e->d_row_off.release(); e->d_suspect.release(); e->d_desc2.release();
     cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -338,6 +370,11 @@ int ba_set_option(ba_engine* e, const char* key, int64_t value) {
     else if (!strcmp(key, "p16")) return tri(&e->opt_p16);
     else if (!strcmp(key, "na_kernel")) return tri(&e->opt_na);
     else if (!strcmp(key, "chain")) return tri(&e->opt_chain);
+    else if (!strcmp(key, "rebase")) return tri(&e->opt_rebase);
+    else if (!strcmp(key, "rebase_window")) {
+        if (value < 0) return fail(e, BA_ERR_INVALID_ARG, "rebase_window must be >= 0 (0 = the full window)");
+        e->opt_rebase_window = value;
+    }
     else if (!strcmp(key, "warps_per_cta")) {
         if (value < 0 || value > 8) return fail(e, BA_ERR_INVALID_ARG, "warps_per_cta must be in 0..8 (0 = auto)");
         e->opt_warps = (int)value;
@@ -539,6 +576,22 @@ int ba_run(ba_engine* e, int want_trace) {
         plan = SysPlan{};
     } else
     if (!p16 && e->opt_kernel != 0) plan = plan_systolic(e, nmax, mmax, want_trace != 0, false, !affine);
+    // Traces whose packed plan (value << tie bits in 32 bits) fails although the plain values fit: two launches, the second in
+    // coordinates relative to the row maxima recorded by the first (REBASE flavour); pairs it cannot vouch for are recomputed
+    // by the level kernel at the end of this function.
+    bool rebase = false;
+    SysPlan plan1;  // the score-only launch of a rebased run
+    // (also preferred over the padded flavour when only that one fits: measured 526 vs 437 GCUPS on 200-500 aa pairs)
+    if (want_trace && affine && !wide && !e->have_mu2 && e->opt_kernel != 0 && e->opt_rebase != 0 &&
+        (!plan.ok || e->opt_rebase == 1 || (plan.pad && e->opt_pad < 0))) {
+        SysPlan p2;
+        if (plan_rebase(e, nmax, mmax, plan1, p2)) {
+            plan = p2;
+            rebase = true;
+        }
+    }
+    if (e->opt_rebase == 1 && !rebase && want_trace)
+        return fail(e, BA_ERR_SCORE_RANGE, "rebased trace run requested but not applicable (model, range or window)");
     if (e->opt_kernel == 1 && !plan.ok)
         return fail(e, BA_ERR_SCORE_RANGE, "systolic kernel requested but its packed-integer range conditions do not hold");
     int kernel = plan.ok ? 1 : 0;
@@ -549,7 +602,7 @@ int ba_run(ba_engine* e, int want_trace) {
     int max_grid = e->sm_count * 2;
     size_t scratch_stride = 0, sys_smem = 0;
     int sysG = e->opt_warps;
-    SysArgs SA{};
+    SysArgs SA{}, SA1{};  // SA1: the score-only launch of a rebased run
     bool long_mode = false;
     int long_grid_max = 0, sys_occ = 0;
     if (na_ded) {
@@ -611,6 +664,7 @@ int ba_run(ba_engine* e, int want_trace) {
         while (sysG > minG && sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax, p16) > kSysSmemLimit) --sysG;
         sys_smem = sys_smem_bytes(s, plan.pad, sysG, e->sc.nsym, mmax, p16);
         sys_occ = sys_smem > kSysSmemLimit ? 0
+                        : rebase ? std::min(sys_occupancy_rebase(s, false, false, sysG, sys_smem), sys_occupancy_rebase(s, true, false, sysG, sys_smem))
                         : p16 ? sys_occupancy_p16(s, sysG, sys_smem)
                               : !affine ? sys_occupancy_na(s, want_trace != 0, plan.pad, sysG, sys_smem)
                                         : sys_occupancy(s, want_trace != 0, plan.pad, plan.bneg, sysG, sys_smem);
@@ -621,13 +675,14 @@ int ba_run(ba_engine* e, int want_trace) {
                 return fail(e, BA_ERR_CUDA, "systolic kernel does not fit on an SM (shared memory " + std::to_string(sys_smem) + ")");
             kernel = 0;
             p16 = false;
+            rebase = false;
         }
     }
     // Short pairs: when every pair fits ONE row block of a CTA of at most 8 warps, chains of pairs run back to back through
     // the systolic array (CHAIN flavour): the pipeline skew is paid per chain, not per pair.
     bool chain_mode = false;
     constexpr int kChainBudget = 3072;  // staged-B bytes of one chain (sum of m + 2s + 6 over its pairs)
-    if (kernel == 1 && !na_ded && affine && !p16 && !plan.pad && plan.bneg && e->opt_chain != 0 && e->opt_long != 1 && N >= 2 &&
+    if (kernel == 1 && !na_ded && affine && !p16 && !rebase && !plan.pad && plan.bneg && e->opt_chain != 0 && e->opt_long != 1 && N >= 2 &&
         mmax + 2 * s + 6 <= kChainBudget) {
         const SysGeo geo = sys_geo(s, false);
         const int minG = (12 * geo.LPR + 31) / 32;
@@ -747,7 +802,7 @@ int ba_run(ba_engine* e, int want_trace) {
     CU(e->d_scores.ensure((size_t)N));
     CU(e->d_start.ensure((size_t)N));
     CU(e->d_endv.ensure((size_t)N * 9));
-    CU(e->d_counter.ensure((size_t)std::max(n_waves, 1)));
+    CU(e->d_counter.ensure((size_t)std::max(2 * n_waves, 1)));
     if (want_trace) {
         CU(e->d_tlen.ensure((size_t)N));
         CU(e->d_complete.ensure((size_t)N));
@@ -796,7 +851,8 @@ int ba_run(ba_engine* e, int want_trace) {
         const int npass_max = (nmax + rows_pass) / rows_pass;
         if (!chain_mode && !p16 && affine && plan.bneg && e->opt_long != 0 && npass_max >= 2 && sysG >= 2 &&
             (e->opt_long == 1 || (N <= 4 && npass_max >= 8))) {
-            const int occl = sys_occupancy_long(s, want_trace != 0, plan.pad, sysG, sys_smem);
+            const int occl = rebase ? std::min(sys_occupancy_rebase(s, false, true, sysG, sys_smem), sys_occupancy_rebase(s, true, true, sysG, sys_smem))
+                                    : sys_occupancy_long(s, want_trace != 0, plan.pad, sysG, sys_smem);
             int coop = 0;
             cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
             if (occl >= 1 && coop) {
@@ -839,6 +895,29 @@ int ba_run(ba_engine* e, int want_trace) {
         SA.bnd = e->d_bnd.p; SA.bnd_iters = biters + 8;  // matches sys_boundary_ints: slack records in front
         SA.codes = want_trace ? e->d_codes.p : nullptr;
         SA.scores = e->d_scores.p; SA.start_state = e->d_start.p; SA.end_values = e->d_endv.p;
+        if (rebase) {
+            // row maxima of every pair (caller order), "minus infinity" until the score-only launch has raised them
+            std::vector<long long> roff((size_t)N);
+            long long rows = 0;
+            for (int64_t p = 0; p < N; ++p) { roff[p] = rows; rows += ln[p] + 1; }
+            CU(e->d_rowmax.ensure((size_t)rows));
+            CU(e->d_row_off.ensure((size_t)N));
+            CU(e->d_suspect.ensure((size_t)N));
+            CU(e->d_simp1.ensure(plan1.sim_p.size()));
+            CU(cudaMemcpyAsync(e->d_row_off.p, roff.data(), sizeof(long long) * N, cudaMemcpyHostToDevice, e->stream));
+            CU(cudaMemcpyAsync(e->d_simp1.p, plan1.sim_p.data(), plan1.sim_p.size() * 4, cudaMemcpyHostToDevice, e->stream));
+            CU(cudaMemsetAsync(e->d_rowmax.p, 0x80, sizeof(int) * (size_t)rows, e->stream));
+            CU(cudaMemsetAsync(e->d_suspect.p, 0, (size_t)N, e->stream));
+            CU(cudaStreamSynchronize(e->stream));  // roff is a local
+            SA.rowmax = e->d_rowmax.p; SA.row_off = e->d_row_off.p; SA.suspect = e->d_suspect.p; SA.df_max = plan.df_max;
+            SA1 = SA;
+            SA1.sim_p = e->d_simp1.p; SA1.tbtab = nullptr;
+            SA1.w_p = (int)(e->sc.w / plan1.g); SA1.beta_p = (int)(e->sc.beta / plan1.g);
+            SA1.k_gd = (int)((e->sc.gamma + e->sc.delta) / plan1.g); SA1.k_2g = (int)(2 * e->sc.gamma / plan1.g);
+            SA1.k_2g2d = (int)((2 * e->sc.gamma + 2 * e->sc.delta) / plan1.g); SA1.k_2d = (int)(2 * e->sc.delta / plan1.g);
+            SA1.k_d = (int)(e->sc.delta / plan1.g);
+            SA1.negp = plan1.negp; SA1.tb_bits = 0; SA1.codes = nullptr;
+        }
     } else {
         scratch_stride = generic_scratch_ints(nmax, s);  // sized for nine states; the non-affine kernel uses a ninth
         const int grid = (int)std::min<int64_t>(biggest_wave, max_grid);
@@ -853,7 +932,7 @@ int ba_run(ba_engine* e, int want_trace) {
         CU(e->d_desc.ensure((size_t)N + 1));
     }
     CU(cudaMemcpyAsync(e->d_desc.p, e->h_desc.data(), sizeof(PairDesc) * e->h_desc.size(), cudaMemcpyHostToDevice, e->stream));
-    CU(cudaMemsetAsync(e->d_counter.p, 0, sizeof(int) * n_waves, e->stream));
+    CU(cudaMemsetAsync(e->d_counter.p, 0, sizeof(int) * 2 * n_waves, e->stream));
 
     struct EventSet {  // destroyed on every exit path (the CU macro returns early on errors)
         std::vector<cudaEvent_t> v;
@@ -880,6 +959,13 @@ int ba_run(ba_engine* e, int want_trace) {
                 const int lg = std::min(long_grid_max, npass);
                 CU(cudaMemsetAsync(e->d_progress.p, 0, sizeof(unsigned long long) * 2 * lg, e->stream));
                 SA.pairs = e->d_desc.p + b + q; SA.npairs = 1; SA.counter = e->d_counter.p + w;
+                if (rebase) {
+                    SA1.pairs = SA.pairs; SA1.npairs = 1; SA1.counter = SA.counter;
+                    CU(launch_fill_systolic_rebase(SA1, lg, sysG, sys_smem, false, true, e->stream));
+                    CU(cudaMemsetAsync(e->d_progress.p, 0, sizeof(unsigned long long) * 2 * lg, e->stream));
+                    CU(launch_fill_systolic_rebase(SA, lg, sysG, sys_smem, true, true, e->stream));
+                    e->stats.kernel_launches++;
+                } else
                 CU(launch_fill_systolic_long(SA, lg, sysG, sys_smem, want_trace != 0, plan.pad, e->stream));
                 if (q + 1 < cnt) e->stats.kernel_launches++;
             }
@@ -896,6 +982,12 @@ int ba_run(ba_engine* e, int want_trace) {
             const int nch = (int)(chain_begin[w + 1] - chain_begin[w]) - 1;
             SA.pairs = e->d_desc.p + b; SA.npairs = nch; SA.chains = e->d_chains.p + chain_begin[w]; SA.counter = e->d_counter.p + w;
             CU(launch_fill_systolic_chain(SA, std::min(nch, max_grid), sysG, sys_smem, want_trace != 0, e->stream));
+        } else if (kernel == 1 && rebase) {
+            SA1.pairs = e->d_desc.p + b; SA1.npairs = (int)cnt; SA1.counter = e->d_counter.p + n_waves + w;
+            CU(launch_fill_systolic_rebase(SA1, grid, sysG, sys_smem, false, false, e->stream));
+            SA.pairs = e->d_desc.p + b; SA.npairs = (int)cnt; SA.counter = e->d_counter.p + w;
+            CU(launch_fill_systolic_rebase(SA, grid, sysG, sys_smem, true, false, e->stream));
+            e->stats.kernel_launches++;
         } else if (kernel == 1) {
             SA.pairs = e->d_desc.p + b; SA.npairs = (int)cnt; SA.counter = e->d_counter.p + w;
             CU(launch_fill_systolic(SA, grid, sysG, sys_smem, want_trace != 0, plan.pad, plan.bneg, e->stream));
@@ -945,8 +1037,76 @@ int ba_run(ba_engine* e, int want_trace) {
         for (int64_t p = 0; p < N; ++p) cb += pair_code_words(ln[p], lm[p]) * 8;
         e->stats.code_bytes = cb;
     }
+    if (rebase) {
+        // pairs the rebased launch could not vouch for (walk stopped at a floor / out-of-band source, values above a row
+        // maximum, score differing from the exact first launch): recompute them with the level kernel
+        std::vector<uint8_t> sus((size_t)N), comp((size_t)N);
+        CU(cudaMemcpyAsync(sus.data(), e->d_suspect.p, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(comp.data(), e->d_complete.p, (size_t)N, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        std::vector<PairDesc> redo;
+        for (int64_t q = 0; q < N; ++q)
+            if (sus[e->h_desc[q].orig] || !comp[e->h_desc[q].orig]) redo.push_back(e->h_desc[q]);
+        e->stats.fallback_pairs = (int32_t)std::min<size_t>(redo.size(), 0x7fffffff);
+        if (!redo.empty()) {
+            int64_t max_words = 0;
+            int rn = 0;
+            for (auto& d : redo) { max_words = std::max<int64_t>(max_words, code_words(d.n, d.m, s)); rn = std::max(rn, d.n); }
+            if ((int64_t)e->d_codes.cap < max_words) {
+                cudaError_t ce = e->d_codes.ensure((size_t)max_words);
+                if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "traceback-code arena (level-kernel recomputation): " + std::string(cudaGetErrorString(ce)));
+            }
+            const size_t stride = generic_scratch_ints(rn, s);
+            const int lgrid = (int)std::min<size_t>(redo.size(), (size_t)e->sm_count * 2);
+            {
+                cudaError_t ce = e->d_scratch.ensure(stride * lgrid);
+                if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "fill scratch: " + std::string(cudaGetErrorString(ce)));
+            }
+            CU(e->d_desc2.ensure(redo.size()));
+            cudaEvent_t r0, r1;
+            CU(cudaEventCreate(&r0));
+            CU(cudaEventCreate(&r1));
+            CU(cudaEventRecord(r0, e->stream));
+            size_t at = 0;
+            while (at < redo.size()) {  // waves that fit the arena, cell-major code tables
+                int64_t used = 0;
+                size_t end = at;
+                while (end < redo.size() && (end == at || used + code_words(redo[end].n, redo[end].m, s) <= (int64_t)e->d_codes.cap)) {
+                    redo[end].code_off = used;
+                    used += code_words(redo[end].n, redo[end].m, s);
+                    ++end;
+                }
+                CU(cudaMemcpyAsync(e->d_desc2.p + at, redo.data() + at, sizeof(PairDesc) * (end - at), cudaMemcpyHostToDevice, e->stream));
+                CU(cudaMemsetAsync(e->d_counter.p, 0, sizeof(int), e->stream));
+                FillArgs A{};
+                A.res = e->d_res.p; A.cls = e->d_cls.p; A.sim = e->d_sim.p; A.sc = e->sc;
+                A.pairs = e->d_desc2.p + at; A.npairs = (int)(end - at); A.counter = e->d_counter.p;
+                A.scratch = e->d_scratch.p; A.scratch_stride = stride;
+                A.codes = e->d_codes.p;
+                A.scores = e->d_scores.p; A.start_state = e->d_start.p; A.end_values = e->d_endv.p;
+                launch_fill_generic(A, (int)std::min<size_t>(end - at, (size_t)lgrid), true, false, e->stream);
+                CU(cudaGetLastError());
+                TraceArgs T{};
+                T.pairs = e->d_desc2.p + at; T.npairs = (int)(end - at); T.s = s; T.codes = e->d_codes.p; T.fmt = 0;
+                T.start_state = e->d_start.p; T.trace = e->d_trace.p; T.trace_len = e->d_tlen.p; T.complete = e->d_complete.p;
+                launch_traceback(T, e->stream);
+                CU(cudaGetLastError());
+                e->stats.kernel_launches += 2;
+                at = end;
+            }
+            CU(cudaEventRecord(r1, e->stream));
+            CU(cudaStreamSynchronize(e->stream));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, r0, r1);
+            cudaEventDestroy(r0);
+            cudaEventDestroy(r1);
+            e->stats.fill_ms += ms;
+            e->stats.total_ms += ms;
+            std::fill(e->h_last_code_off.begin(), e->h_last_code_off.end(), -1);  // the arena now holds the recomputed pairs' tables
+        }
+    }
     e->stats.waves = n_waves;
-    e->stats.kernel_kind = kernel == 0 ? (wide ? 9 : 0) : na_ded ? 8 : chain_mode ? 10 : (p16 ? 5 : !affine ? (plan.pad ? 7 : 6) : (plan.pad ? 2 : 1) + (long_mode ? 2 : 0));
+    e->stats.kernel_kind = kernel == 0 ? (wide ? 9 : 0) : na_ded ? 8 : chain_mode ? 10 : rebase ? (long_mode ? 12 : 11) : (p16 ? 5 : !affine ? (plan.pad ? 7 : 6) : (plan.pad ? 2 : 1) + (long_mode ? 2 : 0));
     e->stats.warps_per_cta = kernel == 0 ? 0 : sysG;
     e->last_fmt = kernel;
     e->last_sysG = kernel == 1 ? sysG : 0;
@@ -1255,6 +1415,7 @@ int run(ba_engine* e, int want_trace) {
         st.cell_states += k->stats.cell_states;
         st.kernel_launches += k->stats.kernel_launches;
         st.code_bytes += k->stats.code_bytes;
+        st.fallback_pairs += k->stats.fallback_pairs;
         st.waves = std::max(st.waves, k->stats.waves);
         st.fill_ms = std::max(st.fill_ms, k->stats.fill_ms);
         st.traceback_ms = std::max(st.traceback_ms, k->stats.traceback_ms);

@@ -268,12 +268,26 @@ struct Geo {
 // the systolic array along the j axis, separated by one dead column, so the 2-iterations-per-row pipeline skew is paid once per
 // chain instead of once per pair.  Every lane switches to the next pair of the chain on its own when it passes the dead column
 // (its row of A, its validity, its slice of the staged B molecules, its code stream); steady blocks are agreed by a warp vote.
+//
+// REBASE = score ranges beyond the packed 32-bit plan (value << TB does not fit although the values themselves do; e.g. scoring
+// parameters without a common divisor on pairs of a few hundred residues and more).  Two launches.  The score-only launch
+// (TB = 0, exact) also records rowmax[i] = the largest value of any cell-state in row i.  The TRACE launch then runs in
+// rebased coordinates V' = V - rowmax[i]: the max-plus recurrence is invariant under a potential, and a potential that depends
+// on i only changes nothing but the additive constants of the x0 = 1 cases (by rowmax[i-1] - rowmax[i], a lane constant).
+// Every true V' is <= 0, and values further than |NEGP| below their row's maximum are clamped to the floor.  A clamp (or any
+// other out-of-range source) can only RAISE a value, and every raised value's argmax chain ends at a floor value -- whose id
+// field is 31, which no case has --, at a poisoned case (source outside the band) or outside the matrix: the traceback stops
+// there with complete = 0.  A walk that reaches the origin therefore saw exact values only, and (all values being >= the
+// true ones) won its ties against a superset of its true competitors: it is the reference's trace.  Pairs whose walk fails,
+// whose values rise above 0 or whose final score differs from the first launch's are recomputed by the level kernel (engine.cu).
 constexpr int KCHAIN = BA_KCHAIN;
-template <int S, bool TRACE, bool PAD, bool BNEG, bool LONG, bool P16 = false, bool NA = false, bool CHAIN = false>
+template <int S, bool TRACE, bool PAD, bool BNEG, bool LONG, bool P16 = false, bool NA = false, bool CHAIN = false, bool REBASE = false>
 __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
     static_assert(!P16 || (!TRACE && !PAD && BNEG && !LONG), "16-bit pair mode: score only, pad-free, beta < 0, batch mode");
     static_assert(!NA || (BNEG && !LONG && !P16), "non-affine flavour: batch mode, 32-bit");
     static_assert(!CHAIN || (!PAD && BNEG && !LONG && !P16 && !NA), "chained short pairs: plain pad-free affine flavour");
+    static_assert(!REBASE || (!PAD && BNEG && !P16 && !NA && !CHAIN), "rebased wide-range flavour: plain pad-free affine flavour");
+    constexpr bool REB = REBASE && TRACE;             // values are relative to the row maxima of the score-only launch
     using G_ = Geo<S, PAD>;
     constexpr int W = G_::W, P = G_::P, LPR = G_::LPR, R = G_::R, RING = G_::RING, NVR = G_::NVR, PB = G_::PB;
     constexpr bool SELFREG = G_::SELFREG;
@@ -311,6 +325,7 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
     const bool row0 = (r == 0), lastrow = (r == R - 1);
     const int TB = TRACE ? A.tb_bits : 0;
     const int NEGP = P16 ? pack2(A.negp) : A.negp;
+    const int NEGF = REB ? (NEGP | 31) : NEGP;      // the floor itself: id field 31 = "no case" for the traceback
     const int beta = P16 ? pack2(A.beta_p) : A.beta_p, kGD = P16 ? pack2(A.k_gd) : A.k_gd, k2G = P16 ? pack2(A.k_2g) : A.k_2g;
     const int k2G2D = P16 ? pack2(A.k_2g2d) : A.k_2g2d, k2D = P16 ? pack2(A.k_2d) : A.k_2d;
     // band-edge poisons of the pad-free flavour (lane constants): sources at a+1 (x0=1,x2=0) do not exist for
@@ -498,7 +513,18 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
             // plain affine flavour: a lane at k = 0 poisons its x2 = 1 cases itself (their sources sit at k = -1, lanes that
             // are outside the pair and, in steady blocks, not masked), so the first rows of a pair can run steady blocks too
             constexpr bool K0FIX = !P16 && !NA && !PAD;
-            const int pK0 = (K0FIX && k == 0) ? NEGP : 0;
+            // REBASE: row potential.  rbase = rowmax[i]; the x0 = 1 cases (sources in row i-1) carry rowmax[i-1] - rowmax[i], folded
+            // into the two lane constants that every one of them already adds (pU1 for x2 = 0, pK0 for x2 = 1)
+            int rbase = 0, dfp = 0, runmax = (int)0x80000000;
+            if (REB && lane_ok) {
+                const int* rm = A.rowmax + A.row_off[d.orig];
+                rbase = rm[i];
+                int dfi = i >= 1 ? rbase - rm[i - 1] : 0;
+                if (dfi > A.df_max || dfi < -A.df_max) { A.suspect[d.orig] = 1; dfi = 0; }
+                dfp = dfi * (1 << TB);
+            }
+            const int pK0 = ((K0FIX && k == 0) ? NEGP : 0) - dfp;
+            const int pU1w = pU1 - dfp;
             const int pWk = K0FIX ? ((c == 0 || k == 0) ? NEGP : 0) : pW;
             const int k2Gk = k2G + pK0, kGDk = kGD + pK0;
             // Steady range of this warp [st_lo, st_hi): every lane of the warp has S < j <= m - max(S,1) throughout
@@ -511,7 +537,8 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
                 st_lo = (S + 1) * P + sig_hi;
                 st_hi = (m_eff - (S > 0 ? S : 1) + 1) * P + sig_lo;
                 if (has_in) st_hi = min(st_hi, q_rec_lim - LA);
-                if (!K0FIX && pass == 0 && g * R < S) st_hi = st_lo;
+                // (REBASE keeps those lanes masked as well: unmasked they would grow without their row's potential)
+                if ((!K0FIX || REBASE) && pass == 0 && g * R < S) st_hi = st_lo;
             }
 
             // position of this lane one iteration before the first one (q = -PRE)
@@ -704,7 +731,7 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
                     lds128o_if<16>(inF[3], inH1[3], inH1[4], inH1[5], xsi_b + s1 * XSLOTB, row0);
                     // origin: M[1111][0,0,0,0] = 0 (pyx:485) enters as the F input of state 1111 (mu1 = mu2 = 0 there)
                     // (the origin lane sits at k = 0, whose x2 = 1 cases carry the poison pK0: cancel it for this one input)
-                    if (CHAIN ? (i == 0 && a == 0 && j == 0 && bb == S) : (q == q_origin)) inF[8] = -pK0;
+                    if (CHAIN ? (i == 0 && a == 0 && j == 0 && bb == S) : (q == q_origin)) inF[8] = -pK0 - rbase * (1 << TB);
                 }
 
                 // ---- additive constants per case (affine_score minus its gap-opening part), with the poisons
@@ -754,10 +781,10 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
                     kF[0] = k2G;                       // x=0101
                     kF[1] = k2G2D + pWk + pB1;         // x=0110
                     kF[2] = mu2 + kGD + pWk;           // x=0111
-                    kF[3] = k2G2D + pU1 + pB0;         // x=1001
+                    kF[3] = k2G2D + pU1w + pB0;        // x=1001
                     kF[4] = k2Gk;                      // x=1010   (x0 = x2 = 1: source at k - 1)
                     kF[5] = mu2 + kGDk + pB0;          // x=1011
-                    kF[6] = mu1 + kGD + pU1;           // x=1101
+                    kF[6] = mu1 + kGD + pU1w;          // x=1101
                     kF[7] = mu1 + kGDk + pB1;          // x=1110
                     kF[8] = mu1 + mu2 + pK0;           // x=1111
                     // half-column cases also re-base the id field of the winner they carry (TRACE): a full-column
@@ -768,24 +795,25 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
                     kh2[1] = kGD + ADJ2 + pWk;             // x=0010
                     kh2[2] = mu2 + k2D + ADJ2 + pWk + pB0; // x=0011
                     kh1[0] = kGD + ADJ1 + pB1;             // x=0100
-                    kh1[1] = kGD + ADJ1 + pU1;             // x=1000
-                    kh1[2] = mu1 + k2D + ADJ1 + pU1 + pB1; // x=1100
+                    kh1[1] = kGD + ADJ1 + pU1w;            // x=1000
+                    kh1[2] = mu1 + k2D + ADJ1 + pU1w + pB1;// x=1100
                 }
                 int M[9];
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
                     const int t01 = t / 3, t23 = t % 3;
-                    const int v1 = xaddmax<P16>(inH1[t], kh1[t01], NEGP);  // floor: nothing ever drops below "minus infinity"
+                    const int v1 = xaddmax<P16>(inH1[t], kh1[t01], NEGF);  // floor: nothing ever drops below "minus infinity"
                     const int v = xaddmax<P16>(inH2[t], kh2[t23], v1);
                     M[t] = xaddmax<P16>(inF[t], kF[t], v);
-                    if (!ST) M[t] = P16 ? ((M[t] & vmask) | nmask) : (valid ? M[t] : NEGP);
+                    if (!ST) M[t] = P16 ? ((M[t] & vmask) | nmask) : (valid ? M[t] : NEGF);
                 }
+                if (REBASE) runmax = vmax3(vmax3(runmax, M[0], M[1]), vmax3(M[2], M[3], M[4]), vmax3(vmax3(M[5], M[6], M[7]), M[8], runmax));
 
                 // ---- results at the end cell
                 if (!ST && (CHAIN ? (lane_ok && i == cur_n && a == 0 && j == cur_m && bb == S) : (q == q_end))) {
                     int Mv[9];  // plain values of the nine states (low half in 16-bit pair mode)
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) Mv[t] = P16 ? (int)(short)(M[t] & 0xffff) : (M[t] >> TB);
+                    for (int t = 0; t < 9; ++t) Mv[t] = P16 ? (int)(short)(M[t] & 0xffff) : (M[t] >> TB) + rbase;
                     int best = Mv[0];
 #pragma unroll
                     for (int t = 1; t < 9; ++t) best = max(best, Mv[t]);
@@ -797,6 +825,7 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
                         if (Mv[t] == best && sh < bsh) { bsh = sh; st = t; }
                         A.end_values[(size_t)cur_orig * 9 + t] = Mv[t] * A.gscale;
                     }
+                    if (REB && A.scores[cur_orig] != (long long)best * A.gscale) A.suspect[cur_orig] = 1;  // the first launch's exact score
                     A.scores[cur_orig] = (long long)best * A.gscale;
                     A.start_state[cur_orig] = (uint8_t)st;
                 }
@@ -1017,6 +1046,10 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
                     ++q;
                 }
             }
+            if (REBASE && lane_ok) {
+                if (!TRACE) atomicMax(A.rowmax + A.row_off[d.orig] + i, runmax);       // row maxima for the rebased launch
+                else if (runmax >= (1 << TB)) A.suspect[d.orig] = 1;                   // no true value exceeds its row's maximum
+            }
             if (has_out) {  // last iteration's record, then make the stream visible to the next pass
                 for (int e = tid; e < REAL; e += blockDim.x) {
                     const int v = e / LPR, cs = e - v * LPR;
@@ -1125,6 +1158,39 @@ int occ_chain_t(int G, size_t smem) {
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, G * 32, smem);
     return nb;
+}
+
+// REBASE flavour (rebased wide-range runs: a score-only launch that records row maxima, then a TRACE launch), batch and long-pair mode
+template <int S, bool TRACE, bool LONG>
+cudaError_t launch_rebase_t(const SysArgs& A, int grid, int G, size_t smem, cudaStream_t st) {
+    auto kern = fill_systolic_kernel<S, TRACE, false, true, LONG, false, false, false, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (LONG) {
+        SysArgs a = A;
+        void* params[] = {&a};
+        return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(G * 32), params, smem, st);
+    }
+    kern<<<grid, G * 32, smem, st>>>(A);
+    return cudaGetLastError();
+}
+template <int S, bool TRACE, bool LONG>
+int occ_rebase_t(int G, size_t smem) {
+    auto kern = fill_systolic_kernel<S, TRACE, false, true, LONG, false, false, false, true>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, G * 32, smem);
+    return nb;
+}
+template <int S>
+cudaError_t launch_rebase_s(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool lng, cudaStream_t st) {
+    if (lng) return trace ? launch_rebase_t<S, true, true>(A, grid, G, smem, st) : launch_rebase_t<S, false, true>(A, grid, G, smem, st);
+    return trace ? launch_rebase_t<S, true, false>(A, grid, G, smem, st) : launch_rebase_t<S, false, false>(A, grid, G, smem, st);
+}
+template <int S>
+int occ_rebase_s(bool trace, bool lng, int G, size_t smem) {
+    if (lng) return trace ? occ_rebase_t<S, true, true>(G, smem) : occ_rebase_t<S, false, true>(G, smem);
+    return trace ? occ_rebase_t<S, true, false>(G, smem) : occ_rebase_t<S, false, false>(G, smem);
 }
 
 // LONG flavour: cooperative launch (all CTAs must be co-resident: they wait on one another)

@@ -15,7 +15,9 @@ namespace ba {
     cudaError_t launch_fill_systolic_na_s##s(const SysArgs&, int, int, size_t, bool, bool, cudaStream_t);               \
     int sys_occupancy_na_s##s(bool, bool, int, size_t);                                                                 \
     cudaError_t launch_fill_systolic_chain_s##s(const SysArgs&, int, int, size_t, bool, cudaStream_t);                  \
-    int sys_occupancy_chain_s##s(bool, int, size_t);
+    int sys_occupancy_chain_s##s(bool, int, size_t);                                                                    \
+    cudaError_t launch_fill_systolic_rebase_s##s(const SysArgs&, int, int, size_t, bool, bool, cudaStream_t);             \
+    int sys_occupancy_rebase_s##s(bool, bool, int, size_t);
 DECL(0) DECL(1) DECL(2) DECL(3) DECL(4)
 #undef DECL
 
@@ -176,6 +178,27 @@ cudaError_t launch_fill_systolic_chain(const SysArgs& A, int grid, int G, size_t
         case 2: return launch_fill_systolic_chain_s2(A, grid, G, smem, trace, st);
         case 3: return launch_fill_systolic_chain_s3(A, grid, G, smem, trace, st);
         case 4: return launch_fill_systolic_chain_s4(A, grid, G, smem, trace, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+int sys_occupancy_rebase(int S, bool trace, bool lng, int G, size_t smem) {
+    switch (S) {
+        case 0: return sys_occupancy_rebase_s0(trace, lng, G, smem);
+        case 1: return sys_occupancy_rebase_s1(trace, lng, G, smem);
+        case 2: return sys_occupancy_rebase_s2(trace, lng, G, smem);
+        case 3: return sys_occupancy_rebase_s3(trace, lng, G, smem);
+        default: return sys_occupancy_rebase_s4(trace, lng, G, smem);
+    }
+}
+
+cudaError_t launch_fill_systolic_rebase(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool lng, cudaStream_t st) {
+    switch (A.sc.s) {
+        case 0: return launch_fill_systolic_rebase_s0(A, grid, G, smem, trace, lng, st);
+        case 1: return launch_fill_systolic_rebase_s1(A, grid, G, smem, trace, lng, st);
+        case 2: return launch_fill_systolic_rebase_s2(A, grid, G, smem, trace, lng, st);
+        case 3: return launch_fill_systolic_rebase_s3(A, grid, G, smem, trace, lng, st);
+        case 4: return launch_fill_systolic_rebase_s4(A, grid, G, smem, trace, lng, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -24,4 +24,8 @@ cudaError_t launch_fill_systolic_chain_s3(const SysArgs& A, int grid, int G, siz
     return trace ? sys::launch_chain_t<3, true>(A, grid, G, smem, st) : sys::launch_chain_t<3, false>(A, grid, G, smem, st);
 }
 int sys_occupancy_chain_s3(bool trace, int G, size_t smem) { return trace ? sys::occ_chain_t<3, true>(G, smem) : sys::occ_chain_t<3, false>(G, smem); }
+cudaError_t launch_fill_systolic_rebase_s3(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool lng, cudaStream_t st) {
+    return sys::launch_rebase_s<3>(A, grid, G, smem, trace, lng, st);
+}
+int sys_occupancy_rebase_s3(bool trace, bool lng, int G, size_t smem) { return sys::occ_rebase_s<3>(trace, lng, G, smem); }
 }  // namespace ba

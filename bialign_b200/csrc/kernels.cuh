@@ -50,6 +50,11 @@ struct SysArgs {
     long long* scores;
     uint8_t* start_state;
     int* end_values;
+    // REBASE flavour (fill_systolic.cuh): row maxima of the score-only launch, in scaled units, pair p (caller order) at row_off[p]
+    int* rowmax;
+    const long long* row_off;
+    uint8_t* suspect;         // [n_pairs] caller order: set when the rebased launch cannot vouch for a pair
+    int df_max;               // bound on |rowmax[i] - rowmax[i-1]| the range plan allowed for
 };
 
 struct TraceArgs {
@@ -120,5 +125,8 @@ int sys_occupancy_chain(int S, bool trace, int G, size_t smem);
 size_t sys_smem_bytes_chain(int S, int G, int nsym, int bpad_total);
 cudaError_t launch_fill_systolic_chain(const SysArgs& A, int grid, int G, size_t smem, bool trace, cudaStream_t st);
 cudaError_t launch_fill_systolic_long(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, cudaStream_t st);
+// rebased wide-range flavour (pad-free affine): score-only launch records row maxima, TRACE launch consumes them
+int sys_occupancy_rebase(int S, bool trace, bool lng, int G, size_t smem);
+cudaError_t launch_fill_systolic_rebase(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool lng, cudaStream_t st);
 
 }  // namespace ba

@@ -67,10 +67,13 @@ typedef struct ba_stats {
                                  6 / 7 = systolic pad-free / padded running the non-affine model,
                                  8 = dedicated non-affine kernel (a lane owns a row and all its band offsets),
                                  9 = general level kernel, 64-bit values (score bound >= 2^30),
-                                 10 = systolic pad-free, short pairs chained along j (every pair fits one row block) */
+                                 10 = systolic pad-free, short pairs chained along j (every pair fits one row block),
+                                 11 / 12 = systolic pad-free, rebased wide-range trace run (batch / long-pair mode): scores
+                                 whose packed form (value << tie bits) exceeds 32 bits; a score-only launch records
+                                 row maxima, the trace launch works relative to them */
     int32_t device;
     int32_t warps_per_cta;    /* CTA width the systolic kernel ran with (0 for the general kernel)      */
-    int32_t reserved;
+    int32_t fallback_pairs;   /* rebased runs: pairs the fast kernel could not vouch for, recomputed by the level kernel */
 } ba_stats;
 
 /* One engine per process per GPU (device = CUDA ordinal, normally LOCAL_RANK). */
@@ -134,7 +137,9 @@ BA_API int ba_get_stats(const ba_engine* e, ba_stats* out);
  * "warps_per_cta" (1..8, 0 = chosen per batch), "long" (multi-CTA long-pair mode: 0 off, 1 force, -1 auto),
  * "p16" (16-bit pair mode for score-only batches: 0 off, 1 force, -1 auto),
  * "na_kernel" (non-affine model: 0 = systolic kernel's non-affine flavour, 1 / -1 = dedicated kernel when applicable),
- * "chain" (batches of short pairs run as chains through the systolic array: 0 off, 1 force, -1 auto). */
+ * "chain" (batches of short pairs run as chains through the systolic array: 0 off, 1 force, -1 auto),
+ * "rebase" (trace runs relative to row maxima: -1 = when the packed 32-bit plan fails, 0 off, 1 force),
+ * "rebase_window" (test hook: cap on the rebased value window in scaled score units; 0 = the full window). */
 BA_API int ba_set_option(ba_engine* e, const char* key, int64_t value);
 
 /* Test hook: copy the raw 4-bit code table of pair p of the last wave (uint64 per cell, index

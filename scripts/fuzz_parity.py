@@ -19,7 +19,7 @@ AA = "ARNDCQEGHILKMFPSTWYV"
 def fuzz(seed=1, rounds=40, verbose=True, max_len=160):
     """Returns (mismatches, pairs checked).  Every round: random scoring parameters (incl. zero and positive costs),
     RNA or protein, max_shift 0..4, 1-8 pairs of lengths 0..max_len, a random kernel / flavour / CTA width / long-pair
-    mode; scores, traces and completeness flags must equal the oracle's literal int64 restatement."""
+    mode / rebased trace run; scores, traces and completeness flags must equal the oracle's literal int64 restatement."""
     import oracle
     from bialign_b200.batch import BatchAligner, trace_hex
 
@@ -67,6 +67,9 @@ def fuzz(seed=1, rounds=40, verbose=True, max_len=160):
         al.set_option("pad", int(rng.choice([-1, 0, 1])))
         al.set_option("long", int(rng.choice([-1, -1, 1])))
         al.set_option("warps_per_cta", int(rng.choice([0, 0, 2, 4, 6])))
+        if rng.random() < 0.25:  # rebased trace run (forced), sometimes with a window so small that pairs fall back
+            al.set_option("rebase", 1)
+            al.set_option("rebase_window", int(rng.choice([0, 0, 30, 300])))
         try:
             scores, cols, offsets, complete = al.align(seqs, structs, pairs, want_trace=True)
             kind = al.engine.stats()["kernel_kind"]

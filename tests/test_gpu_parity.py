@@ -108,7 +108,8 @@ def _check_batch(al, seqs, structs, pairs, params, table_pairs=0):
     from bialign_b200.batch import trace_hex
 
     scores, cols, offsets, complete = al.align(seqs, structs, pairs, want_trace=True)
-    kind = al.engine.stats()["kernel_kind"]
+    al.trace_run_stats = al.engine.stats()
+    kind = al.trace_run_stats["kernel_kind"]
     for q, (ia, ib) in enumerate(pairs):
         r = oracle.run(seqs[ia], seqs[ib], structs[ia], structs[ib], params, mode="codes", want_codes=True)
         assert int(scores[q]) == r["score"], (q, len(seqs[ia]), len(seqs[ib]))
@@ -593,7 +594,7 @@ def test_very_long_molecule_b_falls_back_instead_of_narrowing_the_cta():
     assert int(s_auto[0]) == int(s_gen[0]) and t_auto == trace_hex_(cols, offsets, 0) and bool(complete[0])
     v, end = oracle.eval_trace(seqs[0], seqs[1], structs[0], structs[1], params, t_auto)
     assert v == int(s_auto[0]) and end == [150, 78000, 150, 78000]
-    assert kind_auto in (0, 1, 2, 3, 4)
+    assert kind_auto in (0, 1, 2, 3, 4, 11, 12)
 
 
 def trace_hex_(cols, offsets, p):
@@ -655,3 +656,79 @@ def test_chained_short_pairs_vs_oracle(s):
         assert al.engine.stats()["kernel_kind"] in (1, 2)
         for x, y in zip(chained, plain):
             assert (x == y).all()
+
+
+def _same_results(x, y):
+    return all((a == b).all() for a, b in zip(x, y))
+
+
+@pytest.mark.parametrize("s", [0, 1, 2, 3, 4])
+def test_rebased_trace_run_forced_vs_oracle(s):
+    """The rebased trace run (values relative to the row maxima of a score-only launch, kernel_kind 11) forced on ordinary
+    parameter sets: ragged batches incl. multi-pass pairs and tie storms against the oracle; then with a window so small
+    that the walks hit the floor: those pairs are recomputed by the level kernel and every answer is still the oracle's."""
+    rng = np.random.default_rng(5200 + s)
+    for var in ({}, {"shift_cost": 0, "gap_cost": 0}, {"structure_weight": 0, "gap_opening_cost": -1}):
+        params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150, gap_cost=-50,
+                      shift_cost=-150, max_shift=s)
+        params.update(var)
+        seqs, structs, pairs = _random_protein_batch(rng, 10, 1, 110)
+        seqs[4], structs[4] = "", ""  # an empty molecule A
+        al = _aligner(params)
+        al.set_option("rebase", 1)
+        try:
+            assert _check_batch(al, seqs, structs, pairs, params) == 11
+            assert al.trace_run_stats["fallback_pairs"] == 0 or var
+            al.set_option("rebase_window", 40)
+            assert _check_batch(al, seqs, structs, pairs, params) == 11
+            assert al.trace_run_stats["fallback_pairs"] > 0
+        finally:
+            _unselect(al)
+
+
+def test_rebased_trace_run_beyond_packed_range():
+    """Scores without a common divisor (structure_weight 333): value << tie bits leaves 32 bits beyond ~800 residues (even for
+    the padded flavour).  The engine then picks the rebased run on its own (kernel_kind 11; 12 in long-pair mode) instead of the level kernel.
+    Oracle on a subsample, the level kernel (kernel = 0) on everything: scores, traces, completeness."""
+    from bialign_b200.batch import trace_hex
+
+    rng = np.random.default_rng(77001)
+    params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=333, gap_opening_cost=-157, gap_cost=-49,
+                  shift_cost=-151, max_shift=2)
+    seqs, structs, pairs = _random_protein_batch(rng, 22, 850, 1000)
+    sq2, st2, _ = _random_protein_batch(rng, 2, 250, 350)  # two shorter pairs in the same batch: the oracle's share
+    pairs += [(len(seqs), len(seqs) + 1), (len(seqs) + 2, len(seqs) + 3)]
+    seqs, structs = seqs + sq2, structs + st2
+    al = _aligner(params)
+    fast = al.align(seqs, structs, pairs, want_trace=True)
+    st = al.engine.stats()
+    assert st["kernel_kind"] == 11 and st["fallback_pairs"] <= 2, st
+    al.set_option("kernel", 0)
+    try:
+        slow = al.align(seqs, structs, pairs, want_trace=True)
+        assert al.engine.stats()["kernel_kind"] == 0
+    finally:
+        _unselect(al)
+    assert _same_results(fast, slow)
+    scores, cols, offsets, complete = fast
+    for q in (22, 23):
+        ia, ib = pairs[q]
+        r = oracle.run(seqs[ia], seqs[ib], structs[ia], structs[ib], params, mode="codes")
+        assert int(scores[q]) == r["score"] and trace_hex(cols, offsets, q) == r["trace"] and bool(complete[q]) == r["complete"]
+    # two long pairs: long-pair mode, several row blocks per CTA
+    aa = "ARNDCQEGHILKMFPSTWYV"
+    seqs, structs = [], []
+    for L in (1900, 2000, 2100, 1800):
+        seqs.append("".join(aa[i] for i in rng.integers(0, 20, L)))
+        structs.append("".join("HEC"[i] * 7 for i in rng.integers(0, 3, L // 7 + 1))[:L])
+    params["max_shift"] = 1
+    al = _aligner(params)
+    fast = al.align(seqs, structs, [(0, 1), (2, 3)], want_trace=True)
+    st = al.engine.stats()
+    assert st["kernel_kind"] == 12 and st["fallback_pairs"] == 0, st
+    al.set_option("kernel", 0)
+    try:
+        slow = al.align(seqs, structs, [(0, 1), (2, 3)], want_trace=True)
+    finally:
+        _unselect(al)
+    assert _same_results(fast, slow)
