@@ -847,10 +847,11 @@ int ba_run(ba_engine* e, int want_trace) {
             CU(e->d_tbtab.ensure(plan.tbtab.size()));
             CU(cudaMemcpyAsync(e->d_tbtab.p, plan.tbtab.data(), plan.tbtab.size() * 4, cudaMemcpyHostToDevice, e->stream));
         }
-        // Few, long pairs: spread the row blocks of each pair over the whole grid (LONG flavour, cooperative launch)
+        // Long pairs, fewer per wave than half the CTAs the GPU holds (a wave is what fits the code arena): spread the row
+        // blocks of each pair over a gang of CTAs (LONG flavour, cooperative launch), the whole grid for a single pair
         const int npass_max = (nmax + rows_pass) / rows_pass;
         if (!chain_mode && !p16 && affine && plan.bneg && e->opt_long != 0 && npass_max >= 2 && sysG >= 2 &&
-            (e->opt_long == 1 || (N <= 4 && npass_max >= 8))) {
+            (e->opt_long == 1 || (npass_max >= 8 && biggest_wave * 2 <= max_grid))) {
             const int occl = rebase ? std::min(sys_occupancy_rebase(s, false, true, sysG, sys_smem), sys_occupancy_rebase(s, true, true, sysG, sys_smem))
                                     : sys_occupancy_long(s, want_trace != 0, plan.pad, sysG, sys_smem);
             int coop = 0;
@@ -863,10 +864,10 @@ int ba_run(ba_engine* e, int want_trace) {
             }
         }
         if (long_mode) {
-            const int lg = std::min(long_grid_max, npass_max);
+            const int lg = (int)std::min<int64_t>(long_grid_max, (int64_t)npass_max * biggest_wave);
             cudaError_t ce = e->d_bnd.ensure((size_t)lg * 2 * sys_boundary_ints(s, plan.pad, sysG, mmax));
             if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "boundary streams: " + std::string(cudaGetErrorString(ce)));
-            CU(e->d_progress.ensure((size_t)lg * 2));
+            CU(e->d_progress.ensure((size_t)long_grid_max * 2));
         } else if (multi_pass) {
             cudaError_t ce = e->d_bnd.ensure((size_t)grid * 2 * sys_boundary_ints(s, plan.pad, sysG, mmax));
             if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "boundary streams: " + std::string(cudaGetErrorString(ce)));
@@ -954,20 +955,26 @@ int ba_run(ba_engine* e, int want_trace) {
         const int grid = (int)std::min<int64_t>(cnt, max_grid);
         if (kernel == 1 && long_mode) {
             const int rows_pass = sysG * sys_geo(s, plan.pad).R;
-            for (int64_t q = 0; q < cnt; ++q) {  // one cooperative launch per pair
-                const int npass = (e->h_desc[b + q].n + rows_pass) / rows_pass;
-                const int lg = std::min(long_grid_max, npass);
+            // a gang of cpp CTAs per pair; as many pairs per cooperative launch as the GPU holds gangs (pairs are sorted by
+            // cost, so the pairs of one launch are of similar length)
+            int64_t q = 0;
+            while (q < cnt) {
+                const int np0 = (e->h_desc[b + q].n + rows_pass) / rows_pass;  // row blocks of the longest pair of this launch
+                const int cpp = (int)std::max<int64_t>(1, std::min<int64_t>(np0, long_grid_max / std::min<int64_t>(cnt - q, long_grid_max)));
+                const int np = (int)std::min<int64_t>(cnt - q, long_grid_max / cpp);
+                const int lg = np * cpp;
                 CU(cudaMemsetAsync(e->d_progress.p, 0, sizeof(unsigned long long) * 2 * lg, e->stream));
-                SA.pairs = e->d_desc.p + b + q; SA.npairs = 1; SA.counter = e->d_counter.p + w;
+                SA.pairs = e->d_desc.p + b + q; SA.npairs = np; SA.cpp = cpp; SA.counter = e->d_counter.p + w;
                 if (rebase) {
-                    SA1.pairs = SA.pairs; SA1.npairs = 1; SA1.counter = SA.counter;
+                    SA1.pairs = SA.pairs; SA1.npairs = np; SA1.cpp = cpp; SA1.counter = SA.counter;
                     CU(launch_fill_systolic_rebase(SA1, lg, sysG, sys_smem, false, true, e->stream));
                     CU(cudaMemsetAsync(e->d_progress.p, 0, sizeof(unsigned long long) * 2 * lg, e->stream));
                     CU(launch_fill_systolic_rebase(SA, lg, sysG, sys_smem, true, true, e->stream));
                     e->stats.kernel_launches++;
                 } else
                 CU(launch_fill_systolic_long(SA, lg, sysG, sys_smem, want_trace != 0, plan.pad, e->stream));
-                if (q + 1 < cnt) e->stats.kernel_launches++;
+                q += np;
+                if (q < cnt) e->stats.kernel_launches++;
             }
         } else if (kernel == 1 && p16) {  // two pairs per work item (score only: a single wave)
             SA.pairs = e->d_desc.p; SA.npairs = (int)((N + 1) / 2); SA.counter = e->d_counter.p + w;

@@ -189,6 +189,9 @@ __device__ __forceinline__ void open3(int i0, int i1, int i2, int beta, int& o0,
 // Register caps: narrow bands in batch mode fit 128 registers without spills, which (with 54 KB of shared memory per
 // 4-warp CTA) allows four CTAs = 16 warps per SM (measured on config 3: +3.6 % over three CTAs at 142 registers);
 // wider bands and the long-pair flavour keep 168 (three CTAs of 128 threads: 65536 / 384 = 170).
+#ifndef BA_LONG_NARROW
+#define BA_LONG_NARROW 1
+#endif
 #ifndef BA_SYS_MAXNREG
 #define BA_SYS_MAXNREG 168
 #endif
@@ -246,9 +249,9 @@ struct Geo {
 // beyond n) simply compute garbage that no valid cell ever reads (sources have smaller coordinates; the band edges are
 // poisoned).  Each warp picks the form per ring period on its own; both forms execute one CTA barrier per iteration.
 //
-// LONG = one long pair spread over the whole grid (cooperative launch): CTA b runs the row blocks
-// ("passes") b, b+NC, b+2NC, ... and the boundary stream of pass p is consumed by pass p+1 on another
-// CTA while it is being produced.  Streams live in 2*NC global buffers (pass p -> buffer
+// LONG = long pairs spread over several CTAs each (cooperative launch; a gang of NC = cpp CTAs per pair, the whole grid for
+// a single pair): CTA b of a gang runs the row blocks ("passes") b, b+NC, b+2NC, ... and the boundary stream of pass p is
+// consumed by pass p+1 on another CTA while it is being produced.  Streams live in 2*NC global buffers (pass p -> buffer
 // p%NC + NC*((p/NC)&1): by the time it is overwritten, at pass p+2NC, pass p+1 has finished because
 // every later pass transitively depends on it).  Progress flags (pass id << 32 | records complete)
 // are published every LQB iterations with release semantics and polled with acquire loads; stream
@@ -282,7 +285,7 @@ struct Geo {
 // whose values rise above 0 or whose final score differs from the first launch's are recomputed by the level kernel (engine.cu).
 constexpr int KCHAIN = BA_KCHAIN;
 template <int S, bool TRACE, bool PAD, bool BNEG, bool LONG, bool P16 = false, bool NA = false, bool CHAIN = false, bool REBASE = false>
-__global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
+__global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNREG_NARROW : BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
     static_assert(!P16 || (!TRACE && !PAD && BNEG && !LONG), "16-bit pair mode: score only, pad-free, beta < 0, batch mode");
     static_assert(!NA || (BNEG && !LONG && !P16), "non-affine flavour: batch mode, 32-bit");
     static_assert(!CHAIN || (!PAD && BNEG && !LONG && !P16 && !NA), "chained short pairs: plain pad-free affine flavour");
@@ -366,9 +369,11 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
     bool long_done = false;
     for (;;) {
         int pi = 0;
-        if (LONG) {
+        if (LONG) {  // CTAs blockIdx.x / cpp == pi form the gang of pair pi (one pair per gang and launch)
             if (long_done) return;
             long_done = true;
+            pi = blockIdx.x / A.cpp;
+            if (pi >= A.npairs) return;
         } else {
             if (tid == 0) s_pair = atomicAdd(A.counter, 1);
             __syncthreads();
@@ -430,10 +435,12 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
             for (int kk = 0; kk < K; ++kk) nit += (s_cd[kk].m + 2) * P;
         }
         const size_t bstride = (size_t)A.bnd_iters * REC;  // ints per boundary buffer
-        int* bnd_base = A.bnd + (LONG ? (size_t)0 : (size_t)blockIdx.x * 2 * bstride);
-        const int NC = gridDim.x;
+        const int NC = LONG ? A.cpp : (int)gridDim.x;  // LONG: CTAs that share this pair's row blocks
+        const int lb = LONG ? (int)blockIdx.x - pi * NC : 0;
+        int* bnd_base = A.bnd + (LONG ? (size_t)pi * 2 * NC * bstride : (size_t)blockIdx.x * 2 * bstride);
+        unsigned long long* prog_base = LONG ? A.progress + (size_t)pi * 2 * NC : nullptr;
 
-        for (int pass = LONG ? (int)blockIdx.x : 0; pass < npass; pass += LONG ? NC : 1) {
+        for (int pass = lb; pass < npass; pass += LONG ? NC : 1) {
             const int i = pass * RT + g * R + r;
             const int k = i + a;
             // per-pair lane state (constant over a pass, except in CHAIN mode where a lane moves from pair to pair)
@@ -451,8 +458,8 @@ __global__ void __maxnreg__((S <= 2 && !LONG) ? BA_SYS_MAXNREG_NARROW : BA_SYS_M
             const int buf_out = LONG ? (pass % NC) + NC * (((pass + 2 * NC) / NC) & 1) : (pass & 1);
             const int* bnd_in = bnd_base + (size_t)buf_in * bstride;
             int* bnd_out = bnd_base + (size_t)buf_out * bstride;
-            const unsigned long long* prog_in = LONG ? A.progress + buf_in : nullptr;
-            unsigned long long* prog_out = LONG ? A.progress + buf_out : nullptr;
+            const unsigned long long* prog_in = LONG ? prog_base + buf_in : nullptr;
+            unsigned long long* prog_out = LONG ? prog_base + buf_out : nullptr;
             const unsigned long long tag_in = (unsigned long long)pass << 32;         // producer pass id + 1
             const unsigned long long tag_out = (unsigned long long)(pass + 1) << 32;
             // boundary I/O descriptors: thread e moves record element e (= v*LPR + cs) every iteration

@@ -46,6 +46,7 @@ struct SysArgs {
     int* bnd;                 // per CTA: two boundary streams of bnd_iters records
     int bnd_iters;
     int lq_iters;             // LONG flavour: iterations between progress-flag exchanges (a multiple of the ring period; 0 = default)
+    int cpp;                  // LONG flavour: CTAs per pair (gang size); pair p is run by CTAs [p * cpp, (p + 1) * cpp)
     uint64_t* codes;
     long long* scores;
     uint8_t* start_state;

@@ -18,11 +18,15 @@ def batch(n, lo, hi):
         pairs.append((2 * q, 2 * q + 1))
     return seqs, structs, pairs
 params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=333, gap_opening_cost=-157, gap_cost=-49, shift_cost=-151, max_shift=2)
-for name, (n, lo, hi, opt) in {"3000 pairs 200-500 auto": (3000, 200, 500, -1), "3000 pairs 200-500 rebase": (3000, 200, 500, 1),
-                               "800 pairs 2000": (800, 1900, 2100, -1), "2 pairs 2000": (2, 2000, 2000, -1)}.items():
+std = dict(params, structure_weight=800, gap_opening_cost=-150, gap_cost=-50, shift_cost=-150)
+for name, (n, lo, hi, opt, par) in {"3000 pairs 200-500 gcd1": (3000, 200, 500, -1, params),
+                                    "800 pairs 2000 gcd1": (800, 1900, 2100, -1, params), "2 pairs 2000 gcd1": (2, 2000, 2000, -1, params),
+                                    "800 pairs 2000 gcd50": (800, 1900, 2100, -1, std), "800 pairs 2000 gcd50 long=0": (800, 1900, 2100, -2, std),
+                                    "40 pairs 2000 gcd50": (40, 1900, 2100, -1, std), "40 pairs 2000 gcd50 long=0": (40, 1900, 2100, -2, std)}.items():
     seqs, structs, pairs = batch(n, lo, hi)
-    al = BatchAligner(**params)
-    al.set_option("rebase", opt)
+    al = BatchAligner(**par)
+    if opt == -2:
+        al.set_option("long", 0)
     for rep in range(2):
         t0 = time.time(); out = al.align(seqs, structs, pairs, want_trace=True); t1 = time.time()
     st = al.engine.stats()
