@@ -516,6 +516,16 @@ def run_shapes(world, rank, local_rank, barrier, allmax, allsum, int_peak):
     res, cls, off, pa, pb = workloads.protein_pairs(3000, seed=3 + 100 * rank)
     record("non-affine model: 3000 protein pairs 200-500 per GPU, max_shift 2, score+traceback (cells/s)", al, res, cls, off,
            pa, pb, True, 2, 26, True)
+    # long pairs in a batch (about 90 fit one traceback-memory wave): a gang of CTAs per pair, several pairs per launch
+    al = BatchAligner(device=local_rank, max_shift=2, **prot)
+    res, cls, off, pa, pb = workloads.protein_pairs(400, lo=1900, hi=2100, seed=6 + 100 * rank)
+    record("long pairs in a batch: 400 protein pairs 1900-2100 per GPU, max_shift 2, score+traceback (long-pair gangs)", al, res, cls,
+           off, pa, pb, True, 2, 30, True)
+    # scoring without a common divisor on the same pairs: value << tie bits does not fit 32 bits -> rebased two-launch run
+    al = BatchAligner(device=local_rank, max_shift=2, **dict(prot, structure_weight=333, gap_opening_cost=-157, gap_cost=-49, shift_cost=-151))
+    record("wide score range (structure_weight 333, costs -157/-49/-151: gcd 1): the same 400 pairs, score+traceback (rebased run)", al,
+           res, cls, off, pa, pb, True, 2, 30, True,
+           note="two launches (exact score-only + trace relative to row maxima); GCUPS counts the cell-states once")
     # cfg5: one 8192 x 8192 protein pair, max_shift 3, multi-CTA fill with traceback codes in HBM
     al = BatchAligner(device=local_rank, max_shift=3, **prot)
     res, cls, off, pa, pb = workloads.protein_pairs(1, lo=8192, hi=8192, seed=5)

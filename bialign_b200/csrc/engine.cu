@@ -119,6 +119,7 @@ struct ba_engine {
     int opt_warps = 0;                 // warps per CTA of the systolic kernel (0 = chosen per batch)
     int opt_pad = -1;                  // systolic flavour: -1 auto, 0 pad-free, 1 padded
     int last_fmt = 0, last_sysG = 0;   // code-table layout of the last run (debug fetch)
+    int64_t last_hi_off = 0;
     bool last_pad = false, last_na = false;
     DevBuf<long long> d_scores;
     DevBuf<uint8_t> d_start, d_complete, d_trace;
@@ -603,6 +604,7 @@ int ba_run(ba_engine* e, int want_trace) {
     size_t scratch_stride = 0, sys_smem = 0;
     int sysG = e->opt_warps;
     SysArgs SA{}, SA1{};  // SA1: the score-only launch of a rebased run
+    int64_t hi_plane_off = 0;  // systolic code arena: slot index at which the 16-bit plane starts (in 32-bit words of the arena)
     bool long_mode = false;
     int long_grid_max = 0, sys_occ = 0;
     if (na_ded) {
@@ -703,11 +705,17 @@ int ba_run(ba_engine* e, int want_trace) {
     // Code words of one pair: the level kernel uses the cell-major table of common.cuh; the systolic kernel writes in the
     // order it computes -- [row block][warp][iteration][lane], 256 contiguous bytes per warp and iteration -- so its table
     // also holds the skewed pipeline's idle slots (about 10-15 % more memory, 15x fewer store transactions).
+    // The arena is counted in units: 8-byte words for the level kernels and the dedicated non-affine kernel, 6-byte slots
+    // (a 32-bit plane followed by a 16-bit plane) for the systolic kernel.
+    const bool planes = kernel == 1 && !na_ded;
+    const int64_t unit = planes ? 6 : 8;
     auto pair_code_words = [&](int n, int m) -> int64_t {
         if (kernel != 1) return code_words(n, m, s);
         if (na_ded) return na_code_words(s, sysG, n, m);
         return sys_code_words(s, plan.pad, sysG, n, m);
     };
+    auto arena_cap_units = [&]() -> int64_t { return planes ? std::max<int64_t>(0, (int64_t)e->d_codes.cap * 8 / 6 - 64) : (int64_t)e->d_codes.cap; };
+    auto arena_alloc_words = [&](int64_t units) -> size_t { return planes ? (size_t)(((units + 64) * 6 + 7) / 8) : (size_t)units; };
     // code arena
     size_t arena_words = 0;
     std::vector<int64_t> wave_begin;  // indices into sorted order
@@ -721,30 +729,30 @@ int ba_run(ba_engine* e, int want_trace) {
         // The arena is sticky: once allocated it is reused as long as the largest pair fits (a 90 GB
         // cudaFree + cudaMalloc costs tens of milliseconds and free memory drifts from run to run).
         // An explicit "code_arena_bytes" is an upper bound on what a wave may use (at least one pair always fits).
-        const int64_t limit_words = e->opt_code_arena_bytes > 0 ? std::max<int64_t>(e->opt_code_arena_bytes / 8, max_words)
+        const int64_t limit_words = e->opt_code_arena_bytes > 0 ? std::max<int64_t>(e->opt_code_arena_bytes / unit, max_words)
                                                                  : std::numeric_limits<int64_t>::max();
         const int64_t want_words = std::min(total_words, limit_words);
-        if ((int64_t)e->d_codes.cap >= max_words &&
-            ((int64_t)e->d_codes.cap >= want_words || (e->opt_code_arena_bytes <= 0 && e->arena_is_budget))) {
-            arena_words = (size_t)std::min<int64_t>((int64_t)e->d_codes.cap, want_words);
+        if (arena_cap_units() >= max_words &&
+            (arena_cap_units() >= want_words || (e->opt_code_arena_bytes <= 0 && e->arena_is_budget))) {
+            arena_words = (size_t)std::min<int64_t>(arena_cap_units(), want_words);
         } else {
             int64_t budget_words = limit_words;
             if (e->opt_code_arena_bytes <= 0) {
                 size_t fr = 0, tot = 0;
                 CU(cudaMemGetInfo(&fr, &tot));
-                budget_words = std::max<int64_t>((int64_t)(fr + e->d_codes.cap * 8) / 2 / 8, max_words);
+                budget_words = std::max<int64_t>((int64_t)(fr + e->d_codes.cap * 8) / 2 / unit - 64, max_words);
             }
             arena_words = (size_t)std::min(budget_words, total_words);
             e->arena_is_budget = e->opt_code_arena_bytes <= 0 && budget_words <= total_words;
         }
-        cudaError_t ce = e->d_codes.ensure(arena_words);
+        cudaError_t ce = e->d_codes.ensure(arena_alloc_words((int64_t)arena_words));
         // automatic sizing only: a failed allocation (fragmentation, another tenant on the GPU) is retried with half
         // the arena, i.e. more waves, down to the largest single pair
         while (ce == cudaErrorMemoryAllocation && e->opt_code_arena_bytes <= 0 && (int64_t)arena_words > max_words) {
             cudaGetLastError();  // clear the sticky allocation error
             arena_words = (size_t)std::max<int64_t>((int64_t)arena_words / 2, max_words);
             e->arena_is_budget = true;
-            ce = e->d_codes.ensure(arena_words);
+            ce = e->d_codes.ensure(arena_alloc_words((int64_t)arena_words));
         }
         if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "traceback-code arena: " + std::string(cudaGetErrorString(ce)));
     }
@@ -895,6 +903,8 @@ int ba_run(ba_engine* e, int want_trace) {
         }
         SA.bnd = e->d_bnd.p; SA.bnd_iters = biters + 8;  // matches sys_boundary_ints: slack records in front
         SA.codes = want_trace ? e->d_codes.p : nullptr;
+        hi_plane_off = ((int64_t)arena_words + 63) & ~(int64_t)63;  // the 16-bit plane starts behind the 32-bit one (128-byte aligned)
+        SA.codes_hi = want_trace ? reinterpret_cast<uint16_t*>(reinterpret_cast<uint32_t*>(e->d_codes.p) + hi_plane_off) : nullptr;
         SA.scores = e->d_scores.p; SA.start_state = e->d_start.p; SA.end_values = e->d_endv.p;
         if (rebase) {
             // row maxima of every pair (caller order), "minus infinity" until the score-only launch has raised them
@@ -1009,6 +1019,7 @@ int ba_run(ba_engine* e, int want_trace) {
         if (want_trace) {
             TraceArgs T{};
             T.pairs = e->d_desc.p + b; T.npairs = (int)cnt; T.s = s; T.codes = e->d_codes.p; T.fmt = affine ? kernel : 2;
+            T.codes_hi = SA.codes_hi;
             T.start_state = e->d_start.p; T.trace = e->d_trace.p; T.trace_len = e->d_tlen.p; T.complete = e->d_complete.p;
             if (na_ded) {
                 T.fmt = 3; T.sysG = sysG;
@@ -1041,7 +1052,7 @@ int ba_run(ba_engine* e, int want_trace) {
     if (want_trace) {
         for (int64_t q = wave_begin[n_waves - 1]; q < N; ++q) e->h_last_code_off[e->h_desc[q].orig] = e->h_desc[q].code_off;
         int64_t cb = 0;
-        for (int64_t p = 0; p < N; ++p) cb += pair_code_words(ln[p], lm[p]) * 8;
+        for (int64_t p = 0; p < N; ++p) cb += pair_code_words(ln[p], lm[p]) * unit;
         e->stats.code_bytes = cb;
     }
     if (rebase) {
@@ -1119,6 +1130,7 @@ int ba_run(ba_engine* e, int want_trace) {
     e->last_sysG = kernel == 1 ? sysG : 0;
     e->last_na = na_ded;
     e->last_pad = kernel == 1 && plan.pad;
+    e->last_hi_off = hi_plane_off;
     e->ran = true;
     e->ran_trace = want_trace != 0;
     return BA_OK;
@@ -1258,14 +1270,21 @@ int ba_debug_fetch_codes(ba_engine* e, int64_t pair, uint64_t* out, int64_t word
     const SysGeo geo = sys_geo(S, e->last_pad);
     const int G = e->last_sysG, nit_all = sys_iters(S, e->last_pad, G, m) + 4;
     const int64_t raw = sys_code_words(S, e->last_pad, G, n, m);
-    std::vector<uint64_t> tmp((size_t)raw);
-    CU(cudaMemcpyAsync(tmp.data(), e->d_codes.p + e->h_last_code_off[pair], (size_t)raw * 8, cudaMemcpyDeviceToHost, e->stream));
+    // slots live in two planes: the low word and the upper half of the high word (the fill's 64-bit code word is rebuilt here)
+    std::vector<uint32_t> lo((size_t)raw);
+    std::vector<uint16_t> hi((size_t)raw);
+    const uint32_t* plane_lo = reinterpret_cast<const uint32_t*>(e->d_codes.p);
+    const uint16_t* plane_hi = reinterpret_cast<const uint16_t*>(plane_lo + e->last_hi_off);
+    CU(cudaMemcpyAsync(lo.data(), plane_lo + e->h_last_code_off[pair], (size_t)raw * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(hi.data(), plane_hi + e->h_last_code_off[pair], (size_t)raw * 2, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     for (int i = 0; i <= n; ++i)
         for (int a = -S; a <= S; ++a)
             for (int j = 0; j <= m; ++j)
-                for (int b = -S; b <= S; ++b)
-                    out[code_index(m, S, i, j, a, b)] = tmp[(size_t)sys_code_index(geo.R, geo.LPR, geo.P, S, G, nit_all, i, j, a, b)];
+                for (int b = -S; b <= S; ++b) {
+                    const size_t q = (size_t)sys_code_index(geo.R, geo.LPR, geo.P, S, G, nit_all, i, j, a, b);
+                    out[code_index(m, S, i, j, a, b)] = (uint64_t)lo[q] | ((uint64_t)hi[q] << 48);
+                }
     return BA_OK;
 }
 

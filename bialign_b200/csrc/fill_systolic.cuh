@@ -36,8 +36,8 @@
 // Traceback codes.  With TRACE the integers carry the tie-break of pyx:555-564 in their low bits:
 // value << TB | (inverted rank of the tie key (|T0|+|T1|, |T1|) of (cell, source state)) << 5 |
 // id field (27 - source state), so plain integer max implements (value desc, key asc, case id asc) exactly.  The id
-// field of the winner (5 bits per state, 45 bits per cell) is streamed to HBM, one 8-byte word per
-// cell, each lane writing its own contiguous stream.
+// field of the winner (5 bits per state, 45 bits per cell) is streamed to HBM in computation order, six bytes
+// per lane and iteration: a 32-bit word (states 0-5) and a 16-bit half (states 6-8) in two planes.
 #pragma once
 #include <utility>
 
@@ -134,8 +134,12 @@ __device__ __forceinline__ void stg64o_if(const void* p, unsigned lo, unsigned h
     asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %3, 0;\n @pp st.global.v2.b32 [%0+%4], {%1, %2};\n}\n" ::"l"(p), "r"(lo), "r"(hi), "r"((int)c), "n"(OFF) : "memory");
 }
 template <int OFF>
-__device__ __forceinline__ void stg64o(const void* p, unsigned lo, unsigned hi) {
-    asm volatile("st.global.v2.b32 [%0+%3], {%1, %2};\n" ::"l"(p), "r"(lo), "r"(hi), "n"(OFF) : "memory");
+__device__ __forceinline__ void stg32o(const void* p, unsigned v) {
+    asm volatile("st.global.b32 [%0+%2], %1;\n" ::"l"(p), "r"(v), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void stg16o(const void* p, unsigned v) {  // low 16 bits of v
+    asm volatile("{\n .reg .b16 hh;\n cvt.u16.u32 hh, %1;\n st.global.b16 [%0+%2], hh;\n}\n" ::"l"(p), "r"(v), "n"(OFF) : "memory");
 }
 template <int SOFF, int GOFF>
 __device__ __forceinline__ void cp_async4so_if(unsigned smem_dst, const void* gsrc, bool c) {
@@ -296,7 +300,9 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
     constexpr bool SELFREG = G_::SELFREG;
     constexpr int RSLOT = G_::RSLOT, REC = G_::REC, REAL = G_::REAL, LA = G_::LA, XSLOT = G_::XSLOT, LQB = G_::LQB, XA = G_::XA;
     constexpr int RSLOTB = RSLOT * 4, XSLOTB = XSLOT * 4, RECB = REC * 4;
-    constexpr bool PF = LONG && (P - 1) >= 2;       // ring inputs fetched one iteration ahead (pays off in the long-pair pipeline only)
+    // ring inputs fetched one iteration ahead: pays off only where the long-pair pipeline is latency-bound (wide bands, two CTAs
+    // per SM: 8192 x 8192 at max_shift 3 +1.4 %); at max_shift <= 2 with four CTAs per SM it costs 5 % (measured on gangs of 2000-aa pairs)
+    constexpr bool PF = LONG && S >= 3;
 #ifdef BA_SYS_NO_STEADY
     constexpr bool STEADY_OK = false;
 #else
@@ -514,8 +520,11 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
             // appends 256 contiguous bytes per iteration to its own stream (two full lines per store instruction; the
             // cell-major layout costs one 32-byte sector per lane).  Every lane stores in every iteration: slots of lanes
             // or iterations outside the pair are simply never read (sys_code_index, kernels.cuh).
-            uint64_t* cw = nullptr;  // this lane's slot of the current iteration
-            if (TRACE) cw = A.codes + d.code_off + ((long long)pass * G + g) * (long long)((m + 1) * P + 2 * (RT - 1) + LPR + RING + PRE) * 32 + lane;
+            // A slot is 6 bytes in two planes with the same index: a 32-bit word (states 0-5) and a 16-bit half (states 6-8).
+            uint32_t* const codes_lo = reinterpret_cast<uint32_t*>(A.codes);
+            uint32_t* cw = nullptr;  // this lane's slot of the current iteration (low plane)
+            uint16_t* ch = nullptr;  // steady blocks: the same slot in the high plane
+            if (TRACE) cw = codes_lo + d.code_off + ((long long)pass * G + g) * (long long)((m + 1) * P + 2 * (RT - 1) + LPR + RING + PRE) * 32 + lane;
 
             // plain affine flavour: a lane at k = 0 poisons its x2 = 1 cases itself (their sources sit at k = -1, lanes that
             // are outside the pair and, in steady blocks, not masked), so the first rows of a pair can run steady blocks too
@@ -622,7 +631,7 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                             lane_ok = lane_real && i <= dn.n && k >= 0 && k <= dn.n;
                             simrow = ssim + ((lane_ok && i >= 1) ? A.res[dn.offA + i - 1] : nsym) * nsym;
                             Ak = (lane_ok && k >= 1) ? A.cls[dn.offA + k - 1] : 254;
-                            if (TRACE) cw = A.codes + dn.code_off + ((long long)g * ((dn.m + 1) * P + 2 * (RT - 1) + LPR + RING + PRE) + sigma + PRE) * 32 + lane;
+                            if (TRACE) cw = codes_lo + dn.code_off + ((long long)g * ((dn.m + 1) * P + 2 * (RT - 1) + LPR + RING + PRE) + sigma + PRE) * 32 + lane;
                         } else {  // no more pairs: idle until the array has drained
                             cur_n = -1; cur_m = 0x3fffffff; lane_ok = false; simrow = ssim + nsym * nsym; Ak = 254;
                         }
@@ -851,8 +860,8 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                 if (TRACE && NA) {
                     // the cell's single traceback code: case index of the best state (value desc, case order asc)
                     const int bestp = vmax3(vmax3(M[0], M[1], M[2]), vmax3(M[3], M[4], M[5]), vmax3(M[6], M[7], M[8]));
-                    if constexpr (ST) stg64o<u * 256>(cw, 15u - (unsigned)(bestp & 15), 0u);
-                    else { stg64o<0>(cw, 15u - (unsigned)(bestp & 15), 0u); cw += 32; }
+                    if constexpr (ST) stg32o<u * 128>(cw, 15u - (unsigned)(bestp & 15));
+                    else { stg32o<0>(cw, 15u - (unsigned)(bestp & 15)); cw += 32; }
                     const int msk = ~((1 << TB) - 1);
 #pragma unroll
                     for (int t = 0; t < 9; ++t) M[t] &= msk;  // as a source a state carries no tie information
@@ -864,8 +873,17 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                     for (int t = 0; t < 6; ++t) lo = __funnelshift_r(lo, (unsigned)M[t], 5);
 #pragma unroll
                     for (int t = 6; t < 9; ++t) hi = __funnelshift_r(hi, (unsigned)M[t], 5);
-                    if constexpr (ST) stg64o<u * 256>(cw, lo, hi);
-                    else { if (!CHAIN || kidx < K) stg64o<0>(cw, lo, hi); cw += 32; }
+                    // (the three fields of the high word sit in its upper half: only that half is stored)
+                    if constexpr (ST) {
+                        stg32o<u * 128>(cw, lo);
+                        stg16o<u * 64>(ch, hi >> 16);
+                    } else {
+                        if (!CHAIN || kidx < K) {
+                            stg32o<0>(cw, lo);
+                            stg16o<0>(A.codes_hi + (cw - codes_lo), hi >> 16);
+                        }
+                        cw += 32;
+                    }
                     // table layout [source state][b][lane column]: for one source state the lanes of a warp read
                     // (at most P*LPR <= 32) consecutive words -> no bank conflicts
                     const int msk = ~((1 << TB) - 1);
@@ -1041,6 +1059,7 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                     const int ph = (pslot + 1 == PB) ? 0 : pslot + 1;           // 0 or RING
                     pb_cur = pb_s + ph * RECB;
                     pb_oth = pb_s + (ph ? 0 : LA) * RECB;
+                    if (TRACE && !NA) ch = A.codes_hi + (cw - codes_lo);
                     steady_block(iteration, q, std::make_integer_sequence<int, RING>{});
                     q += RING;
                     pslot = ph + RING - 1;

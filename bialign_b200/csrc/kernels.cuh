@@ -47,7 +47,8 @@ struct SysArgs {
     int bnd_iters;
     int lq_iters;             // LONG flavour: iterations between progress-flag exchanges (a multiple of the ring period; 0 = default)
     int cpp;                  // LONG flavour: CTAs per pair (gang size); pair p is run by CTAs [p * cpp, (p + 1) * cpp)
-    uint64_t* codes;
+    uint64_t* codes;          // code arena; the systolic kernel uses it as a plane of 32-bit words ...
+    uint16_t* codes_hi;       // ... plus this plane of 16-bit halves, same slot index (PairDesc::code_off counts slots)
     long long* scores;
     uint8_t* start_state;
     int* end_values;
@@ -63,6 +64,7 @@ struct TraceArgs {
     int npairs;
     int s;
     const uint64_t* codes;
+    const uint16_t* codes_hi; // systolic layout (sysG > 0, fmt 1 / 2): the 16-bit plane; codes is then the 32-bit plane
     int fmt;                  // 0: nibble t = case id (generic kernel); 1: 5-bit tie fields (systolic kernel);
                               // 2: non-affine model, low nibble = case index 0..12
                               // 3: non-affine model, dedicated kernel: uint32 per (row, j, b), nibble a+S = case index
@@ -85,7 +87,7 @@ size_t sys_smem_bytes(int S, bool pad, int G, int nsym, int mmax, bool p16 = fal
 int sys_occupancy_p16(int S, int G, size_t smem);
 cudaError_t launch_fill_systolic_p16(const SysArgs& A, int grid, int G, size_t smem, cudaStream_t st);
 int sys_iters(int S, bool pad, int G, int m);
-// Code-table geometry of the systolic kernel: [row block][warp][iteration][lane], one uint64 per slot.
+// Code-table geometry of the systolic kernel: [row block][warp][iteration][lane] slots (6 bytes each, two planes).
 long long sys_code_words(int S, bool pad, int G, int n, int m);
 __host__ __device__ __forceinline__ long long sys_code_index(int R, int LPR, int P, int S, int G, int nit_all, int i, int j, int a, int b) {
     // nit_all = iterations per row block incl. the PRE warm-up ones; lane (row r of warp g, column c = a+S) computes

@@ -2,7 +2,7 @@
 //
 // The reference re-enumerates the cases at every visited cell and breaks ties by the "fewest
 // shifts" key (pyx:547-571); because that key depends only on (predecessor cell, source state) the
-// fill already stored the winner, so each step here is one 8-byte (4-byte) read, a field extract and a
+// fill already stored the winner, so each step here is one read of 2-8 bytes, a field extract and a
 // table decode.  The walk is a dependent chain of <= 2(n+m) reads, so throughput comes from running
 // thousands of pairs side by side (one thread per pair).
 #include "common.cuh"
@@ -13,6 +13,7 @@ namespace ba {
 __constant__ int NA_XBITS_TB[13] = {15, 10, 5, 12, 3, 8, 4, 2, 1, 11, 7, 14, 13};  // pyx:233-248 order
 
 struct Walk {
+    long long slot0;  // first slot of the pair (systolic layout)
     int i, j, k, l, state, len, ok;
     bool first;  // the reference's very first termination test never fires (pyx:551, tuple vs list)
     uint8_t* out;
@@ -22,7 +23,7 @@ struct Walk {
 __device__ __forceinline__ const void* code_addr(const TraceArgs& A, const uint64_t* codes, int m, int s, int nit_all, int nit_na,
                                                  int i, int j, int k, int l) {
     if (A.fmt == 3) return reinterpret_cast<const uint32_t*>(codes) + na_code_index(s, A.sysG, nit_na, i, j, l - j);
-    return codes + (A.sysG ? sys_code_index(A.R, A.LPR, A.P, s, A.sysG, nit_all, i, j, k - i, l - j) : code_index(m, s, i, j, k - i, l - j));
+    return codes + code_index(m, s, i, j, k - i, l - j);
 }
 
 // One step of the walk; returns false when the walk ends (w.ok then tells whether it ended at the origin).
@@ -33,7 +34,9 @@ __device__ __forceinline__ bool walk_step(const TraceArgs& A, const uint64_t* co
         return false;
     }
     w.first = false;
-    const void* addr = code_addr(A, codes, m, s, nit_all, nit_na, i, j, k, l);
+    const bool planes = A.sysG > 0 && A.fmt != 3;  // systolic kernel: slot index into a 32-bit and a 16-bit plane
+    const long long slot = planes ? w.slot0 + sys_code_index(A.R, A.LPR, A.P, s, A.sysG, nit_all, i, j, k - i, l - j) : 0;
+    const void* addr = planes ? nullptr : code_addr(A, codes, m, s, nit_all, nit_na, i, j, k, l);
     if (A.fmt == 3) {  // dedicated non-affine kernel: one nibble per cell, the walk ends at the first cell without a case
         const uint32_t w32 = __ldg(reinterpret_cast<const uint32_t*>(addr));
         const int cidx = (int)((w32 >> (4 * (k - i + s))) & 15);
@@ -45,10 +48,10 @@ __device__ __forceinline__ bool walk_step(const TraceArgs& A, const uint64_t* co
         if ((i | j | k | l) < 0 || abs(k - i) > s || abs(l - j) > s) { w.ok = 0; return false; }
         return true;
     }
-    const uint64_t wd = __ldg(reinterpret_cast<const uint64_t*>(addr));
+    const uint64_t wd = planes ? 0 : __ldg(reinterpret_cast<const uint64_t*>(addr));
     int id;
     if (A.fmt == 2) {  // non-affine: the walk ends when no case reproduces the value (origin), pyx:521-528
-        const int cidx = (int)(wd & 15);
+        const int cidx = planes ? (int)(__ldg(reinterpret_cast<const uint32_t*>(A.codes) + slot) & 15) : (int)(wd & 15);
         if (cidx > 12) { w.ok = 1; return false; }
         const int xbn = NA_XBITS_TB[cidx];
         *--w.out = (uint8_t)xbn;
@@ -66,8 +69,9 @@ __device__ __forceinline__ bool walk_step(const TraceArgs& A, const uint64_t* co
         //   19..27        full column, case id = source = 27 - f                     (ids 0-8)
         //    9..17        x=(0,0,t2,t3), source (t01, h): f = 17 - 3*t01 - rank(h)   (ids 9-11, h = 11,10,01)
         //    0..8         x=(t0,t1,0,0), source (h, t23): f = 8 - 3*rank(h) - t23    (ids 12-14)
-        const unsigned half = state < 6 ? (unsigned)wd : (unsigned)(wd >> 32);
-        const int f = (int)((half >> (state < 6 ? 2 + 5 * state : 17 + 5 * (state - 6))) & 31);
+        // -- of which only the upper half is kept, in the 16-bit plane.  One read per step: 4 or 2 bytes.
+        const int f = state < 6 ? (int)((__ldg(reinterpret_cast<const uint32_t*>(A.codes) + slot) >> (2 + 5 * state)) & 31)
+                                : (int)((__ldg(A.codes_hi + slot) >> (1 + 5 * (state - 6))) & 31);
         const int t01 = state / 3, t23 = state % 3;
         id = 15;
         if (f >= 19 && f <= 27) id = 27 - f;
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(128) traceback_kernel(TraceArgs A) {
     w.i = n; w.j = m; w.k = n; w.l = m;
     w.state = A.start_state[d.orig];
     w.out = A.trace + d.trace_off + d.trace_cap;  // one past the end of the slot
-    w.len = 0; w.ok = 0; w.first = true;
+    w.len = 0; w.ok = 0; w.first = true; w.slot0 = d.code_off;
     while (w.len < d.trace_cap && walk_step(A, codes, m, s, nit_all, nit_na, w)) {}
     A.trace_len[d.orig] = w.len;
     A.complete[d.orig] = (uint8_t)w.ok;

@@ -179,6 +179,7 @@ def test_systolic_multipass_and_cta_shapes(warps, pad):
         al = _aligner(params)
         _select(al, 1 + pad)
         al.set_option("warps_per_cta", warps)
+        al.set_option("long", 0)  # (few pairs with many row blocks would otherwise run as long-pair gangs: tested below)
         try:
             assert _check_batch(al, seqs, structs, pairs, params, table_pairs=2) == 1 + pad
         finally:
@@ -688,7 +689,7 @@ def test_rebased_trace_run_forced_vs_oracle(s):
 
 def test_rebased_trace_run_beyond_packed_range():
     """Scores without a common divisor (structure_weight 333): value << tie bits leaves 32 bits beyond ~800 residues (even for
-    the padded flavour).  The engine then picks the rebased run on its own (kernel_kind 11; 12 in long-pair mode) instead of the level kernel.
+    the padded flavour).  The engine then picks the rebased run on its own (kernel_kind 11, or 12 when the pairs run as long-pair gangs) instead of the level kernel.
     Oracle on a subsample, the level kernel (kernel = 0) on everything: scores, traces, completeness."""
     from bialign_b200.batch import trace_hex
 
@@ -702,7 +703,7 @@ def test_rebased_trace_run_beyond_packed_range():
     al = _aligner(params)
     fast = al.align(seqs, structs, pairs, want_trace=True)
     st = al.engine.stats()
-    assert st["kernel_kind"] == 11 and st["fallback_pairs"] <= 2, st
+    assert st["kernel_kind"] in (11, 12) and st["fallback_pairs"] <= 2, st  # 12: few enough pairs for long-pair gangs
     al.set_option("kernel", 0)
     try:
         slow = al.align(seqs, structs, pairs, want_trace=True)
