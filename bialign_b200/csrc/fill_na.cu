@@ -21,6 +21,10 @@
 #include "common.cuh"
 #include "kernels.cuh"
 
+#ifndef BA_NA_RECV
+#define BA_NA_RECV 1
+#endif
+
 namespace ba {
 namespace na {
 
@@ -36,17 +40,35 @@ struct Geo {
     static constexpr int XW = 8;              // ints per exchange record (W <= 7 values)
     static constexpr int PRE = P + 1;         // iterations run before position 0 so that the staged row above is primed
     static constexpr int LA = 8;              // cp.async look-ahead of the boundary staging (iterations)
-    static constexpr int PB = 16;             // landing-zone depth, power of two > LA
+    static constexpr int PB = 16;             // landing-zone depth = 2 LA (a power of two)
 };
 
 __device__ __forceinline__ int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); }
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+__device__ __forceinline__ int lds32(unsigned addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void stg32o_if(const void* p, int v, bool c) {  // [p + OFF] = v iff c (no branch)
+    asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %2, 0;\n @pp st.global.b32 [%0+%3], %1;\n}\n" ::"l"(p), "r"(v), "r"((int)c), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void sts32o_if(unsigned addr, int v, bool c) {
+    asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %2, 0;\n @pp st.shared.s32 [%0+%3], %1;\n}\n" ::"r"(addr), "r"(v), "r"((int)c), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void cp_async4o_if(unsigned smem_dst, const void* gsrc, bool c) {  // 4 bytes, [gsrc + OFF] -> smem_dst iff c
+    asm volatile("{\n .reg .pred pp;\n setp.ne.b32 pp, %2, 0;\n @pp cp.async.ca.shared.global [%0], [%1+%3], 4;\n}\n" ::"r"(smem_dst), "l"(gsrc), "r"((int)c), "n"(OFF) : "memory");
+}
+
 template <bool V> struct BC_ { static constexpr bool value = V; };
 template <int V> struct IC_ { static constexpr int value = V; };
-template <class F, int... U>
+template <bool SEL, class F, int... U>
 __device__ __forceinline__ void steady_block(F& f, const int q, std::integer_sequence<int, U...>) {
-    ((f(BC_<true>{}, IC_<U>{}, q + U), __syncthreads()), ...);
+    ((f(BC_<true>{}, BC_<SEL>{}, IC_<U>{}, q + U), __syncthreads()), ...);
 }
 // One exchange record (8 ints, W of them used): predicated loads into / stores from exactly W registers
 template <int W>
@@ -83,6 +105,7 @@ __global__ void __launch_bounds__(256, 1) fill_na_kernel(SysArgs A) {
     using G_ = Geo<S>;
     constexpr int W = G_::W, P = G_::P, NH = G_::NH, RING = G_::RING, XW = G_::XW, PRE = G_::PRE, LA = G_::LA, PB = G_::PB;
     static_assert(W <= 7 && PRE <= PRE_MAX, "band too wide for this kernel");
+    constexpr bool RECV = BA_NA_RECV && (S <= 2);  // wider bands: the second delay line would cost 56 registers (occupancy)
     extern __shared__ __align__(16) int smem[];
     const int G = blockDim.x >> 5, RT = G * 32;
     int* xs = smem;                                   // [(G+1)][RING][XW]   xs[0] = staged row above the block
@@ -158,11 +181,24 @@ __global__ void __launch_bounds__(256, 1) fill_na_kernel(SysArgs A) {
             for (int dd = 0; dd < NH; ++dd)
 #pragma unroll
                 for (int aa = 0; aa < W; ++aa) h[dd][aa] = NEGP;
+            // RECV: what the lane above sent, rU[d-1][aa] = its value at band offset aa, d iterations ago (one shuffle per band
+            // offset and iteration; the four delays the cases need are taps of this line instead of four shuffles)
+            int rU[RECV ? NH : 1][W];
+#pragma unroll
+            for (int dd = 0; dd < (RECV ? NH : 1); ++dd)
+#pragma unroll
+                for (int aa = 0; aa < W; ++aa) rU[dd][aa] = NEGP;
 
             // boundary I/O: thread e < W moves element e of the record of one iteration
             const bool io = tid < W;
             const int io_e = io ? tid : 0;
             const bool do_flush = has_out && io, do_stage = has_in && io;
+            // running pointers / shared-memory byte addresses of this thread's record element (threads beyond the record shadow
+            // element 0; their stores and copies are predicated off)
+            int* fl_g = bnd_out + io_e;                                                   // record q-1 of iteration q = -PRE
+            const int* st_g = bnd_in + (size_t)(LA + RT + 1) * XW + io_e;                 // record (q + LA + RT) of iteration q = -PRE
+            const unsigned fl_s = smem_u32(xs + G * RING * XW + io_e), st_s = smem_u32(xs + io_e), pb_s = smem_u32(pb + io_e);
+            int pq = (-PRE - 1 + 4 * PB) & (PB - 1);                                      // landing-zone slot of the previous iteration
             if (has_in) {  // prime: records of the producer's iterations q + RT for q = -PRE .. -PRE+LA-1
                 for (int t0 = -PRE; t0 < LA - PRE; ++t0) {
                     const int rec = t0 + RT;
@@ -183,9 +219,11 @@ __global__ void __launch_bounds__(256, 1) fill_na_kernel(SysArgs A) {
 
             // ---- one iteration: W cells of this lane's row.  ST: steady form (no column tests, no end / origin).
             unsigned xin_cur = 0, xin_oth = 0, xout_cur = 0;  // steady blocks: the two halves of the exchange ring
+            unsigned fl_cur = 0, fl_oth = 0, st_cur = 0;      //                ... of the CTA's output block / of the staged row
             bool half = false;
-            auto iteration = [&](auto st_, auto u_, const int q) __attribute__((always_inline)) {
+            auto iteration = [&](auto st_, auto sel_, auto u_, const int q) __attribute__((always_inline)) {
                 constexpr bool ST = decltype(st_)::value;
+                constexpr bool SEL = !ST || decltype(sel_)::value;  // band offsets below row 0 (k < 0) must read "minus infinity"
                 constexpr int u = decltype(u_)::value;  // ST: position inside the block = slot inside the current half
                 ++bb;
                 if (bb == P) { bb = 0; ++j; }
@@ -196,38 +234,54 @@ __global__ void __launch_bounds__(256, 1) fill_na_kernel(SysArgs A) {
                 const int cB = sclsB[l + boff];
 
                 // ---- flush the record of iteration q-1 (exchange block xs[G], written before the last barrier)
-                {
-                    const int ps = ST ? ((half ? NH : 0) + u + RING - 1) % RING : ((slot == 0) ? RING - 1 : slot - 1);
-                    const int val = xs[(G * RING + ps) * XW + io_e];
-                    if (do_flush) bnd_out[(size_t)(q + PRE) * XW + io_e] = val;
+                if (has_out) {
+                    if constexpr (ST) {  // slot u-1 of the current half, or the last slot of the other one
+                        stg32o_if<u * XW * 4>(fl_g, lds32((u >= 1 ? fl_cur : fl_oth) + ((u - 1 + NH) % NH) * (XW * 4)), do_flush);
+                    } else {
+                        stg32o_if<0>(fl_g, lds32(fl_s + ((slot == 0) ? RING - 1 : slot - 1) * (XW * 4)), do_flush);
+                        fl_g += XW;
+                    }
                 }
 
                 // ---- the row above, 1, 2, P and P+1 iterations ago: shuffles; lane 0 reads the exchange block of the warp
                 // above (xs[0]: the staged boundary) with predicated vector loads that overwrite the shuffle results
                 int U1[W], U2[W], UP[W], UQ[W];
+                if constexpr (RECV) {
 #pragma unroll
-                for (int aa = 0; aa < W; ++aa) {
-                    U1[aa] = __shfl_up_sync(0xffffffffu, h[0][aa], 1);
-                    U2[aa] = __shfl_up_sync(0xffffffffu, h[1][aa], 1);
-                    UP[aa] = __shfl_up_sync(0xffffffffu, h[P - 1][aa], 1);
-                    UQ[aa] = __shfl_up_sync(0xffffffffu, h[P][aa], 1);
-                }
-                if constexpr (ST) {
-                    // slot u of the current half; d iterations back: the same half when u >= d, else the other one
-                    lds_rec<W>(U1, (u >= 1 ? xin_cur : xin_oth) + ((u - 1 + NH) % NH) * (XW * 4), lane == 0);
-                    lds_rec<W>(U2, (u >= 2 ? xin_cur : xin_oth) + ((u - 2 + NH) % NH) * (XW * 4), lane == 0);
-                    lds_rec<W>(UP, (u >= P ? xin_cur : xin_oth) + ((u - P + NH) % NH) * (XW * 4), lane == 0);
-                    lds_rec<W>(UQ, xin_oth + u * (XW * 4), lane == 0);
+                    for (int dd = NH - 1; dd >= 1; --dd)
+#pragma unroll
+                        for (int aa = 0; aa < W; ++aa) rU[dd][aa] = rU[dd - 1][aa];
+#pragma unroll
+                    for (int aa = 0; aa < W; ++aa) rU[0][aa] = __shfl_up_sync(0xffffffffu, h[0][aa], 1);
+                    if constexpr (ST) lds_rec<W>(rU[0], (u >= 1 ? xin_cur : xin_oth) + ((u - 1 + NH) % NH) * (XW * 4), lane == 0);
+                    else lds_rec<W>(rU[0], xin_b + (slot == 0 ? RING - 1 : slot - 1) * (XW * 4), lane == 0);
+#pragma unroll
+                    for (int aa = 0; aa < W; ++aa) { U1[aa] = rU[0][aa]; U2[aa] = rU[1][aa]; UP[aa] = rU[P - 1][aa]; UQ[aa] = rU[P][aa]; }
                 } else {
-                    int s1 = slot - 1, s2 = slot - 2, sp = slot - P, sq = slot - (P + 1);
-                    if (s1 < 0) s1 += RING;
-                    if (s2 < 0) s2 += RING;
-                    if (sp < 0) sp += RING;
-                    if (sq < 0) sq += RING;
-                    lds_rec<W>(U1, xin_b + s1 * (XW * 4), lane == 0);
-                    lds_rec<W>(U2, xin_b + s2 * (XW * 4), lane == 0);
-                    lds_rec<W>(UP, xin_b + sp * (XW * 4), lane == 0);
-                    lds_rec<W>(UQ, xin_b + sq * (XW * 4), lane == 0);
+#pragma unroll
+                    for (int aa = 0; aa < W; ++aa) {
+                        U1[aa] = __shfl_up_sync(0xffffffffu, h[0][aa], 1);
+                        U2[aa] = __shfl_up_sync(0xffffffffu, h[1][aa], 1);
+                        UP[aa] = __shfl_up_sync(0xffffffffu, h[P - 1][aa], 1);
+                        UQ[aa] = __shfl_up_sync(0xffffffffu, h[P][aa], 1);
+                    }
+                    if constexpr (ST) {
+                        // slot u of the current half; d iterations back: the same half when u >= d, else the other one
+                        lds_rec<W>(U1, (u >= 1 ? xin_cur : xin_oth) + ((u - 1 + NH) % NH) * (XW * 4), lane == 0);
+                        lds_rec<W>(U2, (u >= 2 ? xin_cur : xin_oth) + ((u - 2 + NH) % NH) * (XW * 4), lane == 0);
+                        lds_rec<W>(UP, (u >= P ? xin_cur : xin_oth) + ((u - P + NH) % NH) * (XW * 4), lane == 0);
+                        lds_rec<W>(UQ, xin_oth + u * (XW * 4), lane == 0);
+                    } else {
+                        int s1 = slot - 1, s2 = slot - 2, sp = slot - P, sq = slot - (P + 1);
+                        if (s1 < 0) s1 += RING;
+                        if (s2 < 0) s2 += RING;
+                        if (sp < 0) sp += RING;
+                        if (sq < 0) sq += RING;
+                        lds_rec<W>(U1, xin_b + s1 * (XW * 4), lane == 0);
+                        lds_rec<W>(U2, xin_b + s2 * (XW * 4), lane == 0);
+                        lds_rec<W>(UP, xin_b + sp * (XW * 4), lane == 0);
+                        lds_rec<W>(UQ, xin_b + sq * (XW * 4), lane == 0);
+                    }
                 }
 
                 // ---- additive constants shared by all band offsets of this iteration (scores of pyx:233-248; the low
@@ -237,25 +291,30 @@ __global__ void __launch_bounds__(256, 1) fill_na_kernel(SysArgs A) {
                 const int c3 = mu1 + kD + pB1 + T_ * 12;
                 const int c5 = kGD + T_ * 10, c6 = kGD + pB1 + T_ * 9, c7 = kGD + T_ * 8, c8 = kGD + pB0 + T_ * 7;
                 const int c11 = mu1 + kGD + pB1 + T_ * 4, c12 = mu1 + kGD + T_ * 3;
+                // the four cases whose second alignment is a match column (0, 4, 9, 10) share mu2: it is added once, to their maximum
+                const int k0 = mu1 + T_ * 15, k4 = kD + pB0 + T_ * 11, k9 = kGD + pB0 + T_ * 6, k10 = kGD + T_ * 5;
                 int M[W];
                 uint32_t code = 0;
 #pragma unroll
                 for (int aa = 0; aa < W; ++aa) {
                     const int mu2 = (cB == cA[aa]) ? w_p : 0;
-                    int v = addmax(UQ[aa], mu1 + mu2 + T_ * 15, NEGP);              // 1111  case 0
-                    v = addmax(U1[aa], c1, v);                                       // 1010  case 1
-                    v = addmax(h[P - 1][aa], c2, v);                                 // 0101  case 2
-                    if (aa + 1 < W) v = addmax(UP[aa + 1], c3, v);                   // 1100  case 3
-                    if (aa >= 1) v = addmax(h[0][aa - 1], mu2 + kD + pB0 + T_ * 11, v);  // 0011  case 4
-                    if (aa + 1 < W) v = addmax(U1[aa + 1], c5, v);                   // 1000  case 5
-                    v = addmax(h[P - 2][aa], c6, v);                                 // 0100  case 6
+                    // three independent chains (max is associative: the case order lives in the low nibble), then the one case
+                    // that depends on this iteration's neighbouring offset
+                    int va = UQ[aa] + k0;                                            // 1111  case 0
+                    va = addmax(U2[aa], k9, va);                                     // 1011  case 9
+                    if (aa >= 1) va = addmax(h[0][aa - 1], k4, va);                  // 0011  case 4
+                    if (aa >= 1) va = addmax(h[P - 1][aa - 1], k10, va);             // 0111  case 10
+                    int vb = addmax(U1[aa], c1, NEGP);                               // 1010  case 1 (and the floor)
+                    vb = addmax(h[P - 1][aa], c2, vb);                               // 0101  case 2
+                    if (aa + 1 < W) vb = addmax(UP[aa + 1], c3, vb);                 // 1100  case 3
+                    if (aa + 1 < W) vb = addmax(U1[aa + 1], c5, vb);                 // 1000  case 5
+                    int vc = h[P - 2][aa] + c6;                                      // 0100  case 6
+                    vc = addmax(h[0][aa], c8, vc);                                   // 0001  case 8
+                    vc = addmax(UP[aa], c11, vc);                                    // 1110  case 11
+                    if (aa + 1 < W) vc = addmax(UQ[aa + 1], c12, vc);                // 1101  case 12
+                    int v = addmax(va, mu2, max(vb, vc));
                     if (aa >= 1) v = addmax(M[aa - 1], c7, v);                       // 0010  case 7 (same iteration)
-                    v = addmax(h[0][aa], c8, v);                                     // 0001  case 8
-                    v = addmax(U2[aa], mu2 + kGD + pB0 + T_ * 6, v);                 // 1011  case 9
-                    if (aa >= 1) v = addmax(h[P - 1][aa - 1], mu2 + kGD + T_ * 5, v);    // 0111  case 10
-                    v = addmax(UP[aa], c11, v);                                      // 1110  case 11
-                    if (aa + 1 < W) v = addmax(UQ[aa + 1], c12, v);                  // 1101  case 12
-                    v = (colok && okA[aa]) ? v : NEGP;
+                    if (SEL) v = (colok && okA[aa]) ? v : NEGP;
                     if (!ST && aa == S && q == q_origin) v = 0;                      // M[0,0,0,0] = 0 (numpy zeros, pyx:27-35)
                     if (TRACE) {
                         code = __funnelshift_r(code, (uint32_t)v, 4);  // low nibble (15 - case index) in at the top
@@ -287,14 +346,17 @@ __global__ void __launch_bounds__(256, 1) fill_na_kernel(SysArgs A) {
                 // ---- stage the row above this block for iteration q (what lane 0 of warp 0 reads from the next one on)
                 if (has_in) {
                     asm volatile("cp.async.wait_group %0;\n" ::"n"(LA - 1) : "memory");
-                    if (do_stage) {
-                        int val = pb[((q + 4 * PB) & (PB - 1)) * XW + io_e];
-                        if (!ST && q + RT >= nit) val = NEGP;
-                        xs[(ST ? (half ? NH : 0) + u : slot) * XW + io_e] = val;
-                        if (ST || q + LA + RT < nit) {
-                            const unsigned dst = smem_u32(pb + ((q + LA + 4 * PB) & (PB - 1)) * XW + io_e);
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(bnd_in + (size_t)(q + LA + RT + PRE + 1) * XW + io_e) : "memory");
-                        }
+                    pq = (pq + 1) & (PB - 1);
+                    int val = lds32(pb_s + pq * (XW * 4));
+                    const unsigned land = pb_s + (pq ^ LA) * (XW * 4);  // slot of iteration q + LA (PB = 2 LA)
+                    if constexpr (ST) {
+                        sts32o_if<u * XW * 4>(st_cur, val, do_stage);
+                        cp_async4o_if<u * XW * 4>(land, st_g, do_stage);
+                    } else {
+                        if (q + RT >= nit) val = NEGP;
+                        sts32o_if<0>(st_s + slot * (XW * 4), val, do_stage);
+                        cp_async4o_if<0>(land, st_g, do_stage && q + LA + RT < nit);
+                        st_g += XW;
                     }
                     asm volatile("cp.async.commit_group;\n" ::: "memory");
                 }
@@ -308,11 +370,20 @@ __global__ void __launch_bounds__(256, 1) fill_na_kernel(SysArgs A) {
                     xin_cur = xin_b + (half ? NH : 0) * (XW * 4);
                     xin_oth = xin_b + (half ? 0 : NH) * (XW * 4);
                     xout_cur = xout_b + (half ? NH : 0) * (XW * 4);
-                    steady_block(iteration, q, std::make_integer_sequence<int, NH>{});
+                    fl_cur = fl_s + (half ? NH : 0) * (XW * 4);
+                    fl_oth = fl_s + (half ? 0 : NH) * (XW * 4);
+                    st_cur = st_s + (half ? NH : 0) * (XW * 4);
+                    // Only band offsets below row 0 (k < 0: the first S rows of a pair) are ever read as "minus infinity" by valid
+                    // cells; everything else outside the pair (rows beyond n, k > n) has larger coordinates than any valid cell
+                    // and is never a source, so steady blocks elsewhere skip the per-cell validity select.
+                    if (S > 0 && pass == 0 && g == 0) steady_block<true>(iteration, q, std::make_integer_sequence<int, NH>{});
+                    else steady_block<false>(iteration, q, std::make_integer_sequence<int, NH>{});
                     q += NH;
                     slot = half ? RING - 1 : NH - 1;
+                    fl_g += NH * XW;
+                    st_g += NH * XW;
                 } else {
-                    iteration(BC_<false>{}, IC_<0>{}, q);
+                    iteration(BC_<false>{}, BC_<true>{}, IC_<0>{}, q);
                     __syncthreads();
                     ++q;
                 }

@@ -193,6 +193,9 @@ __device__ __forceinline__ void open3(int i0, int i1, int i2, int beta, int& o0,
 // Register caps: narrow bands in batch mode fit 128 registers without spills, which (with 54 KB of shared memory per
 // 4-warp CTA) allows four CTAs = 16 warps per SM (measured on config 3: +3.6 % over three CTAs at 142 registers);
 // wider bands and the long-pair flavour keep 168 (three CTAs of 128 threads: 65536 / 384 = 170).
+#ifndef BA_TB_PACKED
+#define BA_TB_PACKED 1
+#endif
 #ifndef BA_LONG_NARROW
 #define BA_LONG_NARROW 1
 #endif
@@ -295,6 +298,7 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
     static_assert(!CHAIN || (!PAD && BNEG && !LONG && !P16 && !NA), "chained short pairs: plain pad-free affine flavour");
     static_assert(!REBASE || (!PAD && BNEG && !P16 && !NA && !CHAIN), "rebased wide-range flavour: plain pad-free affine flavour");
     constexpr bool REB = REBASE && TRACE;             // values are relative to the row maxima of the score-only launch
+    constexpr bool TBPACK = BA_TB_PACKED && TRACE && !NA && S <= 3;  // tie-break table packed three entries per word (3 TB <= 32 bits)
     using G_ = Geo<S, PAD>;
     constexpr int W = G_::W, P = G_::P, LPR = G_::LPR, R = G_::R, RING = G_::RING, NVR = G_::NVR, PB = G_::PB;
     constexpr bool SELFREG = G_::SELFREG;
@@ -344,8 +348,17 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
 
     // ---- one-time shared-memory initialisation: everything "minus infinity"
     for (int q = tid; q < (int)((G + 1) * RING * RSLOT + (G + 1) * RING * XSLOT + PB * REC); q += blockDim.x) smem[q] = NEGP;
-    if (TRACE && !NA)
-        for (int q = tid; q < P * LPR * 12; q += blockDim.x) tbtab[q] = A.tbtab[q];
+    if (TRACE && !NA) {
+        if constexpr (TBPACK) {  // three TB-bit entries per word: word w of (b, column) = states 3w, 3w+1, 3w+2
+            for (int q = tid; q < P * LPR * 3; q += blockDim.x) {
+                const int w = q / (P * LPR), rem = q - w * (P * LPR);
+                const int* src = A.tbtab + (3 * w) * (P * LPR) + rem;
+                tbtab[q] = src[0] | (src[P * LPR] << TB) | (src[2 * P * LPR] << (2 * TB));
+            }
+        } else {
+            for (int q = tid; q < P * LPR * 12; q += blockDim.x) tbtab[q] = A.tbtab[q];
+        }
+    }
     for (int q = tid; q < (nsym + 1) * nsym; q += blockDim.x) ssim[q] = (q < nsym * nsym) ? A.sim_p[q] : 0;
     __syncthreads();
 
@@ -889,8 +902,18 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                     const int msk = ~((1 << TB) - 1);
                     {
                         const unsigned tp = tb_b + bb * (LPR * 4);
+                        if constexpr (TBPACK) {  // three loads instead of nine (the L1 data pipe is the busiest one), six shifts more
 #pragma unroll
-                        for (int t = 0; t < 9; ++t) M[t] = (M[t] & msk) | lds32(tp + t * (P * LPR * 4));
+                            for (int w = 0; w < 3; ++w) {
+                                const unsigned tw = (unsigned)lds32(tp + w * (P * LPR * 4));
+                                M[3 * w + 0] = (M[3 * w + 0] & msk) | (int)(tw & ~msk);
+                                M[3 * w + 1] = (M[3 * w + 1] & msk) | (int)((tw >> TB) & ~msk);
+                                M[3 * w + 2] = (M[3 * w + 2] & msk) | (int)((tw >> (2 * TB)) & ~msk);
+                            }
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 9; ++t) M[t] = (M[t] & msk) | lds32(tp + t * (P * LPR * 4));
+                        }
                     }
                 }
 
