@@ -511,10 +511,11 @@ def run_shapes(world, rank, local_rank, barrier, allmax, allsum, int_peak):
     res, cls, off, pa, pb = workloads.rna_pairs(125000, seed=4 + 100 * rank)
     record("cfg4: 125000 RNA pairs len 120 per GPU, max_shift 2, score only (16-bit pair mode)", al, res, cls, off, pa, pb,
            False, 2, 30, True)
-    # non-affine model (the CLI default, gap_opening_cost 0) on the cfg3 shape: 3000 pairs per GPU, score + traceback
+    # non-affine model (the CLI default, gap_opening_cost 0) on the cfg3 slice: 12 500 pairs per GPU, score + traceback
+    # (3000 pairs, the shape of earlier rounds, leave 1776 resident one-warp CTAs 1.7 pairs each: a third of that run is tail)
     al = BatchAligner(device=local_rank, max_shift=2, **dict(prot, gap_opening_cost=0, gap_cost=-200, shift_cost=-250))
-    res, cls, off, pa, pb = workloads.protein_pairs(3000, seed=3 + 100 * rank)
-    record("non-affine model: 3000 protein pairs 200-500 per GPU, max_shift 2, score+traceback (cells/s)", al, res, cls, off,
+    res, cls, off, pa, pb = workloads.protein_pairs(12500, seed=3 + 100 * rank)
+    record("non-affine model: 12500 protein pairs 200-500 per GPU, max_shift 2, score+traceback (cells/s)", al, res, cls, off,
            pa, pb, True, 2, 26, True)
     # long pairs in a batch (about 90 fit one traceback-memory wave): a gang of CTAs per pair, several pairs per launch
     al = BatchAligner(device=local_rank, max_shift=2, **prot)

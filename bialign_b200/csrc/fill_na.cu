@@ -295,32 +295,41 @@ __global__ void __launch_bounds__(256, 1) fill_na_kernel(SysArgs A) {
                 const int k0 = mu1 + T_ * 15, k4 = kD + pB0 + T_ * 11, k9 = kGD + pB0 + T_ * 6, k10 = kGD + T_ * 5;
                 int M[W];
                 uint32_t code = 0;
+                // Three independent chains per cell (max is associative: the case order lives in the low nibble); inputs that
+                // arrive late (U1: this iteration's shuffle) come last in their chain.  Then the one case that depends on this
+                // iteration's neighbouring offset (0010).  (A running maximum over the cleared values, which takes the nibble
+                // clearing off that chain, measured 2 % slower: five more instructions on the pipe that limits this kernel.)
+                int rest[W];
 #pragma unroll
                 for (int aa = 0; aa < W; ++aa) {
                     const int mu2 = (cB == cA[aa]) ? w_p : 0;
-                    // three independent chains (max is associative: the case order lives in the low nibble), then the one case
-                    // that depends on this iteration's neighbouring offset
                     int va = UQ[aa] + k0;                                            // 1111  case 0
                     va = addmax(U2[aa], k9, va);                                     // 1011  case 9
-                    if (aa >= 1) va = addmax(h[0][aa - 1], k4, va);                  // 0011  case 4
                     if (aa >= 1) va = addmax(h[P - 1][aa - 1], k10, va);             // 0111  case 10
-                    int vb = addmax(U1[aa], c1, NEGP);                               // 1010  case 1 (and the floor)
-                    vb = addmax(h[P - 1][aa], c2, vb);                               // 0101  case 2
+                    if (aa >= 1) va = addmax(h[0][aa - 1], k4, va);                  // 0011  case 4
+                    int vb = addmax(h[P - 1][aa], c2, NEGP);                         // 0101  case 2 (and the floor)
                     if (aa + 1 < W) vb = addmax(UP[aa + 1], c3, vb);                 // 1100  case 3
+                    vb = addmax(U1[aa], c1, vb);                                     // 1010  case 1
                     if (aa + 1 < W) vb = addmax(U1[aa + 1], c5, vb);                 // 1000  case 5
                     int vc = h[P - 2][aa] + c6;                                      // 0100  case 6
-                    vc = addmax(h[0][aa], c8, vc);                                   // 0001  case 8
                     vc = addmax(UP[aa], c11, vc);                                    // 1110  case 11
                     if (aa + 1 < W) vc = addmax(UQ[aa + 1], c12, vc);                // 1101  case 12
-                    int v = addmax(va, mu2, max(vb, vc));
-                    if (aa >= 1) v = addmax(M[aa - 1], c7, v);                       // 0010  case 7 (same iteration)
-                    if (SEL) v = (colok && okA[aa]) ? v : NEGP;
-                    if (!ST && aa == S && q == q_origin) v = 0;                      // M[0,0,0,0] = 0 (numpy zeros, pyx:27-35)
-                    if (TRACE) {
-                        code = __funnelshift_r(code, (uint32_t)v, 4);  // low nibble (15 - case index) in at the top
-                        v &= ~15;
+                    vc = addmax(h[0][aa], c8, vc);                                   // 0001  case 8
+                    rest[aa] = addmax(va, mu2, max(vb, vc));
+                }
+                {
+#pragma unroll
+                    for (int aa = 0; aa < W; ++aa) {
+                        int v = rest[aa];
+                        if (aa >= 1) v = addmax(M[aa - 1], c7, v);                   // 0010  case 7 (same iteration)
+                        if (SEL) v = (colok && okA[aa]) ? v : NEGP;
+                        if (!ST && aa == S && q == q_origin) v = 0;                  // M[0,0,0,0] = 0 (numpy zeros, pyx:27-35)
+                        if (TRACE) {
+                            code = __funnelshift_r(code, (uint32_t)v, 4);  // low nibble (15 - case index) in at the top
+                            v &= ~15;
+                        }
+                        M[aa] = v;
                     }
-                    M[aa] = v;
                 }
                 // nibble aa = case index of band offset aa; a cell no case reaches reads 15 ("none": NEGP has a zero low nibble)
                 if (TRACE) { *cw = (~code) >> (32 - 4 * W); cw += 32; }

@@ -69,6 +69,14 @@ def main():
         res, cls, off, pa, pb = workloads.rna_pairs(125000, seed=4)
         run("cfg4 125k RNA pairs len 120 s=2 score-only", al, res, cls, off, pa, pb, False)
         run("cfg4 125k RNA pairs len 120 s=2 trace", al, res, cls, off, pa, pb, True)
+    if "na12k" in which:  # the non-affine model on the config-3 slice (12 500 pairs: no tail effect), optionally one CTA width
+        na = dict(prot, gap_opening_cost=0, gap_cost=-200, shift_cost=-250)
+        al = BatchAligner(max_shift=2, **na)
+        if os.environ.get("BA_WARPS"):
+            al.set_option("warps_per_cta", int(os.environ["BA_WARPS"]))
+        res, cls, off, pa, pb = workloads.protein_pairs(12500, seed=3)
+        run("non-affine: 12500 protein pairs 200-500 s=2 trace" + (" G=" + os.environ["BA_WARPS"] if os.environ.get("BA_WARPS") else ""),
+            al, res, cls, off, pa, pb, True)
     if "na" in which:
         na = dict(prot, gap_opening_cost=0, gap_cost=-200, shift_cost=-250)
         al = BatchAligner(max_shift=2, **na)
