@@ -105,6 +105,7 @@ struct ba_engine {
     DevBuf<int> d_simp, d_tbtab, d_bnd;
     DevBuf<unsigned long long> d_progress;
     int opt_long = -1;                 // multi-CTA long-pair mode: -1 auto, 0 off, 1 force
+    int opt_io_warp = -1;              // long-pair mode: a dedicated I/O warp per CTA: -1 auto, 0 off, 1 on
     int opt_p16 = -1;                  // 16-bit pair mode for score-only batches: -1 auto, 0 off, 1 force
     int opt_na = -1;                   // non-affine model: -1 / 1 dedicated kernel when applicable, 0 systolic NA flavour
     int opt_chain = -1;                // short pairs chained along j: -1 auto, 0 off, 1 force
@@ -368,6 +369,7 @@ int ba_set_option(ba_engine* e, const char* key, int64_t value) {
     else if (!strcmp(key, "kernel")) return tri(&e->opt_kernel);
     else if (!strcmp(key, "pad")) return tri(&e->opt_pad);
     else if (!strcmp(key, "long")) return tri(&e->opt_long);
+    else if (!strcmp(key, "io_warp")) return tri(&e->opt_io_warp);
     else if (!strcmp(key, "p16")) return tri(&e->opt_p16);
     else if (!strcmp(key, "na_kernel")) return tri(&e->opt_na);
     else if (!strcmp(key, "chain")) return tri(&e->opt_chain);
@@ -606,6 +608,7 @@ int ba_run(ba_engine* e, int want_trace) {
     SysArgs SA{}, SA1{};  // SA1: the score-only launch of a rebased run
     int64_t hi_plane_off = 0;  // systolic code arena: slot index at which the 16-bit plane starts (in 32-bit words of the arena)
     bool long_mode = false;
+    int io_warp = 0;
     int long_grid_max = 0, sys_occ = 0;
     if (na_ded) {
         // CTA width: a row block is 32 rows per warp and lags 32 iterations per warp; estimate warp-iterations per pair
@@ -860,8 +863,12 @@ int ba_run(ba_engine* e, int want_trace) {
         const int npass_max = (nmax + rows_pass) / rows_pass;
         if (!chain_mode && !p16 && affine && plan.bneg && e->opt_long != 0 && npass_max >= 2 && sysG >= 2 &&
             (e->opt_long == 1 || (npass_max >= 8 && biggest_wave * 2 <= max_grid))) {
+            // The I/O warp (one more warp per CTA that owns the boundary I/O and the progress flags) pays where the pipeline is
+            // latency-bound: a handful of pairs whose row blocks are (nearly) all resident.  Measured: 928 x 933 pair 2.69 ->
+            // 2.16 ms, 8192 x 8192 +7 %; gangs of 2000-aa pairs at max_shift 2 lose 13 % (three CTAs per SM instead of four).
+            io_warp = (!rebase && (e->opt_io_warp == 1 || (e->opt_io_warp < 0 && N <= 4))) ? 1 : 0;
             const int occl = rebase ? std::min(sys_occupancy_rebase(s, false, true, sysG, sys_smem), sys_occupancy_rebase(s, true, true, sysG, sys_smem))
-                                    : sys_occupancy_long(s, want_trace != 0, plan.pad, sysG, sys_smem);
+                                    : sys_occupancy_long(s, want_trace != 0, plan.pad, sysG, sys_smem, io_warp != 0);
             int coop = 0;
             cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
             if (occl >= 1 && coop) {
@@ -893,6 +900,8 @@ int ba_run(ba_engine* e, int want_trace) {
             CU(cudaMemcpyAsync(e->d_chains.p, h_chains.data(), sizeof(int) * h_chains.size(), cudaMemcpyHostToDevice, e->stream));
         }
         SA.progress = e->d_progress.p;
+        SA.io_warp = long_mode ? io_warp : 0;
+        SA.gwarps = sysG;
         {   // Flag period of the long-pair pipeline.  Many row blocks (a CTA per block, several per SM): a flag exchange costs an
             // extra barrier and a spinning thread, so it is rare (default, ~32 iterations).  Few row blocks (one CTA per SM, the pair is
             // latency-bound): every row block starts one flag period later than it could, so the period is three ring periods

@@ -166,9 +166,9 @@ __device__ __forceinline__ void sts128o_if(unsigned addr, int x, int y, int z, i
 template <int V> struct IC { static constexpr int value = V; };
 template <bool V> struct BC_ { static constexpr bool value = V; };
 // one statically unrolled ring period: iteration u uses ring slot u; one CTA barrier per iteration
-template <class F, int... U>
+template <bool IO, class F, int... U>
 __device__ __forceinline__ void steady_block(F& f, const int q, std::integer_sequence<int, U...>) {
-    ((f(BC_<true>{}, IC<U>{}, q + U), __syncthreads()), ...);
+    ((f(BC_<true>{}, IC<U>{}, q + U, BC_<IO>{}), __syncthreads()), ...);
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -291,12 +291,13 @@ struct Geo {
 // true ones) won its ties against a superset of its true competitors: it is the reference's trace.  Pairs whose walk fails,
 // whose values rise above 0 or whose final score differs from the first launch's are recomputed by the level kernel (engine.cu).
 constexpr int KCHAIN = BA_KCHAIN;
-template <int S, bool TRACE, bool PAD, bool BNEG, bool LONG, bool P16 = false, bool NA = false, bool CHAIN = false, bool REBASE = false>
+template <int S, bool TRACE, bool PAD, bool BNEG, bool LONG, bool P16 = false, bool NA = false, bool CHAIN = false, bool REBASE = false, bool IOW = false>
 __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNREG_NARROW : BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
     static_assert(!P16 || (!TRACE && !PAD && BNEG && !LONG), "16-bit pair mode: score only, pad-free, beta < 0, batch mode");
     static_assert(!NA || (BNEG && !LONG && !P16), "non-affine flavour: batch mode, 32-bit");
     static_assert(!CHAIN || (!PAD && BNEG && !LONG && !P16 && !NA), "chained short pairs: plain pad-free affine flavour");
     static_assert(!REBASE || (!PAD && BNEG && !P16 && !NA && !CHAIN), "rebased wide-range flavour: plain pad-free affine flavour");
+    static_assert(!IOW || LONG, "the I/O warp exists in the long-pair flavour only");
     constexpr bool REB = REBASE && TRACE;             // values are relative to the row maxima of the score-only launch
     constexpr bool TBPACK = BA_TB_PACKED && TRACE && !NA && S <= 3;  // tie-break table packed three entries per word (3 TB <= 32 bits)
     using G_ = Geo<S, PAD>;
@@ -313,7 +314,10 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
     constexpr bool STEADY_OK = !PAD;                // pad cells need the per-cell validity select
 #endif
     extern __shared__ __align__(16) int smem[];
-    const int G = blockDim.x >> 5;
+    // IOW (long-pair flavour, launched when A.io_warp is set): one more warp than the G compute warps.  It owns the boundary I/O of the CTA -- the flush
+    // of the last row's records, the staging of the incoming stream, the progress flags -- so that no compute warp carries it:
+    // in long-pair mode a CTA advances at the pace of its slowest warp (one barrier per iteration), and that was warp 0.
+    const int G = LONG ? A.gwarps : (int)(blockDim.x >> 5);  // compute warps (a plain kernel argument: stays in uniform registers)
     const int RT = G * R;  // rows per pass
     int* ring = smem;
     int* xs = ring + (size_t)(G + 1) * RING * RSLOT;
@@ -332,7 +336,9 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
 
     const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
     const int r = lane / LPR, c = lane - r * LPR;
-    const bool lane_real = (r < R) && (c < W);
+    const bool io_warp = IOW && g == G;
+    const int ftid = IOW ? G * 32 : 0;  // the thread that publishes / polls progress flags
+    const bool lane_real = (r < R) && (c < W) && !io_warp;
     const int a = c - S;
     const int sigma = 2 * (g * R + r) + c;
     const bool row0 = (r == 0), lastrow = (r == R - 1);
@@ -482,11 +488,11 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
             const unsigned long long tag_in = (unsigned long long)pass << 32;         // producer pass id + 1
             const unsigned long long tag_out = (unsigned long long)(pass + 1) << 32;
             // boundary I/O descriptors: thread e moves record element e (= v*LPR + cs) every iteration
-            const bool io_thread = tid < REAL;
+            const bool io_thread = IOW ? io_warp : tid < REAL;
             // Threads beyond the record shadow element 0 for the (harmless) loads; their stores and copies are predicated off.
             // (Letting them duplicate thread 0's work instead, which makes all of this thread-independent, measured 5 % slower:
             // the fourth warp skipping the boundary I/O matters more than the divergence bookkeeping.)
-            const int io_e = io_thread ? tid : 0;
+            const int io_e = io_thread ? (IOW ? lane : tid) : 0;
             const int io_v = io_e / LPR, io_cs = io_e - io_v * LPR;
             const bool io_ring = io_v < NVR;
             const int io_stride = io_ring ? RSLOT : XSLOT;
@@ -500,15 +506,22 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
             // Boundary streams hold record `rec` at offset (rec + PRE + 1) * REC, so the unconditional flush of
             // "iteration q-1" in the very first iteration lands in a slack record.  Running pointers, shared-memory
             // addresses in bytes: the fast path is ~7 instructions per direction and iteration.
-            const bool do_flush = has_out && io_thread, do_stage = !LONG && has_in && io_thread;
+            const bool do_flush = has_out && io_thread && !IOW, do_stage = !LONG && has_in && io_thread;
+            // IOW: the I/O warp moves the whole record, lane l the elements l, l + 32, ...
+            // (its address arithmetic is redone every iteration inside the I/O branch: kept in registers across the compute
+            // path it would cost every thread of the CTA six registers, and the I/O warp has the time)
+            constexpr int NE = (REAL + 31) / 32;
             // LONG staging: thread e4 < REC/4 moves four consecutive record elements (one 16-byte cp.async.cg)
             constexpr int NVEC = REC / 4;
+            static_assert(NVEC <= 32, "the staging threads must fit one warp");
+            const int stid = IOW ? lane : tid;                                // index among the staging threads
+            const bool stg_thread = (IOW ? io_warp : true) && stid < NVEC;
             unsigned lg_dst[4] = {0, 0, 0, 0};
             int lg_ring = 0, lg_real = 0;
-            if (LONG && tid < NVEC) {
+            if (LONG && stg_thread) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int e = 4 * tid + u, v = e / LPR, cs = e - v * LPR;
+                    const int e = 4 * stid + u, v = e / LPR, cs = e - v * LPR;
                     const bool rg = v < NVR;
                     lg_ring |= rg ? (1 << u) : 0;
                     lg_real |= (e < REAL) ? (1 << u) : 0;
@@ -568,6 +581,10 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                 if (has_in) st_hi = min(st_hi, q_rec_lim - LA);
                 // (REBASE keeps those lanes masked as well: unmasked they would grow without their row's potential)
                 if ((!K0FIX || REBASE) && pass == 0 && g * R < S) st_hi = st_lo;
+                if (io_warp) {  // immediate-offset I/O wherever the staged records exist
+                    st_lo = -PRE;
+                    st_hi = has_in ? q_rec_lim - LA : nit;
+                }
             }
 
             // position of this lane one iteration before the first one (q = -PRE)
@@ -600,15 +617,15 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                 for (int k = 0; k < P - 1; ++k) dL[y][k] = NEGP;
 
             if (LONG && has_in) {  // wait for the first records of the producer pass, then prime with 16-byte copies
-                if (tid == 0) {
+                if (tid == ftid) {
                     const unsigned long long want = tag_in | (unsigned long long)min(LA + 2 * RT, nit);
                     while (ld_acquire_u64(prog_in) < want) __nanosleep(100);
                 }
                 __syncthreads();
                 for (int t0 = -PRE; t0 < LA - PRE; ++t0) {
                     const int rec = t0 + 2 * RT;
-                    if (tid < NVEC && rec < nit)
-                        cp_async16s(smem_u32(pb + ((t0 + PB) % PB) * REC + 4 * tid), bnd_in + (size_t)(rec + PRE + 1) * REC + 4 * tid);
+                    if (stg_thread && rec < nit)
+                        cp_async16s(smem_u32(pb + ((t0 + PB) % PB) * REC + 4 * stid), bnd_in + (size_t)(rec + PRE + 1) * REC + 4 * stid);
                     cp_async_commit();
                 }
             } else if (has_in) {  // prime the cp.async pipeline: records for iterations -PRE..LA-PRE-1
@@ -623,16 +640,62 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
             __syncthreads();
 
             unsigned pb_cur = 0, pb_oth = 0;  // steady blocks: the two halves of the prefetch buffer (this thread's element)
-            // ---- one iteration (one band cell per lane).  ST: steady form, u = ring slot (compile time).
-            auto iteration = [&](auto st_, auto u_, const int q) __attribute__((always_inline)) {
+            // ---- long-pair flavour: stage the incoming boundary (virtual row above warp 0) for iteration q and fetch the record of
+            // iteration q + LA; run by the staging threads of warp 0, or of the I/O warp (IOW)
+            auto stage_long = [&](auto st_, auto u_, const int q) __attribute__((always_inline)) {
                 constexpr bool ST = decltype(st_)::value;
                 constexpr int u = decltype(u_)::value;
+                const int ws = ST ? u : wslot;
+                    cp_async_wait<LA - 1>();
+                    if (stg_thread) {
+                        const int ps_r = ST ? ((pslot + 1 == PB ? 0 : pslot + 1) + u) : pslot;  // prefetch-buffer slot of q
+                        const int ps_w = ps_r >= LA ? ps_r - LA : ps_r + LA;                     // ... and of q + LA
+                        int4 v4 = make_int4(NEGP, NEGP, NEGP, NEGP);
+                        if (ST || q < q_rec_lim) v4 = *reinterpret_cast<const int4*>(pb + ps_r * REC + 4 * stid);
+                        const int vals[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                        for (int uu = 0; uu < 4; ++uu)
+                            if ((lg_real >> uu) & 1)
+                                sts32(lg_dst[uu] + (((lg_ring >> uu) & 1) ? ws * RSLOTB : ws * XSLOTB), vals[uu]);
+                        if (ST || q + LA < q_rec_lim)
+                            cp_async16s(smem_u32(pb + ps_w * REC + 4 * stid),
+                                        bnd_in + (size_t)(q + LA + 2 * RT + PRE + 1) * REC + 4 * stid);
+                    }
+                    cp_async_commit();
+            };
+            // ---- one iteration (one band cell per lane).  ST: steady form, u = ring slot (compile time).
+            // IO: the instantiation the I/O warp runs (a loop of its own: merging the two roles after every iteration would
+            // undo the register renaming of the steady blocks)
+            auto iteration = [&](auto st_, auto u_, const int q, auto io_) __attribute__((always_inline)) {
+                constexpr bool ST = decltype(st_)::value;
+                constexpr int u = decltype(u_)::value;
+                constexpr bool IO = IOW && decltype(io_)::value;
                 // ---- advance position
                 ++bb;
                 if (bb == P) { bb = 0; ++j; }
                 if (!ST) {
                     wslot = (wslot + 1 == RING) ? 0 : wslot + 1;
                     pslot = (pslot + 1 == PB) ? 0 : pslot + 1;
+                }
+                if constexpr (IO) {
+                    {  // the I/O warp: flush the record of iteration q-1, stage the one of iteration q, nothing else
+#pragma unroll
+                        for (int kk = 0; kk < NE; ++kk) {
+                            const int e0 = lane + 32 * kk;
+                            const bool on = has_out && e0 < REAL;
+                            const int e = e0 < REAL ? e0 : 0, v = e / LPR, cs = e - v * LPR, x = e - NVR * LPR;
+                            const bool rg = v < NVR;
+                            const int col = rg ? v * 32 + (R - 1) * LPR + cs + G * RING * RSLOT
+                                               : (int)((G + 1) * RING * RSLOT) + (x < 4 * LPR ? x : XA + x - 4 * LPR) + G * RING * XSLOT;
+                            const int ps = ST ? (u + RING - 1) % RING : ((wslot == 0) ? RING - 1 : wslot - 1);
+                            const int val = lds32(smem_u32(smem + col + ps * (rg ? RSLOT : XSLOT)));
+                            if constexpr (ST) stg32o_if<u * RECB>(fl_g + 32 * kk, val, on);
+                            else stg32_if(fl_g + 32 * kk, val, on);
+                        }
+                        if (!ST) fl_g += REC;
+                        if (has_in) stage_long(st_, u_, q);
+                        return;
+                    }
                 }
                 if constexpr (CHAIN && !ST) {
                     if (bb == 0 && j >= cur_m + 2) {  // past the dead column: this lane enters the next pair of the chain
@@ -673,13 +736,15 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                 }
 
                 // ---- flush the CTA's last row of iteration q-1 to the outgoing boundary stream
-                if constexpr (ST) {
-                    constexpr int ps = (u + RING - 1) % RING;
-                    stg32o_if<u * RECB>(fl_g, lds32(fl_s + ps * io_stride_b), do_flush);
-                } else {
-                    const int ps = (wslot == 0) ? RING - 1 : wslot - 1;
-                    stg32_if(fl_g, lds32(fl_s + ps * io_stride_b), do_flush);
-                    fl_g += REC;
+                if constexpr (!IOW) {
+                    if constexpr (ST) {
+                        constexpr int ps = (u + RING - 1) % RING;
+                        stg32o_if<u * RECB>(fl_g, lds32(fl_s + ps * io_stride_b), do_flush);
+                    } else {
+                        const int ps = (wslot == 0) ? RING - 1 : wslot - 1;
+                        stg32_if(fl_g, lds32(fl_s + ps * io_stride_b), do_flush);
+                        fl_g += REC;
+                    }
                 }
 
                 // ---- gather the 27 inputs
@@ -1015,23 +1080,10 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
 
                 // ---- stage the incoming boundary: virtual row above warp 0, iteration q
                 const int ws = ST ? u : wslot;
-                if (LONG && has_in) {
-                    cp_async_wait<LA - 1>();
-                    if (tid < NVEC) {
-                        const int ps_r = ST ? ((pslot + 1 == PB ? 0 : pslot + 1) + u) : pslot;  // prefetch-buffer slot of q
-                        const int ps_w = ps_r >= LA ? ps_r - LA : ps_r + LA;                     // ... and of q + LA
-                        int4 v4 = make_int4(NEGP, NEGP, NEGP, NEGP);
-                        if (ST || q < q_rec_lim) v4 = *reinterpret_cast<const int4*>(pb + ps_r * REC + 4 * tid);
-                        const int vals[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-                        for (int uu = 0; uu < 4; ++uu)
-                            if ((lg_real >> uu) & 1)
-                                sts32(lg_dst[uu] + (((lg_ring >> uu) & 1) ? ws * RSLOTB : ws * XSLOTB), vals[uu]);
-                        if (ST || q + LA < q_rec_lim)
-                            cp_async16s(smem_u32(pb + ps_w * REC + 4 * tid),
-                                        bnd_in + (size_t)(q + LA + 2 * RT + PRE + 1) * REC + 4 * tid);
+                if (LONG) {
+                    if constexpr (!IOW) {
+                        if (has_in) stage_long(st_, u_, q);
                     }
-                    cp_async_commit();
                 } else if (has_in) {
                     cp_async_wait<LA - 1>();
                     if constexpr (ST) {
@@ -1054,10 +1106,12 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
 
             int next_flag = 0;  // LONG: next iteration (a multiple of RING) at which progress is published / awaited
             const int lqb = (LONG && A.lq_iters > 0) ? A.lq_iters : LQB;
+            auto pass_loop = [&](auto io_) __attribute__((always_inline)) {
+            constexpr bool IO = decltype(io_)::value;
             for (int q = -PRE; q < nit;) {
                 const bool aligned = (wslot == RING - 1);  // q is a multiple of RING
                 if (LONG && aligned && q >= next_flag) {
-                    if (tid == 0) {
+                    if (tid == ftid) {
                         if (has_out && q > 0) {  // records 0..q-2 were stored before the last barrier
                             __threadfence();
                             st_release_u64(prog_out, tag_out | (unsigned long long)(q - 1));
@@ -1083,17 +1137,24 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                     pb_cur = pb_s + ph * RECB;
                     pb_oth = pb_s + (ph ? 0 : LA) * RECB;
                     if (TRACE && !NA) ch = A.codes_hi + (cw - codes_lo);
-                    steady_block(iteration, q, std::make_integer_sequence<int, RING>{});
+                    steady_block<IO>(iteration, q, std::make_integer_sequence<int, RING>{});
                     q += RING;
                     pslot = ph + RING - 1;
                     fl_g += RING * REC;
                     st_g += RING * REC;
                     if (TRACE) cw += RING * 32;
                 } else {
-                    iteration(BC_<false>{}, IC<0>{}, q);
+                    iteration(BC_<false>{}, IC<0>{}, q, io_);
                     __syncthreads();
                     ++q;
                 }
+            }
+            };
+            if constexpr (IOW) {
+                if (io_warp) pass_loop(BC_<true>{});
+                else pass_loop(BC_<false>{});
+            } else {
+                pass_loop(BC_<false>{});
             }
             if (REBASE && lane_ok) {
                 if (!TRACE) atomicMax(A.rowmax + A.row_off[d.orig] + i, runmax);       // row maxima for the rebased launch
@@ -1109,7 +1170,7 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                 __threadfence();
                 if (LONG) {
                     __syncthreads();
-                    if (tid == 0) {
+                    if (tid == ftid) {
                         __threadfence();
                         st_release_u64(prog_out, tag_out | (unsigned long long)nit);
                     }
@@ -1243,21 +1304,24 @@ int occ_rebase_s(bool trace, bool lng, int G, size_t smem) {
 }
 
 // LONG flavour: cooperative launch (all CTAs must be co-resident: they wait on one another)
+// (A.io_warp picks the instantiation with the I/O warp: gwarps + 1 warps per CTA)
 template <int S, bool TRACE, bool PAD>
 cudaError_t launch_long_t(const SysArgs& A, int grid, int G, size_t smem, cudaStream_t st) {
-    auto kern = fill_systolic_kernel<S, TRACE, PAD, true, true>;
+    auto kern = A.io_warp ? fill_systolic_kernel<S, TRACE, PAD, true, true, false, false, false, false, true>
+                          : fill_systolic_kernel<S, TRACE, PAD, true, true>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     SysArgs a = A;
     void* params[] = {&a};
-    return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(G * 32), params, smem, st);
+    return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3((G + (A.io_warp ? 1 : 0)) * 32), params, smem, st);
 }
 template <int S, bool TRACE, bool PAD>
-int occ_long_t(int G, size_t smem) {
-    auto kern = fill_systolic_kernel<S, TRACE, PAD, true, true>;
+int occ_long_t(int G, size_t smem, bool iow) {  // G: compute warps
+    auto kern = iow ? fill_systolic_kernel<S, TRACE, PAD, true, true, false, false, false, false, true>
+                    : fill_systolic_kernel<S, TRACE, PAD, true, true>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, G * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, (G + (iow ? 1 : 0)) * 32, smem);
     return nb;
 }
 
@@ -1284,9 +1348,9 @@ cudaError_t launch_long_s(const SysArgs& A, int grid, int G, size_t smem, bool t
     return trace ? launch_long_t<S, true, false>(A, grid, G, smem, st) : launch_long_t<S, false, false>(A, grid, G, smem, st);
 }
 template <int S>
-int occ_long_s(bool trace, bool pad, int G, size_t smem) {
-    if (pad) return trace ? occ_long_t<S, true, true>(G, smem) : occ_long_t<S, false, true>(G, smem);
-    return trace ? occ_long_t<S, true, false>(G, smem) : occ_long_t<S, false, false>(G, smem);
+int occ_long_s(bool trace, bool pad, int G, size_t smem, bool iow) {
+    if (pad) return trace ? occ_long_t<S, true, true>(G, smem, iow) : occ_long_t<S, false, true>(G, smem, iow);
+    return trace ? occ_long_t<S, true, false>(G, smem, iow) : occ_long_t<S, false, false>(G, smem, iow);
 }
 template <int S>
 int occ_s(bool trace, bool pad, bool bneg, int G, size_t smem) {

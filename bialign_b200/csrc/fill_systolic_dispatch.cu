@@ -8,7 +8,7 @@ namespace ba {
     cudaError_t launch_fill_systolic_s##s(const SysArgs&, int, int, size_t, bool, bool, bool, cudaStream_t);            \
     int sys_occupancy_s##s(bool, bool, bool, int, size_t);                                                              \
     cudaError_t launch_fill_systolic_long_s##s(const SysArgs&, int, int, size_t, bool, bool, cudaStream_t);             \
-    int sys_occupancy_long_s##s(bool, bool, int, size_t);                                                              \
+    int sys_occupancy_long_s##s(bool, bool, int, size_t, bool);                                                              \
     size_t sys_smem_bytes_s##s(bool, int, int, int, bool);                                                              \
     cudaError_t launch_fill_systolic_p16_s##s(const SysArgs&, int, int, size_t, cudaStream_t);                          \
     int sys_occupancy_p16_s##s(int, size_t);                                                                            \
@@ -129,13 +129,13 @@ cudaError_t launch_fill_systolic_na(const SysArgs& A, int grid, int G, size_t sm
     return cudaErrorInvalidValue;
 }
 
-int sys_occupancy_long(int S, bool trace, bool pad, int G, size_t smem) {
+int sys_occupancy_long(int S, bool trace, bool pad, int G, size_t smem, bool iow) {
     switch (S) {
-        case 0: return sys_occupancy_long_s0(trace, pad, G, smem);
-        case 1: return sys_occupancy_long_s1(trace, pad, G, smem);
-        case 2: return sys_occupancy_long_s2(trace, pad, G, smem);
-        case 3: return sys_occupancy_long_s3(trace, pad, G, smem);
-        default: return sys_occupancy_long_s4(trace, pad, G, smem);
+        case 0: return sys_occupancy_long_s0(trace, pad, G, smem, iow);
+        case 1: return sys_occupancy_long_s1(trace, pad, G, smem, iow);
+        case 2: return sys_occupancy_long_s2(trace, pad, G, smem, iow);
+        case 3: return sys_occupancy_long_s3(trace, pad, G, smem, iow);
+        default: return sys_occupancy_long_s4(trace, pad, G, smem, iow);
     }
 }
 

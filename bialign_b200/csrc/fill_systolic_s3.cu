@@ -7,7 +7,7 @@ cudaError_t launch_fill_systolic_s3(const SysArgs& A, int grid, int G, size_t sm
 cudaError_t launch_fill_systolic_long_s3(const SysArgs& A, int grid, int G, size_t smem, bool trace, bool pad, cudaStream_t st) {
     return sys::launch_long_s<3>(A, grid, G, smem, trace, pad, st);
 }
-int sys_occupancy_long_s3(bool trace, bool pad, int G, size_t smem) { return sys::occ_long_s<3>(trace, pad, G, smem); }
+int sys_occupancy_long_s3(bool trace, bool pad, int G, size_t smem, bool iow) { return sys::occ_long_s<3>(trace, pad, G, smem, iow); }
 int sys_occupancy_s3(bool trace, bool pad, bool bneg, int G, size_t smem) { return sys::occ_s<3>(trace, pad, bneg, G, smem); }
 size_t sys_smem_bytes_s3(bool pad, int G, int nsym, int bpad, bool p16) {
     return pad ? sys::smem_bytes_t<3, true>(G, nsym, bpad, p16) : sys::smem_bytes_t<3, false>(G, nsym, bpad, p16);

@@ -47,6 +47,8 @@ struct SysArgs {
     int bnd_iters;
     int lq_iters;             // LONG flavour: iterations between progress-flag exchanges (a multiple of the ring period; 0 = default)
     int cpp;                  // LONG flavour: CTAs per pair (gang size); pair p is run by CTAs [p * cpp, (p + 1) * cpp)
+    int gwarps;               // LONG flavour: compute warps per CTA (the launch has gwarps + io_warp warps)
+    int io_warp;              // LONG flavour: 1 = the CTA has one warp more than its G compute warps, which owns the boundary I/O
     uint64_t* codes;          // code arena; the systolic kernel uses it as a plane of 32-bit words ...
     uint16_t* codes_hi;       // ... plus this plane of 16-bit halves, same slot index (PairDesc::code_off counts slots)
     long long* scores;
@@ -121,7 +123,7 @@ __host__ __device__ __forceinline__ long long na_code_index(int S, int G, int ni
     const int qq = j * P + (b + S) + rr + P + 1 /* PRE */;
     return (((long long)pass * G + g) * nit_all + qq) * 32 + lane;
 }
-int sys_occupancy_long(int S, bool trace, bool pad, int G, size_t smem);
+int sys_occupancy_long(int S, bool trace, bool pad, int G, size_t smem, bool iow = false);  // G: compute warps
 // chained short pairs (pad-free affine flavour); bpad_total = bytes of one staged-B array incl. all slack
 constexpr int BA_KCHAIN = 16;
 int sys_occupancy_chain(int S, bool trace, int G, size_t smem);
