@@ -908,7 +908,7 @@ int ba_run(ba_engine* e, int want_trace) {
             // (measured on the 928 x 933 pair, fill time: 1 period 2.65 ms, 2: 2.42, 3: 2.30, 6: 2.48).
             const SysGeo geo = sys_geo(s, plan.pad);
             const char* ov = getenv("BA_LONG_LQ");
-            SA.lq_iters = ov ? std::max(1, atoi(ov)) * geo.RING : (long_mode && npass_max <= e->sm_count ? 3 * geo.RING : 0);
+            SA.lq_iters = ov ? std::max(1, atoi(ov)) * geo.RING : (long_mode && !io_warp && npass_max <= e->sm_count ? 3 * geo.RING : 0);
         }
         SA.bnd = e->d_bnd.p; SA.bnd_iters = biters + 8;  // matches sys_boundary_ints: slack records in front
         SA.codes = want_trace ? e->d_codes.p : nullptr;
