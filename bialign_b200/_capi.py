@@ -16,7 +16,7 @@ SYMBOLS = ["ba_engine_create", "ba_engine_destroy", "ba_last_error", "ba_set_sco
            "ba_version", "ba_engine_create_multi", "ba_engine_device_count", "ba_set_pair_mu2"]
 
 
-ENGINE_OPTIONS = {"kernel": -1, "pad": -1, "long": -1, "io_warp": -1, "p16": -1, "na_kernel": -1, "chain": -1, "rebase": -1, "rebase_window": 0, "warps_per_cta": 0, "code_arena_bytes": 0}
+ENGINE_OPTIONS = {"kernel": -1, "pad": -1, "long": -1, "io_warp": -1, "col_chunks": 0, "p16": -1, "na_kernel": -1, "chain": -1, "rebase": -1, "rebase_window": 0, "warps_per_cta": 0, "code_arena_bytes": 0}
 
 
 class BaStats(ctypes.Structure):

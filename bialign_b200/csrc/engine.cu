@@ -106,6 +106,9 @@ struct ba_engine {
     DevBuf<unsigned long long> d_progress;
     int opt_long = -1;                 // multi-CTA long-pair mode: -1 auto, 0 off, 1 force
     int opt_io_warp = -1;              // long-pair mode: a dedicated I/O warp per CTA: -1 auto, 0 off, 1 on
+    int opt_col_chunks = 0;            // long-pair mode with the I/O warp: column chunks per row block: 0 auto, 1 none, 2..64 forced
+    DevBuf<int> d_tile_order, d_colbuf;
+    DevBuf<unsigned long long> d_dbg_ts;  // BA_DEBUG_TS=<file>: row-block timeline of a single-pair long-mode run
     int opt_p16 = -1;                  // 16-bit pair mode for score-only batches: -1 auto, 0 off, 1 force
     int opt_na = -1;                   // non-affine model: -1 / 1 dedicated kernel when applicable, 0 systolic NA flavour
     int opt_chain = -1;                // short pairs chained along j: -1 auto, 0 off, 1 force
@@ -346,7 +349,7 @@ void ba_engine_destroy(ba_engine* e) {
     e->d_scratch.release(); e->d_counter.release(); e->d_scores.release(); e->d_start.release();
     e->d_complete.release(); e->d_trace.release(); e->d_endv.release(); e->d_tlen.release(); e->h_stage.release();
     e->d_simp.release(); e->d_tbtab.release(); e->d_bnd.release(); e->d_progress.release();
-    e->d_mu2.release(); e->d_mu2_off.release(); e->d_chains.release();
+    e->d_mu2.release(); e->d_mu2_off.release(); e->d_chains.release(); e->d_tile_order.release(); e->d_colbuf.release();
     e->d_rowmax.release(); e->d_simp1.release(); e->d_row_off.release(); e->d_suspect.release(); e->d_desc2.release();
     cudaStreamDestroy(e->stream);
     delete e;
@@ -370,6 +373,10 @@ int ba_set_option(ba_engine* e, const char* key, int64_t value) {
     else if (!strcmp(key, "pad")) return tri(&e->opt_pad);
     else if (!strcmp(key, "long")) return tri(&e->opt_long);
     else if (!strcmp(key, "io_warp")) return tri(&e->opt_io_warp);
+    else if (!strcmp(key, "col_chunks")) {
+        if (value < 0 || value > 64) return fail(e, BA_ERR_INVALID_ARG, "col_chunks must be in 0..64 (0 = auto, 1 = none)");
+        e->opt_col_chunks = (int)value;
+    }
     else if (!strcmp(key, "p16")) return tri(&e->opt_p16);
     else if (!strcmp(key, "na_kernel")) return tri(&e->opt_na);
     else if (!strcmp(key, "chain")) return tri(&e->opt_chain);
@@ -609,6 +616,8 @@ int ba_run(ba_engine* e, int want_trace) {
     int64_t hi_plane_off = 0;  // systolic code arena: slot index at which the 16-bit plane starts (in 32-bit words of the arena)
     bool long_mode = false;
     int io_warp = 0;
+    size_t dbg_nts = 0;
+    int ntc = 1, chunk_cols = 0, tile_iters = 0;  // column-chunked tiles (long-pair mode with the I/O warp, one pair per launch)
     int long_grid_max = 0, sys_occ = 0;
     if (na_ded) {
         // CTA width: a row block is 32 rows per warp and lags 32 iterations per warp; estimate warp-iterations per pair
@@ -878,7 +887,34 @@ int ba_run(ba_engine* e, int want_trace) {
                 return fail(e, BA_ERR_CUDA, "long-pair mode requested but cooperative launch is unavailable");
             }
         }
-        if (long_mode) {
+        // Column chunks: when one pair has more row blocks than the GPU holds CTAs, a second (partly empty) round of row blocks
+        // would cost a whole pass; instead the row blocks are cut into column chunks and the tiles are dealt in start order.
+        // Runs of a single pair only.
+        if (long_mode && io_warp && !plan.pad && !rebase && N == 1 && e->opt_col_chunks != 1) {
+            const SysGeo geo = sys_geo(s, false);
+            const int64_t its = (int64_t)(mmax + 1) * geo.P;
+            int want = e->opt_col_chunks >= 2 ? e->opt_col_chunks : (npass_max > long_grid_max ? (int)std::min<int64_t>(32, std::max<int64_t>(2, its / 4096)) : 1);
+            const char* ov = getenv("BA_COL_CHUNKS");
+            if (ov) want = std::max(1, atoi(ov));
+            want = (int)std::min<int64_t>(want, (mmax + 1) / 64);  // at least 64 columns per chunk
+            if (want >= 2) {
+                chunk_cols = (mmax + 1 + want - 1) / want;
+                ntc = (mmax + 1 + chunk_cols - 1) / chunk_cols;
+                tile_iters = chunk_cols * geo.P + 2 * (rows_pass - 1) + geo.LPR + geo.RING;
+            }
+        }
+        if (long_mode && ntc > 1) {
+            const SysGeo geo = sys_geo(s, false);
+            const size_t ntiles = (size_t)npass_max * ntc;
+            cudaError_t ce = e->d_bnd.ensure(ntiles * (size_t)(tile_iters + 8) * geo.REC);
+            if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "boundary streams (tiles): " + std::string(cudaGetErrorString(ce)));
+            CU(e->d_progress.ensure(std::max<size_t>(ntiles, (size_t)long_grid_max * 2)));
+            const size_t rowsz = (((size_t)npass_max * rows_pass + 2) * geo.LPR + 31) & ~(size_t)31;
+            ce = e->d_colbuf.ensure((size_t)(ntc - 1) * geo.P * 12 * rowsz);
+            if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "column buffer: " + std::string(cudaGetErrorString(ce)));
+            CU(e->d_tile_order.ensure((size_t)ntc));
+            SA.ntc = ntc; SA.chunk_cols = chunk_cols; SA.tile_next = e->d_tile_order.p; SA.colbuf = e->d_colbuf.p; SA.col_rowsz = (int)rowsz;
+        } else if (long_mode) {
             const int lg = (int)std::min<int64_t>(long_grid_max, (int64_t)npass_max * biggest_wave);
             cudaError_t ce = e->d_bnd.ensure((size_t)lg * 2 * sys_boundary_ints(s, plan.pad, sysG, mmax));
             if (ce != cudaSuccess) return fail(e, BA_ERR_OOM, "boundary streams: " + std::string(cudaGetErrorString(ce)));
@@ -901,6 +937,13 @@ int ba_run(ba_engine* e, int want_trace) {
         }
         SA.progress = e->d_progress.p;
         SA.io_warp = long_mode ? io_warp : 0;
+        if (long_mode && N == 1 && getenv("BA_DEBUG_TS")) {
+            const size_t nts = (size_t)npass_max * std::max(ntc, 1) * 2;
+            CU(e->d_dbg_ts.ensure(nts));
+            CU(cudaMemsetAsync(e->d_dbg_ts.p, 0, nts * 8, e->stream));
+            SA.dbg_ts = e->d_dbg_ts.p;
+            dbg_nts = nts;
+        }
         SA.gwarps = sysG;
         {   // Flag period of the long-pair pipeline.  Many row blocks (a CTA per block, several per SM): a flag exchange costs an
             // extra barrier and a spinning thread, so it is rare (default, ~32 iterations).  Few row blocks (one CTA per SM, the pair is
@@ -910,7 +953,7 @@ int ba_run(ba_engine* e, int want_trace) {
             const char* ov = getenv("BA_LONG_LQ");
             SA.lq_iters = ov ? std::max(1, atoi(ov)) * geo.RING : (long_mode && !io_warp && npass_max <= e->sm_count ? 3 * geo.RING : 0);
         }
-        SA.bnd = e->d_bnd.p; SA.bnd_iters = biters + 8;  // matches sys_boundary_ints: slack records in front
+        SA.bnd = e->d_bnd.p; SA.bnd_iters = (ntc > 1 ? tile_iters : biters) + 8;  // matches sys_boundary_ints: slack records in front
         SA.codes = want_trace ? e->d_codes.p : nullptr;
         hi_plane_off = ((int64_t)arena_words + 63) & ~(int64_t)63;  // the 16-bit plane starts behind the 32-bit one (128-byte aligned)
         SA.codes_hi = want_trace ? reinterpret_cast<uint16_t*>(reinterpret_cast<uint32_t*>(e->d_codes.p) + hi_plane_off) : nullptr;
@@ -979,10 +1022,13 @@ int ba_run(ba_engine* e, int want_trace) {
             int64_t q = 0;
             while (q < cnt) {
                 const int np0 = (e->h_desc[b + q].n + rows_pass) / rows_pass;  // row blocks of the longest pair of this launch
-                const int cpp = (int)std::max<int64_t>(1, std::min<int64_t>(np0, long_grid_max / std::min<int64_t>(cnt - q, long_grid_max)));
+                // (tiles: cnt == 1; the gang is as large as the GPU holds, every tile has a flag of its own)
+                const int64_t units = ntc > 1 ? (int64_t)np0 * ntc : np0;
+                const int cpp = (int)std::max<int64_t>(1, std::min<int64_t>(units, long_grid_max / std::min<int64_t>(cnt - q, long_grid_max)));
                 const int np = (int)std::min<int64_t>(cnt - q, long_grid_max / cpp);
                 const int lg = np * cpp;
-                CU(cudaMemsetAsync(e->d_progress.p, 0, sizeof(unsigned long long) * 2 * lg, e->stream));
+                CU(cudaMemsetAsync(e->d_progress.p, 0, sizeof(unsigned long long) * (ntc > 1 ? (size_t)units : (size_t)2 * lg), e->stream));
+                if (ntc > 1) CU(cudaMemsetAsync(e->d_tile_order.p, 0, sizeof(int) * ntc, e->stream));
                 SA.pairs = e->d_desc.p + b + q; SA.npairs = np; SA.cpp = cpp; SA.counter = e->d_counter.p + w;
                 if (rebase) {
                     SA1.pairs = SA.pairs; SA1.npairs = np; SA1.cpp = cpp; SA1.counter = SA.counter;
@@ -1046,6 +1092,16 @@ int ba_run(ba_engine* e, int want_trace) {
     lap("launches");
     CU(cudaStreamSynchronize(e->stream));
     lap("device");
+    if (dbg_nts) {  // debug hook: "<tile> <start ns> <end ns>" per line, relative to the earliest start
+        std::vector<unsigned long long> ts(dbg_nts);
+        CU(cudaMemcpy(ts.data(), e->d_dbg_ts.p, dbg_nts * 8, cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull;
+        for (size_t q = 0; q < dbg_nts; q += 2) if (ts[q]) t0 = std::min(t0, ts[q]);
+        if (FILE* f = fopen(getenv("BA_DEBUG_TS"), "w")) {
+            for (size_t q = 0; q < dbg_nts; q += 2) fprintf(f, "%zu %llu %llu\n", q / 2, ts[q] - t0, ts[q + 1] - t0);
+            fclose(f);
+        }
+    }
     {
         float ms = 0;
         for (int w = 0; w < n_waves; ++w) {

@@ -290,6 +290,19 @@ struct Geo {
 // there with complete = 0.  A walk that reaches the origin therefore saw exact values only, and (all values being >= the
 // true ones) won its ties against a superset of its true competitors: it is the reference's trace.  Pairs whose walk fails,
 // whose values rise above 0 or whose final score differs from the first launch's are recomputed by the level kernel (engine.cu).
+//
+// TILES (I/O-warp flavour of the long-pair mode, one pair per launch, A.ntc > 1): the row blocks are cut into column chunks and
+// a free CTA claims the first READY (row block, chunk) tile, lowest chunk first (A.tile_next[c] = next row block of chunk c;
+// new row blocks start as early as they can, every other CTA works further to the right), so that a pair with more row
+// blocks than the GPU holds CTAs keeps every CTA busy instead of running a second, partly empty round.  A tile is ready when
+// the tile to its left is complete and the one above has produced its first records: a claimed tile never waits for an
+// unclaimed one, so the scheme cannot deadlock whatever the timing.  Tile (p, c) streams its top boundary
+// from tile (p-1, c) exactly like a row block streams from the one above, and starts when tile (p, c-1) is complete.  The
+// only state that crosses a chunk boundary are the twelve x1 = 1 values (the ring values) of the chunk's last column: they
+// go through a global column buffer indexed by (b, value, row, band offset), written by the cells of column j1-1 and read
+// by the cells of column j1 in place of their ring inputs; every other source of a cell lies in its own column (and, where
+// it would lie in the previous cell of that column below b = -S, is poisoned anyway).  Every tile has its own boundary
+// stream and its own progress flag (zeroed per launch), so nothing is reused and nothing can be overwritten early.
 constexpr int KCHAIN = BA_KCHAIN;
 template <int S, bool TRACE, bool PAD, bool BNEG, bool LONG, bool P16 = false, bool NA = false, bool CHAIN = false, bool REBASE = false, bool IOW = false>
 __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNREG_NARROW : BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
@@ -298,6 +311,7 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
     static_assert(!CHAIN || (!PAD && BNEG && !LONG && !P16 && !NA), "chained short pairs: plain pad-free affine flavour");
     static_assert(!REBASE || (!PAD && BNEG && !P16 && !NA && !CHAIN), "rebased wide-range flavour: plain pad-free affine flavour");
     static_assert(!IOW || LONG, "the I/O warp exists in the long-pair flavour only");
+    constexpr bool TILES = IOW && !PAD && !REBASE;    // column-chunked tiles are possible (enabled per launch by A.ntc > 1)
     constexpr bool REB = REBASE && TRACE;             // values are relative to the row maxima of the score-only launch
     constexpr bool TBPACK = BA_TB_PACKED && TRACE && !NA && S <= 3;  // tie-break table packed three entries per word (3 TB <= 32 bits)
     using G_ = Geo<S, PAD>;
@@ -454,18 +468,59 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
         __syncthreads();
 
         const int npass = CHAIN ? 1 : (n + RT) / RT;  // ceil((n+1)/RT)
-        int nit = (m + 1) * P + 2 * (RT - 1) + LPR + RING;
+        int nit_full = (m + 1) * P + 2 * (RT - 1) + LPR + RING;
         if (CHAIN) {  // all pairs of the chain back to back, one dead column after each
-            nit = 2 * (RT - 1) + LPR + RING;
-            for (int kk = 0; kk < K; ++kk) nit += (s_cd[kk].m + 2) * P;
+            nit_full = 2 * (RT - 1) + LPR + RING;
+            for (int kk = 0; kk < K; ++kk) nit_full += (s_cd[kk].m + 2) * P;
         }
+        const bool tiles = TILES && A.ntc > 1;
+        const int ntc = tiles ? A.ntc : 1;            // column chunks per row block
+        const int rowsz = tiles ? A.col_rowsz : 0;    // column buffer: ints per (b, value) plane
         const size_t bstride = (size_t)A.bnd_iters * REC;  // ints per boundary buffer
         const int NC = LONG ? A.cpp : (int)gridDim.x;  // LONG: CTAs that share this pair's row blocks
         const int lb = LONG ? (int)blockIdx.x - pi * NC : 0;
-        int* bnd_base = A.bnd + (LONG ? (size_t)pi * 2 * NC * bstride : (size_t)blockIdx.x * 2 * bstride);
-        unsigned long long* prog_base = LONG ? A.progress + (size_t)pi * 2 * NC : nullptr;
+        int* bnd_base = A.bnd + (LONG ? (tiles ? (size_t)0 : (size_t)pi * 2 * NC * bstride) : (size_t)blockIdx.x * 2 * bstride);
+        unsigned long long* prog_base = LONG ? A.progress + (tiles ? (size_t)0 : (size_t)pi * 2 * NC) : nullptr;
 
-        for (int pass = lb; pass < npass; pass += LONG ? NC : 1) {
+        for (int tix = lb;; tix += LONG ? NC : 1) {
+            int tile = tix;
+            if constexpr (TILES) {
+                if (tiles) {
+                    if (tid == ftid) {  // claim the first ready tile, lowest chunk first; -1: every tile has been claimed
+                        int got = -2;
+                        while (got == -2) {
+                            bool any = false;
+                            for (int c = 0; c < ntc && got == -2; ++c) {
+                                const int p = *reinterpret_cast<volatile int*>(A.tile_next + c);
+                                if (p >= npass) continue;
+                                any = true;
+                                const int cw_ = min(A.chunk_cols, m + 1 - c * A.chunk_cols);
+                                const int nit_c = cw_ * P + 2 * (RT - 1) + LPR + RING;
+                                if (c > 0 && ld_acquire_u64(prog_base + p * ntc + c - 1) <
+                                                 (((unsigned long long)(p + 1) << 32) | (unsigned long long)(A.chunk_cols * P + 2 * (RT - 1) + LPR + RING)))
+                                    continue;
+                                if (p > 0 && ld_acquire_u64(prog_base + (p - 1) * ntc + c) < (((unsigned long long)p << 32) | (unsigned long long)min(LA + 2 * RT, nit_c)))
+                                    continue;
+                                if (atomicCAS(A.tile_next + c, p, p + 1) == p) got = p * ntc + c;
+                            }
+                            if (got == -2) {
+                                if (!any) got = -1;
+                                else __nanosleep(200);
+                            }
+                        }
+                        s_pair = got;
+                    }
+                    __syncthreads();
+                    tile = s_pair;
+                    __syncthreads();
+                    if (tile < 0) break;
+                } else if (tix >= npass) break;
+            } else if (tix >= npass) break;
+            const int pass = tiles ? tile / ntc : tile, tc = tiles ? tile - pass * ntc : 0;
+            // columns [j0, j1) of this tile (everything without tiles), and its iterations
+            const int j0 = tiles ? tc * A.chunk_cols : 0, j1 = tiles ? min(j0 + A.chunk_cols, m + 1) : m + 1;
+            const int nit = tiles ? (j1 - j0) * P + 2 * (RT - 1) + LPR + RING : nit_full;
+            const bool col_in = tiles && tc > 0, col_out = tiles && tc + 1 < ntc;
             const int i = pass * RT + g * R + r;
             const int k = i + a;
             // per-pair lane state (constant over a pass, except in CHAIN mode where a lane moves from pair to pair)
@@ -479,8 +534,9 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
             const int* simrow_hi = ssim + ((lane_ok_hi && i >= 1) ? ra_hi[i - 1] : nsym) * nsym;
             const int wlo = A.w_p & 0xffff, whi = A.w_p << 16;
             const bool has_in = pass > 0, has_out = pass + 1 < npass;
-            const int buf_in = LONG ? ((pass - 1 + 2 * NC) % NC) + NC * ((((pass - 1 + 2 * NC) / NC) & 1)) : ((pass + 1) & 1);
-            const int buf_out = LONG ? (pass % NC) + NC * (((pass + 2 * NC) / NC) & 1) : (pass & 1);
+            // (tiles: one stream and one flag per tile; the producer of tile (p, c) is tile (p-1, c))
+            const int buf_in = tiles ? tile - ntc : LONG ? ((pass - 1 + 2 * NC) % NC) + NC * ((((pass - 1 + 2 * NC) / NC) & 1)) : ((pass + 1) & 1);
+            const int buf_out = tiles ? tile : LONG ? (pass % NC) + NC * (((pass + 2 * NC) / NC) & 1) : (pass & 1);
             const int* bnd_in = bnd_base + (size_t)buf_in * bstride;
             int* bnd_out = bnd_base + (size_t)buf_out * bstride;
             const unsigned long long* prog_in = LONG ? prog_base + buf_in : nullptr;
@@ -535,8 +591,8 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
             const int io_stride_b = io_stride * 4;
             const int q_rec_lim = nit - 2 * RT;                                          // records beyond are "minus infinity"
             // iteration at which this lane sits on the origin / on the end cell (INT_MIN: never)
-            const int q_origin = (i == 0 && a == 0) ? S + sigma : (int)0x80000000;
-            const int q_end = (lane_ok && i == d.n && a == 0) ? d.m * P + S + sigma : (int)0x80000000;
+            const int q_origin = (i == 0 && a == 0 && j0 == 0) ? S + sigma : (int)0x80000000;
+            const int q_end = (lane_ok && i == d.n && a == 0 && j1 == d.m + 1) ? (d.m - j0) * P + S + sigma : (int)0x80000000;
             const int q_end_hi = (lane_ok_hi && i == dh.n && a == 0 && dh.orig >= 0) ? dh.m * P + S + sigma : (int)0x80000000;
             // P16 lane constants: additive constants with the lane's band-edge poisons folded in (SIMD adds)
             const int c16_a1 = P16 ? vadd2(k2G2D, pW) : 0, c16_a3 = P16 ? vadd2(k2G2D, pU1) : 0;
@@ -550,7 +606,7 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
             uint32_t* const codes_lo = reinterpret_cast<uint32_t*>(A.codes);
             uint32_t* cw = nullptr;  // this lane's slot of the current iteration (low plane)
             uint16_t* ch = nullptr;  // steady blocks: the same slot in the high plane
-            if (TRACE) cw = codes_lo + d.code_off + ((long long)pass * G + g) * (long long)((m + 1) * P + 2 * (RT - 1) + LPR + RING + PRE) * 32 + lane;
+            if (TRACE) cw = codes_lo + d.code_off + (((long long)pass * G + g) * (long long)((m + 1) * P + 2 * (RT - 1) + LPR + RING + PRE) + (long long)j0 * P) * 32 + lane;
 
             // plain affine flavour: a lane at k = 0 poisons its x2 = 1 cases itself (their sources sit at k = -1, lanes that
             // are outside the pair and, in steady blocks, not masked), so the first rows of a pair can run steady blocks too
@@ -578,6 +634,9 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                 const int m_eff = P16 ? min(d.m, dh.m) : d.m;
                 st_lo = (S + 1) * P + sig_hi;
                 st_hi = (m_eff - (S > 0 ? S : 1) + 1) * P + sig_lo;
+                // (tiles: iterations count from the tile's first column; the last column of a chunk that hands its state on runs
+                // the generic form, and so does, as everywhere, the first S + 1)
+                if (tiles) st_hi = (min(m_eff - (S > 0 ? S : 1), col_out ? j1 - 2 : j1 - 1) - j0 + 1) * P + sig_lo;
                 if (has_in) st_hi = min(st_hi, q_rec_lim - LA);
                 // (REBASE keeps those lanes masked as well: unmasked they would grow without their row's potential)
                 if ((!K0FIX || REBASE) && pass == 0 && g * R < S) st_hi = st_lo;
@@ -588,8 +647,8 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
             }
 
             // position of this lane one iteration before the first one (q = -PRE)
-            int pos = -PRE - 1 - sigma;
-            int j = -((-pos + P - 1) / P);
+            int pos = j0 * P - PRE - 1 - sigma;
+            int j = pos >= 0 ? pos / P : -((-pos + P - 1) / P);
             int bb = pos - j * P;
             int wslot = (((-PRE - 1) % RING) + RING) % RING;  // slot of the previous iteration: q mod RING
             int pslot = (((-PRE - 1) % PB) + PB) % PB;        // prefetch-buffer slot of the previous iteration: q mod PB
@@ -616,6 +675,19 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
 #pragma unroll
                 for (int k = 0; k < P - 1; ++k) dL[y][k] = NEGP;
 
+            if constexpr (TILES) {
+                if (tiles) {
+                    // the staged row above, its exchange block and the landing zone start from "minus infinity" in every tile
+                    for (int qq = tid; qq < RING * RSLOT; qq += blockDim.x) ring[qq] = NEGP;
+                    for (int qq = tid; qq < RING * XSLOT; qq += blockDim.x) xs[qq] = NEGP;
+                    for (int qq = tid; qq < PB * REC; qq += blockDim.x) pb[qq] = NEGP;
+                    if (col_in && tid == ftid) {  // the chunk to the left of this one (same row block) must be complete
+                        const unsigned long long want = tag_out | (unsigned long long)(A.chunk_cols * P + 2 * (RT - 1) + LPR + RING);
+                        while (ld_acquire_u64(prog_base + tile - 1) < want) __nanosleep(100);
+                    }
+                    __syncthreads();
+                }
+            }
             if (LONG && has_in) {  // wait for the first records of the producer pass, then prime with 16-byte copies
                 if (tid == ftid) {
                     const unsigned long long want = tag_in | (unsigned long long)min(LA + 2 * RT, nit);
@@ -639,6 +711,11 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
             }
             __syncthreads();
 
+            if (LONG && A.dbg_ts && tid == ftid) {  // debug hook (BA_DEBUG_TS): when a row block (tile) got going and when it ended
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+                A.dbg_ts[2 * (size_t)tile] = t;
+            }
             unsigned pb_cur = 0, pb_oth = 0;  // steady blocks: the two halves of the prefetch buffer (this thread's element)
             // ---- long-pair flavour: stage the incoming boundary (virtual row above warp 0) for iteration q and fetch the record of
             // iteration q + LA; run by the staging threads of warp 0, or of the I/O warp (IOW)
@@ -715,7 +792,9 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                     }
                 }
                 const int l = j + bb - S;
-                const bool valid = ST || (lane_ok && (bb < W) && ((unsigned)j <= (unsigned)cur_m) && ((unsigned)l <= (unsigned)cur_m));
+                // (tiles: the columns of this tile only; j1 - 1 = m without tiles)
+                const bool jin = TILES ? ((unsigned)(j - j0) < (unsigned)(j1 - j0)) : ((unsigned)j <= (unsigned)cur_m);
+                const bool valid = ST || (lane_ok && (bb < W) && jin && ((unsigned)l <= (unsigned)cur_m));
                 int vmask = 0, nmask = 0;  // P16: per-half validity
                 if (P16 && !ST) {
                     const bool valid_hi = lane_ok_hi && (bb < W) && ((unsigned)j <= (unsigned)dh.m) && ((unsigned)l <= (unsigned)dh.m);
@@ -794,6 +873,29 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                     rv[8] = dQ[0];
 #pragma unroll
                     for (int y = 0; y < 3; ++y) rv[9 + y] = dL[y][0];
+                }
+                if constexpr (TILES && !ST) {
+                    if (col_in && j == j0 && lane_real) {
+                        // first column of a chunk: the x1 = 1 sources sit in the last column of the chunk to the left -> column buffer.
+                        // Plane (b, value), element (row + 1) * LPR + column; a source at b + 1 beyond the band is poisoned (any sane
+                        // value will do: b is clamped), likewise the left neighbour of column 0; row -1 does not exist.
+                        const int* cbuf = A.colbuf + (size_t)(tc - 1) * (size_t)(P * 12) * rowsz;
+                        const int b1 = min(bb + 1, P - 1);
+                        const int eS = (i + 1) * LPR + c, eW = (c == 0) ? eS : eS - 1, eU0 = eS - LPR, eU1 = eU0 + 1;
+                        const int* p0 = cbuf + (size_t)(bb * 12) * rowsz;   // same b
+                        const int* p1 = cbuf + (size_t)(b1 * 12) * rowsz;   // b + 1
+                        const bool up = i >= 1;
+                        rv[0] = up ? __ldcg(p0 + 0 * (size_t)rowsz + eU1) : NEGP;
+                        rv[1] = up ? __ldcg(p1 + 1 * (size_t)rowsz + eU0) : NEGP;
+                        rv[2] = up ? __ldcg(p0 + 2 * (size_t)rowsz + eU0) : NEGP;
+#pragma unroll
+                        for (int y = 0; y < 3; ++y) rv[3 + y] = up ? __ldcg(p1 + (3 + y) * (size_t)rowsz + eU1) : NEGP;
+                        rv[6] = __ldcg(p1 + 6 * (size_t)rowsz + eW);
+                        rv[7] = __ldcg(p0 + 7 * (size_t)rowsz + eW);
+                        rv[8] = __ldcg(p0 + 8 * (size_t)rowsz + eS);
+#pragma unroll
+                        for (int y = 0; y < 3; ++y) rv[9 + y] = __ldcg(p1 + (9 + y) * (size_t)rowsz + eS);
+                    }
                 }
                 inF[6] = rv[0]; inF[7] = rv[1]; inF[8] = rv[2];     // x=1101, 1110, 1111   Q[11][*]
                 inF[1] = rv[6]; inF[2] = rv[7]; inF[0] = rv[8];     // x=0110, 0111, 0101   Q[01][*]
@@ -956,7 +1058,8 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                         stg32o<u * 128>(cw, lo);
                         stg16o<u * 64>(ch, hi >> 16);
                     } else {
-                        if (!CHAIN || kidx < K) {
+                        // (tiles: the slot of a lane and iteration belongs to the tile in whose columns the lane is at that time)
+                        if ((!CHAIN || kidx < K) && (!TILES || !tiles || jin)) {
                             stg32o<0>(cw, lo);
                             stg16o<0>(A.codes_hi + (cw - codes_lo), hi >> 16);
                         }
@@ -1052,6 +1155,20 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                     wr[6 * 32] = Qv[0][1];
                     wr[7 * 32] = Qv[0][2];
                     if (!SELFREG) wr[8 * 32] = Qv[0][0];
+                    if constexpr (TILES) {
+                        if (col_out && j == j1 - 1 && lane_real) {  // last column of a chunk: hand the twelve ring values on
+                            int* cb = A.colbuf + (size_t)tc * (size_t)(P * 12) * rowsz + (size_t)(bb * 12) * rowsz + (i + 1) * LPR + c;
+#pragma unroll
+                            for (int y = 0; y < 3; ++y) {
+                                cb[(0 + y) * (size_t)rowsz] = Qv[2][y];
+                                cb[(3 + y) * (size_t)rowsz] = Lv[2][y];
+                                cb[(9 + y) * (size_t)rowsz] = Lv[0][y];
+                            }
+                            cb[6 * (size_t)rowsz] = Qv[0][1];
+                            cb[7 * (size_t)rowsz] = Qv[0][2];
+                            cb[8 * (size_t)rowsz] = Qv[0][0];
+                        }
+                    }
                     sts128o_if<0>(xso_b + wslot * XSLOTB, hQ10[0], Lv[1][0], Lv[1][1], Lv[1][2], lastrow);
                     sts64o_if<XA * 4>(xso_b - 8 * c + wslot * XSLOTB, hQ10[2], Qv[1][1], lastrow);
                 }
@@ -1116,18 +1233,21 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                 const bool aligned = (wslot == RING - 1);  // q is a multiple of RING
                 if constexpr (IOW) {
                     if (IO && aligned && q >= next_flag) {
+                        // at the head of a row block the flags go every ring period: the row block below starts as soon as its
+                        // first records exist (every row block of a pair starts one such lag after the one above)
+                        const int per = (q < 2 * RT + 2 * lqb) ? RING : lqb;
                         __syncwarp();
                         if (lane == 0) {
                             if (has_out && q > 0) {  // records 0..q-2: flushed by this warp in the iterations before this one
                                 st_release_u64(prog_out, tag_out | (unsigned long long)(q - 1));  // (release: ordered after them)
                             }
                             if (has_in) {
-                                const unsigned long long want = tag_in | (unsigned long long)min(q + lqb + LA + 2 * RT, nit);
+                                const unsigned long long want = tag_in | (unsigned long long)min(q + per + LA + 2 * RT, nit);
                                 while (ld_acquire_u64(prog_in) < want) __nanosleep(40);
                             }
                         }
                         __syncwarp();
-                        next_flag = q + lqb;
+                        next_flag = q + per;
                     }
                 } else if (LONG && aligned && q >= next_flag) {
                     if (tid == ftid) {
@@ -1175,6 +1295,11 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
             } else {
                 pass_loop(BC_<false>{});
             }
+            if (LONG && A.dbg_ts && tid == ftid) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+                A.dbg_ts[2 * (size_t)tile + 1] = t;
+            }
             if (REBASE && lane_ok) {
                 if (!TRACE) atomicMax(A.rowmax + A.row_off[d.orig] + i, runmax);       // row maxima for the rebased launch
                 else if (runmax >= (1 << TB)) A.suspect[d.orig] = 1;                   // no true value exceeds its row's maximum
@@ -1193,6 +1318,13 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                         __threadfence();
                         st_release_u64(prog_out, tag_out | (unsigned long long)nit);
                     }
+                }
+            } else if (TILES && tiles) {  // last row block: the chunk to the right still waits for this tile's column state
+                __threadfence();
+                __syncthreads();
+                if (tid == ftid) {
+                    __threadfence();
+                    st_release_u64(prog_out, tag_out | (unsigned long long)nit);
                 }
             }
             if (has_in) cp_async_wait<0>();

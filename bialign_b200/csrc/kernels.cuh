@@ -48,6 +48,11 @@ struct SysArgs {
     int lq_iters;             // LONG flavour: iterations between progress-flag exchanges (a multiple of the ring period; 0 = default)
     int cpp;                  // LONG flavour: CTAs per pair (gang size); pair p is run by CTAs [p * cpp, (p + 1) * cpp)
     int gwarps;               // LONG flavour: compute warps per CTA (the launch has gwarps + io_warp warps)
+    int ntc, chunk_cols;      // I/O-warp flavour, one pair per launch: column chunks per row block (<= 1: none), columns per chunk
+    int* tile_next;           //   [ntc] next unclaimed row block of every chunk (zeroed per launch)
+    int* colbuf;              //   column buffer [chunk boundary][b][12 values][col_rowsz]: element (row + 1) * LPR + column
+    int col_rowsz;
+    unsigned long long* dbg_ts;  // LONG flavour, debug hook: [tile][2] globaltimer at the start / end of every row block (tile), or null
     int io_warp;              // LONG flavour: 1 = the CTA has one warp more than its G compute warps, which owns the boundary I/O
     uint64_t* codes;          // code arena; the systolic kernel uses it as a plane of 32-bit words ...
     uint16_t* codes_hi;       // ... plus this plane of 16-bit halves, same slot index (PairDesc::code_off counts slots)

@@ -135,6 +135,9 @@ BA_API int ba_get_stats(const ba_engine* e, ba_stats* out);
 /* Tuning knobs: "code_arena_bytes" (traceback-code arena, default: 1/2 of free HBM),
  * "kernel" (0 generic, 1 systolic, -1 auto), "pad" (systolic flavour: 0 pad-free, 1 padded, -1 auto),
  * "warps_per_cta" (1..8, 0 = chosen per batch), "long" (multi-CTA long-pair mode: 0 off, 1 force, -1 auto),
+ * "io_warp" (long-pair mode: one more warp per CTA that owns the boundary I/O and the progress flags: 0 off, 1 on,
+ * -1 = for a handful of long pairs), "col_chunks" (a single long pair with the I/O warp: column chunks per row block, tiles dealt
+ * in start order: 0 = automatic (when the pair has more row blocks than the GPU holds CTAs), 1 = none, 2..64 forced),
  * "p16" (16-bit pair mode for score-only batches: 0 off, 1 force, -1 auto),
  * "na_kernel" (non-affine model: 0 = systolic kernel's non-affine flavour, 1 / -1 = dedicated kernel when applicable),
  * "chain" (batches of short pairs run as chains through the systolic array: 0 off, 1 force, -1 auto),

@@ -287,6 +287,42 @@ def test_long_pair_mode_multi_cta(warps, pad):
             _unselect(al)
 
 
+@pytest.mark.parametrize("warps", [2, 4])
+def test_long_pair_io_warp_and_column_chunks(warps):
+    """Long-pair mode with the I/O warp (a warp of its own for boundary streams and flags), alone and with the row blocks cut
+    into column chunks (tiles dealt in start order, column state handed on through the global column buffer): single pairs
+    of several row blocks vs the oracle -- scores, traces, end values and the winning case of every reachable cell-state."""
+    rng = np.random.default_rng(4200 + warps)
+    for s in (0, 1, 2, 3, 4):
+        params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=800, gap_opening_cost=-150,
+                      gap_cost=-50, shift_cost=-150, max_shift=s)
+        for chunks in (1, 2, 3):
+            seqs, structs, pairs = _random_protein_batch(rng, 1, 150, 230)
+            al = _aligner(params)
+            _select(al, 1)
+            al.set_option("warps_per_cta", warps)
+            al.set_option("long", 1)
+            al.set_option("io_warp", 1)
+            al.set_option("col_chunks", chunks)
+            try:
+                assert _check_batch(al, seqs, structs, pairs, params, table_pairs=1) == 3
+            finally:
+                _unselect(al)
+    # a handful of pairs in one launch (gangs) with the I/O warp forced; tie storms through the chunk boundaries
+    params = dict(type="Protein", simmatrix="BLOSUM62", structure_weight=0, gap_opening_cost=-1, gap_cost=0, shift_cost=0, max_shift=2)
+    seqs, structs, pairs = _random_protein_batch(rng, 3, 100, 180)
+    al = _aligner(params)
+    _select(al, 1)
+    al.set_option("long", 1)
+    al.set_option("io_warp", 1)
+    try:
+        _check_batch(al, seqs, structs, pairs, params, table_pairs=3)
+        al.set_option("col_chunks", 2)
+        _check_batch(al, seqs[:2], structs[:2], pairs[:1], params, table_pairs=1)
+    finally:
+        _unselect(al)
+
+
 def test_long_pair_auto_mode_many_passes():
     """One 1500 x 1400 pair, max_shift 1: auto-selected long mode, dozens of passes over dozens of CTAs."""
     rng = np.random.default_rng(1234)
