@@ -106,7 +106,7 @@ struct ba_engine {
     DevBuf<unsigned long long> d_progress;
     int opt_long = -1;                 // multi-CTA long-pair mode: -1 auto, 0 off, 1 force
     int opt_io_warp = -1;              // long-pair mode: a dedicated I/O warp per CTA: -1 auto, 0 off, 1 on
-    int opt_col_chunks = 0;            // long-pair mode with the I/O warp: column chunks per row block: 0 auto, 1 none, 2..64 forced
+    int opt_col_chunks = 0;            // long-pair mode with the I/O warp: column chunks per row block: 0 / 1 none, 2..64 that many
     DevBuf<int> d_tile_order, d_colbuf;
     DevBuf<unsigned long long> d_dbg_ts;  // BA_DEBUG_TS=<file>: row-block timeline of a single-pair long-mode run
     int opt_p16 = -1;                  // 16-bit pair mode for score-only batches: -1 auto, 0 off, 1 force
@@ -893,7 +893,11 @@ int ba_run(ba_engine* e, int want_trace) {
         if (long_mode && io_warp && !plan.pad && !rebase && N == 1 && e->opt_col_chunks != 1) {
             const SysGeo geo = sys_geo(s, false);
             const int64_t its = (int64_t)(mmax + 1) * geo.P;
-            int want = e->opt_col_chunks >= 2 ? e->opt_col_chunks : (npass_max > long_grid_max ? (int)std::min<int64_t>(32, std::max<int64_t>(2, its / 4096)) : 1);
+            // (not automatic: measured on the 8192 x 8192 pair, 14 chunks 57.5 ms against 52 ms without -- every row block of
+            // every chunk starts one pipeline lag (~50 us) after the one above, and with chunks that lag is paid 512 times on
+            // the critical path instead of 216 times)
+            (void)its;
+            int want = e->opt_col_chunks >= 2 ? e->opt_col_chunks : 1;
             const char* ov = getenv("BA_COL_CHUNKS");
             if (ov) want = std::max(1, atoi(ov));
             want = (int)std::min<int64_t>(want, (mmax + 1) / 64);  // at least 64 columns per chunk

@@ -166,9 +166,9 @@ __device__ __forceinline__ void sts128o_if(unsigned addr, int x, int y, int z, i
 template <int V> struct IC { static constexpr int value = V; };
 template <bool V> struct BC_ { static constexpr bool value = V; };
 // one statically unrolled ring period: iteration u uses ring slot u; one CTA barrier per iteration
-template <bool IO, class F, int... U>
+template <bool IO, int MODE, class F, int... U>
 __device__ __forceinline__ void steady_block(F& f, const int q, std::integer_sequence<int, U...>) {
-    ((f(BC_<true>{}, IC<U>{}, q + U, BC_<IO>{}), __syncthreads()), ...);
+    ((f(IC<MODE>{}, IC<U>{}, q + U, BC_<IO>{}), __syncthreads()), ...);
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -327,6 +327,12 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
 #else
     constexpr bool STEADY_OK = !PAD;                // pad cells need the per-cell validity select
 #endif
+#ifndef BA_SYS_GUARD
+#define BA_SYS_GUARD 1
+#endif
+    // the guarded static form (see the iteration lambda); batch flavours only: in the long-pair flavours it bought nothing
+    // (the start-up lag of a row block is not the generic form's cost) and the larger code cost 5-15 %
+    constexpr bool GUARD_OK = BA_SYS_GUARD && STEADY_OK && !P16 && !CHAIN && !LONG;
     extern __shared__ __align__(16) int smem[];
     // IOW (long-pair flavour, launched when A.io_warp is set): one more warp than the G compute warps.  It owns the boundary I/O of the CTA -- the flush
     // of the last row's records, the staging of the incoming stream, the progress flags -- so that no compute warp carries it:
@@ -592,7 +598,7 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
             const int q_rec_lim = nit - 2 * RT;                                          // records beyond are "minus infinity"
             // iteration at which this lane sits on the origin / on the end cell (INT_MIN: never)
             const int q_origin = (i == 0 && a == 0 && j0 == 0) ? S + sigma : (int)0x80000000;
-            const int q_end = (lane_ok && i == d.n && a == 0 && j1 == d.m + 1) ? (d.m - j0) * P + S + sigma : (int)0x80000000;
+            const int q_end = (lane_ok && i == d.n && a == 0 && (!tiles || j1 == d.m + 1)) ? (d.m - j0) * P + S + sigma : (int)0x80000000;
             const int q_end_hi = (lane_ok_hi && i == dh.n && a == 0 && dh.orig >= 0) ? dh.m * P + S + sigma : (int)0x80000000;
             // P16 lane constants: additive constants with the lane's band-edge poisons folded in (SIMD adds)
             const int c16_a1 = P16 ? vadd2(k2G2D, pW) : 0, c16_a3 = P16 ? vadd2(k2G2D, pU1) : 0;
@@ -720,7 +726,7 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
             // ---- long-pair flavour: stage the incoming boundary (virtual row above warp 0) for iteration q and fetch the record of
             // iteration q + LA; run by the staging threads of warp 0, or of the I/O warp (IOW)
             auto stage_long = [&](auto st_, auto u_, const int q) __attribute__((always_inline)) {
-                constexpr bool ST = decltype(st_)::value;
+                constexpr bool ST = decltype(st_)::value != 0;
                 constexpr int u = decltype(u_)::value;
                 const int ws = ST ? u : wslot;
                     cp_async_wait<LA - 1>();
@@ -743,8 +749,13 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
             // ---- one iteration (one band cell per lane).  ST: steady form, u = ring slot (compile time).
             // IO: the instantiation the I/O warp runs (a loop of its own: merging the two roles after every iteration would
             // undo the register renaming of the steady blocks)
+            // Forms (st_): 0 generic; 1 steady (no range tests at all); 2 guarded: the static slots and renamed registers of the
+            // steady form plus the per-cell validity select -- for whole ring periods that are not strictly inside the pair but
+            // hold neither the origin nor the end cell (the head and the tail of every row block: the row block below starts one
+            // such head later than the one above, and in generic form a head costs 2.2 x as much).
             auto iteration = [&](auto st_, auto u_, const int q, auto io_) __attribute__((always_inline)) {
-                constexpr bool ST = decltype(st_)::value;
+                constexpr int MODE = decltype(st_)::value;
+                constexpr bool ST = MODE != 0, GUARD = MODE == 2;
                 constexpr int u = decltype(u_)::value;
                 constexpr bool IO = IOW && decltype(io_)::value;
                 // ---- advance position
@@ -794,7 +805,7 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                 const int l = j + bb - S;
                 // (tiles: the columns of this tile only; j1 - 1 = m without tiles)
                 const bool jin = TILES ? ((unsigned)(j - j0) < (unsigned)(j1 - j0)) : ((unsigned)j <= (unsigned)cur_m);
-                const bool valid = ST || (lane_ok && (bb < W) && jin && ((unsigned)l <= (unsigned)cur_m));
+                const bool valid = (ST && !GUARD) || (lane_ok && (bb < W) && jin && ((unsigned)l <= (unsigned)cur_m));
                 int vmask = 0, nmask = 0;  // P16: per-half validity
                 if (P16 && !ST) {
                     const bool valid_hi = lane_ok_hi && (bb < W) && ((unsigned)j <= (unsigned)dh.m) && ((unsigned)l <= (unsigned)dh.m);
@@ -874,7 +885,7 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
 #pragma unroll
                     for (int y = 0; y < 3; ++y) rv[9 + y] = dL[y][0];
                 }
-                if constexpr (TILES && !ST) {
+                if constexpr (TILES && (!ST || GUARD)) {
                     if (col_in && j == j0 && lane_real) {
                         // first column of a chunk: the x1 = 1 sources sit in the last column of the chunk to the left -> column buffer.
                         // Plane (b, value), element (row + 1) * LPR + column; a source at b + 1 beyond the band is poisoned (any sane
@@ -1001,7 +1012,7 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                     const int v1 = xaddmax<P16>(inH1[t], kh1[t01], NEGF);  // floor: nothing ever drops below "minus infinity"
                     const int v = xaddmax<P16>(inH2[t], kh2[t23], v1);
                     M[t] = xaddmax<P16>(inF[t], kF[t], v);
-                    if (!ST) M[t] = P16 ? ((M[t] & vmask) | nmask) : (valid ? M[t] : NEGF);
+                    if (!ST || GUARD) M[t] = (P16 && !GUARD) ? ((M[t] & vmask) | nmask) : (valid ? M[t] : NEGF);
                 }
                 if (REBASE) runmax = vmax3(vmax3(runmax, M[0], M[1]), vmax3(M[2], M[3], M[4]), vmax3(vmax3(M[5], M[6], M[7]), M[8], runmax));
 
@@ -1055,8 +1066,10 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                     for (int t = 6; t < 9; ++t) hi = __funnelshift_r(hi, (unsigned)M[t], 5);
                     // (the three fields of the high word sit in its upper half: only that half is stored)
                     if constexpr (ST) {
-                        stg32o<u * 128>(cw, lo);
-                        stg16o<u * 64>(ch, hi >> 16);
+                        if (!(GUARD && TILES) || !tiles || jin) {
+                            stg32o<u * 128>(cw, lo);
+                            stg16o<u * 64>(ch, hi >> 16);
+                        }
                     } else {
                         // (tiles: the slot of a lane and iteration belongs to the tile in whose columns the lane is at that time)
                         if ((!CHAIN || kidx < K) && (!TILES || !tiles || jin)) {
@@ -1144,6 +1157,20 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                     }
                     sts128o_if<u * XSLOTB>(xso_b, hQ10[0], Lv[1][0], Lv[1][1], Lv[1][2], lastrow);
                     sts64o_if<u * XSLOTB + XA * 4>(xso_b - 8 * c, hQ10[2], Qv[1][1], lastrow);
+                    if constexpr (TILES && GUARD) {
+                        if (col_out && j == j1 - 1 && lane_real) {  // last column of a chunk: hand the twelve ring values on
+                            int* cb = A.colbuf + (size_t)tc * (size_t)(P * 12) * rowsz + (size_t)(bb * 12) * rowsz + (i + 1) * LPR + c;
+#pragma unroll
+                            for (int y = 0; y < 3; ++y) {
+                                cb[(0 + y) * (size_t)rowsz] = Qv[2][y];
+                                cb[(3 + y) * (size_t)rowsz] = Lv[2][y];
+                                cb[(9 + y) * (size_t)rowsz] = Lv[0][y];
+                            }
+                            cb[6 * (size_t)rowsz] = Qv[0][1];
+                            cb[7 * (size_t)rowsz] = Qv[0][2];
+                            cb[8 * (size_t)rowsz] = Qv[0][0];
+                        }
+                    }
                 } else {
                     int* wr = ring + own_ring + wslot * RSLOT + lane;
 #pragma unroll
@@ -1233,9 +1260,9 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                 const bool aligned = (wslot == RING - 1);  // q is a multiple of RING
                 if constexpr (IOW) {
                     if (IO && aligned && q >= next_flag) {
-                        // at the head of a row block the flags go every ring period: the row block below starts as soon as its
-                        // first records exist (every row block of a pair starts one such lag after the one above)
-                        const int per = (q < 2 * RT + 2 * lqb) ? RING : lqb;
+                        // (flags every ring period at the head of a row block, so that the row block below starts sooner, measured
+                        // slower: 928 x 933 pair 1.83 -> 2.07 ms -- the release / acquire round trips then pace the I/O warp)
+                        const int per = lqb;
                         __syncwarp();
                         if (lane == 0) {
                             if (has_out && q > 0) {  // records 0..q-2: flushed by this warp in the iterations before this one
@@ -1271,19 +1298,27 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                     const bool mine = kidx < K && posn + 1 >= (S + 1) * P && posn + RING <= (cur_m - (S > 0 ? S : 1) + 1) * P - 1;
                     steady = __all_sync(0xffffffffu, mine);
                 }
-                if (steady) {
+                bool guard = false;  // warp-uniform
+                if constexpr (GUARD_OK && !IO) {
+                    if (!steady && aligned && q + RING <= (has_in ? q_rec_lim - LA : nit)) {
+                        const bool hit = (q_origin >= q && q_origin < q + RING) || (q_end >= q && q_end < q + RING);
+                        guard = !__any_sync(0xffffffffu, hit);
+                    }
+                }
+                if (steady || guard) {
                     const int ph = (pslot + 1 == PB) ? 0 : pslot + 1;           // 0 or RING
                     pb_cur = pb_s + ph * RECB;
                     pb_oth = pb_s + (ph ? 0 : LA) * RECB;
                     if (TRACE && !NA) ch = A.codes_hi + (cw - codes_lo);
-                    steady_block<IO>(iteration, q, std::make_integer_sequence<int, RING>{});
+                    if (steady) steady_block<IO, 1>(iteration, q, std::make_integer_sequence<int, RING>{});
+                    else steady_block<IO, GUARD_OK ? 2 : 1>(iteration, q, std::make_integer_sequence<int, RING>{});
                     q += RING;
                     pslot = ph + RING - 1;
                     fl_g += RING * REC;
                     st_g += RING * REC;
                     if (TRACE) cw += RING * 32;
                 } else {
-                    iteration(BC_<false>{}, IC<0>{}, q, io_);
+                    iteration(IC<0>{}, IC<0>{}, q, io_);
                     __syncthreads();
                     ++q;
                 }

@@ -137,7 +137,7 @@ BA_API int ba_get_stats(const ba_engine* e, ba_stats* out);
  * "warps_per_cta" (1..8, 0 = chosen per batch), "long" (multi-CTA long-pair mode: 0 off, 1 force, -1 auto),
  * "io_warp" (long-pair mode: one more warp per CTA that owns the boundary I/O and the progress flags: 0 off, 1 on,
  * -1 = for a handful of long pairs), "col_chunks" (a single long pair with the I/O warp: column chunks per row block, tiles dealt
- * in start order: 0 = automatic (when the pair has more row blocks than the GPU holds CTAs), 1 = none, 2..64 forced),
+ * claimed by readiness: 0 / 1 = none (the default: measured slower than plain row blocks), 2..64 = that many),
  * "p16" (16-bit pair mode for score-only batches: 0 off, 1 force, -1 auto),
  * "na_kernel" (non-affine model: 0 = systolic kernel's non-affine flavour, 1 / -1 = dedicated kernel when applicable),
  * "chain" (batches of short pairs run as chains through the systolic array: 0 off, 1 force, -1 auto),
