@@ -332,6 +332,7 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
 #endif
     // the guarded static form (see the iteration lambda); batch flavours only: in the long-pair flavours it bought nothing
     // (the start-up lag of a row block is not the generic form's cost) and the larger code cost 5-15 %
+    // (16-bit pair mode: its per-half masks make the guarded form cost more than it saves, 1688 -> 1624 GCUPS on config 4)
     constexpr bool GUARD_OK = BA_SYS_GUARD && STEADY_OK && !P16 && !CHAIN && !LONG;
     extern __shared__ __align__(16) int smem[];
     // IOW (long-pair flavour, launched when A.io_warp is set): one more warp than the G compute warps.  It owns the boundary I/O of the CTA -- the flush
@@ -1012,7 +1013,7 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                     const int v1 = xaddmax<P16>(inH1[t], kh1[t01], NEGF);  // floor: nothing ever drops below "minus infinity"
                     const int v = xaddmax<P16>(inH2[t], kh2[t23], v1);
                     M[t] = xaddmax<P16>(inF[t], kF[t], v);
-                    if (!ST || GUARD) M[t] = (P16 && !GUARD) ? ((M[t] & vmask) | nmask) : (valid ? M[t] : NEGF);
+                    if (!ST || GUARD) M[t] = P16 ? ((M[t] & vmask) | nmask) : (valid ? M[t] : NEGF);
                 }
                 if (REBASE) runmax = vmax3(vmax3(runmax, M[0], M[1]), vmax3(M[2], M[3], M[4]), vmax3(vmax3(M[5], M[6], M[7]), M[8], runmax));
 
@@ -1301,7 +1302,8 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                 bool guard = false;  // warp-uniform
                 if constexpr (GUARD_OK && !IO) {
                     if (!steady && aligned && q + RING <= (has_in ? q_rec_lim - LA : nit)) {
-                        const bool hit = (q_origin >= q && q_origin < q + RING) || (q_end >= q && q_end < q + RING);
+                        const bool hit = (q_origin >= q && q_origin < q + RING) || (q_end >= q && q_end < q + RING) ||
+                                         (P16 && q_end_hi >= q && q_end_hi < q + RING);
                         guard = !__any_sync(0xffffffffu, hit);
                     }
                 }
