@@ -900,7 +900,7 @@ int ba_run(ba_engine* e, int want_trace) {
             int want = e->opt_col_chunks >= 2 ? e->opt_col_chunks : 1;
             const char* ov = getenv("BA_COL_CHUNKS");
             if (ov) want = std::max(1, atoi(ov));
-            want = (int)std::min<int64_t>(want, (mmax + 1) / 64);  // at least 64 columns per chunk
+            want = (int)std::min<int64_t>(want, (mmax + 1) / 16);  // at least 16 columns per chunk
             if (want >= 2) {
                 chunk_cols = (mmax + 1 + want - 1) / want;
                 ntc = (mmax + 1 + chunk_cols - 1) / chunk_cols;
@@ -942,7 +942,7 @@ int ba_run(ba_engine* e, int want_trace) {
         SA.progress = e->d_progress.p;
         SA.io_warp = long_mode ? io_warp : 0;
         if (long_mode && N == 1 && getenv("BA_DEBUG_TS")) {
-            const size_t nts = (size_t)npass_max * std::max(ntc, 1) * 2;
+            const size_t nts = (size_t)npass_max * std::max(ntc, 1) * 8;
             CU(e->d_dbg_ts.ensure(nts));
             CU(cudaMemsetAsync(e->d_dbg_ts.p, 0, nts * 8, e->stream));
             SA.dbg_ts = e->d_dbg_ts.p;
@@ -1100,9 +1100,13 @@ int ba_run(ba_engine* e, int want_trace) {
         std::vector<unsigned long long> ts(dbg_nts);
         CU(cudaMemcpy(ts.data(), e->d_dbg_ts.p, dbg_nts * 8, cudaMemcpyDeviceToHost));
         unsigned long long t0 = ~0ull;
-        for (size_t q = 0; q < dbg_nts; q += 2) if (ts[q]) t0 = std::min(t0, ts[q]);
-        if (FILE* f = fopen(getenv("BA_DEBUG_TS"), "w")) {
-            for (size_t q = 0; q < dbg_nts; q += 2) fprintf(f, "%zu %llu %llu\n", q / 2, ts[q] - t0, ts[q + 1] - t0);
+        for (size_t q = 0; q < dbg_nts; q += 8) if (ts[q]) t0 = std::min(t0, ts[q]);
+        if (FILE* f = fopen(getenv("BA_DEBUG_TS"), "w")) {  // tile, start, end, then when iterations 0, 50, 100, 200, 400, 800 were reached
+            for (size_t q = 0; q < dbg_nts; q += 8) {
+                fprintf(f, "%zu", q / 8);
+                for (int k = 0; k < 8; ++k) fprintf(f, " %lld", ts[q + k] ? (long long)(ts[q + k] - t0) : -1ll);
+                fprintf(f, "\n");
+            }
             fclose(f);
         }
     }

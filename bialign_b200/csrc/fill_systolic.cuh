@@ -330,10 +330,16 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
 #ifndef BA_SYS_GUARD
 #define BA_SYS_GUARD 1
 #endif
+// (long-pair flavours: measured with the row-block timeline hook -- the head of a row block gets faster (first 50 iterations of
+// the 928 x 933 pair 31 -> 20 us, start-to-start lag 54 -> 35 us), but a consumer that starts closer to its producer only stalls
+// at its flag points until the old distance is back; fill times unchanged (2.04 / 53.4 ms), column chunks slower: off)
+#ifndef BA_SYS_GUARD_LONG
+#define BA_SYS_GUARD_LONG 0
+#endif
     // the guarded static form (see the iteration lambda); batch flavours only: in the long-pair flavours it bought nothing
     // (the start-up lag of a row block is not the generic form's cost) and the larger code cost 5-15 %
     // (16-bit pair mode: its per-half masks make the guarded form cost more than it saves, 1688 -> 1624 GCUPS on config 4)
-    constexpr bool GUARD_OK = BA_SYS_GUARD && STEADY_OK && !P16 && !CHAIN && !LONG;
+    constexpr bool GUARD_OK = BA_SYS_GUARD && STEADY_OK && !P16 && !CHAIN && (!LONG || BA_SYS_GUARD_LONG);
     extern __shared__ __align__(16) int smem[];
     // IOW (long-pair flavour, launched when A.io_warp is set): one more warp than the G compute warps.  It owns the boundary I/O of the CTA -- the flush
     // of the last row's records, the staging of the incoming stream, the progress flags -- so that no compute warp carries it:
@@ -721,7 +727,7 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
             if (LONG && A.dbg_ts && tid == ftid) {  // debug hook (BA_DEBUG_TS): when a row block (tile) got going and when it ended
                 unsigned long long t;
                 asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
-                A.dbg_ts[2 * (size_t)tile] = t;
+                A.dbg_ts[8 * (size_t)tile] = t;
             }
             unsigned pb_cur = 0, pb_oth = 0;  // steady blocks: the two halves of the prefetch buffer (this thread's element)
             // ---- long-pair flavour: stage the incoming boundary (virtual row above warp 0) for iteration q and fetch the record of
@@ -886,7 +892,7 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
 #pragma unroll
                     for (int y = 0; y < 3; ++y) rv[9 + y] = dL[y][0];
                 }
-                if constexpr (TILES && (!ST || GUARD)) {
+                if constexpr (TILES && !ST) {
                     if (col_in && j == j0 && lane_real) {
                         // first column of a chunk: the x1 = 1 sources sit in the last column of the chunk to the left -> column buffer.
                         // Plane (b, value), element (row + 1) * LPR + column; a source at b + 1 beyond the band is poisoned (any sane
@@ -1067,7 +1073,7 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                     for (int t = 6; t < 9; ++t) hi = __funnelshift_r(hi, (unsigned)M[t], 5);
                     // (the three fields of the high word sit in its upper half: only that half is stored)
                     if constexpr (ST) {
-                        if (!(GUARD && TILES) || !tiles || jin) {
+                        if (!(GUARD && TILES) || !tiles || jin) {  // (tiles: see the generic form)
                             stg32o<u * 128>(cw, lo);
                             stg16o<u * 64>(ch, hi >> 16);
                         }
@@ -1158,20 +1164,6 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                     }
                     sts128o_if<u * XSLOTB>(xso_b, hQ10[0], Lv[1][0], Lv[1][1], Lv[1][2], lastrow);
                     sts64o_if<u * XSLOTB + XA * 4>(xso_b - 8 * c, hQ10[2], Qv[1][1], lastrow);
-                    if constexpr (TILES && GUARD) {
-                        if (col_out && j == j1 - 1 && lane_real) {  // last column of a chunk: hand the twelve ring values on
-                            int* cb = A.colbuf + (size_t)tc * (size_t)(P * 12) * rowsz + (size_t)(bb * 12) * rowsz + (i + 1) * LPR + c;
-#pragma unroll
-                            for (int y = 0; y < 3; ++y) {
-                                cb[(0 + y) * (size_t)rowsz] = Qv[2][y];
-                                cb[(3 + y) * (size_t)rowsz] = Lv[2][y];
-                                cb[(9 + y) * (size_t)rowsz] = Lv[0][y];
-                            }
-                            cb[6 * (size_t)rowsz] = Qv[0][1];
-                            cb[7 * (size_t)rowsz] = Qv[0][2];
-                            cb[8 * (size_t)rowsz] = Qv[0][0];
-                        }
-                    }
                 } else {
                     int* wr = ring + own_ring + wslot * RSLOT + lane;
 #pragma unroll
@@ -1257,7 +1249,14 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
             const int lqb = (LONG && A.lq_iters > 0) ? A.lq_iters : (IOW ? 4 * RING : LQB);
             auto pass_loop = [&](auto io_) __attribute__((always_inline)) {
             constexpr bool IO = decltype(io_)::value;
+            int dbg_k = 0;  // debug hook: compute warp 0 stamps when it reaches iteration 0, 50, 100, 200, 400, 800
             for (int q = -PRE; q < nit;) {
+                if (LONG && !IO && A.dbg_ts && tid == 0 && dbg_k < 6 && q >= (dbg_k == 0 ? 0 : (25 << dbg_k))) {
+                    unsigned long long t;
+                    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+                    A.dbg_ts[8 * (size_t)tile + 2 + dbg_k] = t;
+                    ++dbg_k;
+                }
                 const bool aligned = (wslot == RING - 1);  // q is a multiple of RING
                 if constexpr (IOW) {
                     if (IO && aligned && q >= next_flag) {
@@ -1305,6 +1304,11 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                         const bool hit = (q_origin >= q && q_origin < q + RING) || (q_end >= q && q_end < q + RING) ||
                                          (P16 && q_end_hi >= q && q_end_hi < q + RING);
                         guard = !__any_sync(0xffffffffu, hit);
+                        if constexpr (TILES) {  // the columns that talk to the column buffer run the generic form
+                            const int sg_lo = 2 * (g * R), sg_hi = 2 * (g * R + R - 1) + LPR - 1;
+                            if (col_in && q < sg_hi + P + 1) guard = false;
+                            if (col_out && q + RING > (j1 - 1 - j0) * P + sg_lo) guard = false;
+                        }
                     }
                 }
                 if (steady || guard) {
@@ -1335,7 +1339,7 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
             if (LONG && A.dbg_ts && tid == ftid) {
                 unsigned long long t;
                 asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
-                A.dbg_ts[2 * (size_t)tile + 1] = t;
+                A.dbg_ts[8 * (size_t)tile + 1] = t;
             }
             if (REBASE && lane_ok) {
                 if (!TRACE) atomicMax(A.rowmax + A.row_off[d.orig] + i, runmax);       // row maxima for the rebased launch

@@ -67,6 +67,8 @@ def fuzz(seed=1, rounds=40, verbose=True, max_len=160):
         al.set_option("pad", int(rng.choice([-1, 0, 1])))
         al.set_option("long", int(rng.choice([-1, -1, 1])))
         al.set_option("warps_per_cta", int(rng.choice([0, 0, 2, 4, 6])))
+        al.set_option("io_warp", int(rng.choice([-1, 0, 1])))        # long-pair mode: with / without the I/O warp
+        al.set_option("col_chunks", int(rng.choice([0, 0, 2, 3])))   # ... and (single pairs) column-chunked tiles
         if rng.random() < 0.25:  # rebased trace run (forced), sometimes with a window so small that pairs fall back
             al.set_option("rebase", 1)
             al.set_option("rebase_window", int(rng.choice([0, 0, 30, 300])))

@@ -27,8 +27,12 @@ eng.load_sequences(res, cls, off); eng.load_pairs(pa, pb)
 for _ in range(3):
     eng.run(want_trace=True)
 st = eng.stats()
-t = np.loadtxt(path, dtype=np.int64).reshape(-1, 3)
+t = np.loadtxt(path, dtype=np.int64).reshape(-1, 9)
 start, end = t[:, 1] / 1e3, t[:, 2] / 1e3  # us
+marks = t[:, 3:9] / 1e3 - start[:, None]  # us after the tile's start at which iterations 0, 50, 100, 200, 400, 800 were reached
+with np.printoptions(precision=1, suppress=True):
+    print("  iterations 0 / 50 / 100 / 200 / 400 / 800 reached, us after the start of the row block (median over row blocks 1..):",
+          np.median(marks[1:], axis=0))
 ntc = max(chunks, 1)
 ntiles = len(t)
 print(f"cfg{which} chunks={chunks}: fill {st['fill_ms']:.3f} ms, {ntiles} tiles, span {end.max():.1f} us")
