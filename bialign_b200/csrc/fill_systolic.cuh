@@ -304,14 +304,16 @@ struct Geo {
 // it would lie in the previous cell of that column below b = -S, is poisoned anyway).  Every tile has its own boundary
 // stream and its own progress flag (zeroed per launch), so nothing is reused and nothing can be overwritten early.
 constexpr int KCHAIN = BA_KCHAIN;
-template <int S, bool TRACE, bool PAD, bool BNEG, bool LONG, bool P16 = false, bool NA = false, bool CHAIN = false, bool REBASE = false, bool IOW = false>
+template <int S, bool TRACE, bool PAD, bool BNEG, bool LONG, bool P16 = false, bool NA = false, bool CHAIN = false, bool REBASE = false, bool IOW = false,
+          bool TILED = false>
 __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNREG_NARROW : BA_SYS_MAXNREG) fill_systolic_kernel(SysArgs A) {
     static_assert(!P16 || (!TRACE && !PAD && BNEG && !LONG), "16-bit pair mode: score only, pad-free, beta < 0, batch mode");
     static_assert(!NA || (BNEG && !LONG && !P16), "non-affine flavour: batch mode, 32-bit");
     static_assert(!CHAIN || (!PAD && BNEG && !LONG && !P16 && !NA), "chained short pairs: plain pad-free affine flavour");
     static_assert(!REBASE || (!PAD && BNEG && !P16 && !NA && !CHAIN), "rebased wide-range flavour: plain pad-free affine flavour");
     static_assert(!IOW || LONG, "the I/O warp exists in the long-pair flavour only");
-    constexpr bool TILES = IOW && !PAD && !REBASE;    // column-chunked tiles are possible (enabled per launch by A.ntc > 1)
+    static_assert(!TILED || (IOW && !PAD && !REBASE), "column-chunked tiles: pad-free I/O-warp flavour");
+    constexpr bool TILES = TILED;                     // column-chunked tiles (a flavour of its own: launched when A.ntc > 1)
     constexpr bool REB = REBASE && TRACE;             // values are relative to the row maxima of the score-only launch
     constexpr bool TBPACK = BA_TB_PACKED && TRACE && !NA && S <= 3;  // tie-break table packed three entries per word (3 TB <= 32 bits)
     using G_ = Geo<S, PAD>;
@@ -1501,6 +1503,9 @@ template <int S, bool TRACE, bool PAD>
 cudaError_t launch_long_t(const SysArgs& A, int grid, int G, size_t smem, cudaStream_t st) {
     auto kern = A.io_warp ? fill_systolic_kernel<S, TRACE, PAD, true, true, false, false, false, false, true>
                           : fill_systolic_kernel<S, TRACE, PAD, true, true>;
+    if constexpr (!PAD) {
+        if (A.io_warp && A.ntc > 1) kern = fill_systolic_kernel<S, TRACE, PAD, true, true, false, false, false, false, true, true>;
+    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     SysArgs a = A;
