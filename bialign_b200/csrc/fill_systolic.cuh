@@ -338,6 +338,9 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
 #ifndef BA_SYS_GUARD_LONG
 #define BA_SYS_GUARD_LONG 0
 #endif
+#ifndef BA_LONG_CREDIT
+#define BA_LONG_CREDIT 1
+#endif
     // the guarded static form (see the iteration lambda); batch flavours only: in the long-pair flavours it bought nothing
     // (the start-up lag of a row block is not the generic form's cost) and the larger code cost 5-15 %
     // (16-bit pair mode: its per-half masks make the guarded form cost more than it saves, 1688 -> 1624 GCUPS on config 4)
@@ -1246,11 +1249,13 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
             int next_flag = 0;  // LONG: next iteration (a multiple of RING) at which progress is published / awaited
             // (IOW: the flags belong to the I/O warp alone -- it wrote the records it publishes and it is the only reader of the
             // incoming stream --, so there is no CTA barrier at a flag point: a late I/O warp simply holds the CTA at the iteration
-            // barrier.  Period: four ring periods; measured on the 8192 x 8192 pair, fill time: 1 period 76.4 ms (the release /
-            // acquire round trips then sit on the I/O warp's own critical path), 2: 53.4, 4: 51.7)
-            const int lqb = (LONG && A.lq_iters > 0) ? A.lq_iters : (IOW ? 4 * RING : LQB);
+            // barrier.  Publish period: three ring periods; measured on the 8192 x 8192 pair with the credit-style input side
+            // below, fill time: 1 period 50.8 ms, 2: 49.4, 3: 49.5, 4: 50.3, 6: 50.6 (when the input side still waited for a whole
+            // period of look-ahead at every flag point: 1 period 76.4 ms, 2: 53.4, 4: 51.7))
+            const int lqb = (LONG && A.lq_iters > 0) ? A.lq_iters : (IOW ? 3 * RING : LQB);
             auto pass_loop = [&](auto io_) __attribute__((always_inline)) {
             constexpr bool IO = decltype(io_)::value;
+            int avail = min(LA + 2 * RT, nit);  // IOW: records of the producer known to be complete (the first wait saw these)
             int dbg_k = 0;  // debug hook: compute warp 0 stamps when it reaches iteration 0, 50, 100, 200, 400, 800
             for (int q = -PRE; q < nit;) {
                 if (LONG && !IO && A.dbg_ts && tid == 0 && dbg_k < 6 && q >= (dbg_k == 0 ? 0 : (25 << dbg_k))) {
@@ -1261,6 +1266,31 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                 }
                 const bool aligned = (wslot == RING - 1);  // q is a multiple of RING
                 if constexpr (IOW) {
+#if BA_LONG_CREDIT
+                    // Publish every lqb iterations; on the input side keep the last progress value read and poll only when the
+                    // records this ring period fetches are not covered by it: a consumer that starts right behind its producer
+                    // waits for exactly what it needs instead of for a whole flag period of look-ahead.
+                    if (IO && aligned) {
+                        if (q >= next_flag) {
+                            __syncwarp();
+                            if (lane == 0 && has_out && q > 0)  // records 0..q-2: flushed by this warp in the iterations before this one
+                                st_release_u64(prog_out, tag_out | (unsigned long long)(q - 1));  // (release: ordered after them)
+                            next_flag = q + lqb;
+                        }
+                        if (has_in) {
+                            const int need = min(q + RING + LA + 2 * RT, nit);
+                            if (avail < need) {  // warp-uniform
+                                unsigned long long v = 0;
+                                if (lane == 0) {
+                                    const unsigned long long want = tag_in | (unsigned long long)need;
+                                    while ((v = ld_acquire_u64(prog_in)) < want) __nanosleep(40);
+                                }
+                                v = __shfl_sync(0xffffffffu, v, 0);
+                                avail = (v >> 32) > (tag_in >> 32) ? nit : (int)(unsigned)v;  // a later tag: the producer is done
+                            }
+                        }
+                    }
+#else
                     if (IO && aligned && q >= next_flag) {
                         // (flags every ring period at the head of a row block, so that the row block below starts sooner, measured
                         // slower: 928 x 933 pair 1.83 -> 2.07 ms -- the release / acquire round trips then pace the I/O warp)
@@ -1278,6 +1308,7 @@ __global__ void __maxnreg__((S <= 2 && (!LONG || BA_LONG_NARROW)) ? BA_SYS_MAXNR
                         __syncwarp();
                         next_flag = q + per;
                     }
+#endif
                 } else if (LONG && aligned && q >= next_flag) {
                     if (tid == ftid) {
                         if (has_out && q > 0) {  // records 0..q-2 were stored before the last barrier
