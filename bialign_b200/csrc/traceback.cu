@@ -96,7 +96,10 @@ __device__ __forceinline__ bool walk_step(const TraceArgs& A, const uint64_t* co
 
 // One thread per pair: thousands of independent walks hide the read latency of each.  (A warp per pair whose idle lanes
 // prefetch the diagonal ahead of the walker was measured on the 928 x 933 and 8192 x 8192 pairs: 0.61 vs 0.55 ms and
-// 8.3 vs 7.8 ms -- the path leaves the predicted diagonal too often -- and dropped.)
+// 8.3 vs 7.8 ms -- the path leaves the predicted diagonal too often -- and dropped.  So was a warp per pair whose lanes
+// prefetch, while the walker's read is in flight, EVERY predecessor of the current cell in both planes, each followed by
+// zero to two match columns: 0.84 vs 0.52 ms and 9.3 vs 7.8 ms -- the index arithmetic of the prefetches costs the lone
+// warp more than the hits save.)
 __global__ void __launch_bounds__(128) traceback_kernel(TraceArgs A) {
     const int pi = blockIdx.x * blockDim.x + threadIdx.x;
     if (pi >= A.npairs) return;
