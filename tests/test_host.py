@@ -347,3 +347,15 @@ def test_rna_without_structure_needs_the_rna_module(monkeypatch):
                   max_shift=1, sequence_match_similarity=100, sequence_mismatch_similarity=0)
     with pytest.raises(ImportError):
         ba.BiAligner("GGGAAACCC", "GGAAACC", None, None, **params)
+
+
+def test_every_engine_option_is_documented_and_known_to_the_library():
+    """The Python layer's option table, the header's ba_set_option comment and the library's own key list agree
+    (no compute call: the keys are looked up in the strings of the built library)."""
+    from bialign_b200 import _capi
+
+    header = open(os.path.join(ROOT, "include", "bialign_b200.h")).read()
+    lib = open(os.path.join(ROOT, "bialign_b200", "libbialign_b200.so"), "rb").read()
+    for key in _capi.ENGINE_OPTIONS:
+        assert '"%s"' % key in header, key
+        assert key.encode() + b"\0" in lib, key
