@@ -436,7 +436,7 @@ def main():
                 "traffic": (traffic * my_cs if traffic else None),
                 "hbm": {"achieved": st["code_bytes"] / fill_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": st["code_bytes"] / fill_s / 1e9 / hbm_peak,
-                        "what": "traceback-code stores (8 B per lane and iteration, 256 B per warp) during the fill",
+                        "what": "traceback-code stores (a 6-byte slot per lane and iteration: 128 + 64 contiguous bytes per warp) during the fill",
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}}
     out = {"metric": "batched bialign GCUPS (cell-states/s)", "value": value, "unit": "GCUPS", "n_gpus": n_gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
