@@ -1,9 +1,10 @@
-"""world_size-2 gloo test of the multi-rank host path: LPT sharding + result gather.
+"""world_size-2 and -3 gloo tests of the multi-rank host path: LPT sharding + result gather.
 The per-rank engine call is replaced by the CPU oracle (tests may use it; the product never does)."""
 import os
 import sys
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -47,13 +48,15 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_sharding_and_gather(tmp_path):
-    port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    r0, r1 = np.load(tmp_path / "rank0.npy"), np.load(tmp_path / "rank1.npy")
-    m0, m1 = np.load(tmp_path / "mine0.npy"), np.load(tmp_path / "mine1.npy")
-    assert (r0 == r1).all() and (r0 != 0).any()
-    assert sorted(np.concatenate([m0, m1]).tolist()) == list(range(10))  # disjoint cover
+@pytest.mark.parametrize("world", [2, 3])  # 10 pairs: an even and an uneven deal
+def test_multi_rank_sharding_and_gather(tmp_path, world):
+    port = 29500 + (os.getpid() % 2000) + world
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    ranks = [np.load(tmp_path / f"rank{r}.npy") for r in range(world)]
+    mines = [np.load(tmp_path / f"mine{r}.npy") for r in range(world)]
+    r0 = ranks[0]
+    assert all((r == r0).all() for r in ranks) and (r0 != 0).any()
+    assert sorted(np.concatenate(mines).tolist()) == list(range(10))  # disjoint cover
     # single-process answer
     sys.path.insert(0, HERE)
     import oracle
@@ -65,11 +68,14 @@ def test_two_rank_sharding_and_gather(tmp_path):
         a, sa = workloads.decode_protein(res, cls, off, int(pa[p]))
         b, sb = workloads.decode_protein(res, cls, off, int(pb[p]))
         assert oracle.run(a, b, sa, sb, params, mode="codes")["score"] == r0[p]
-    t0, t1 = np.load(tmp_path / "traces0.npz"), np.load(tmp_path / "traces1.npz")
-    d0, d1 = np.load(tmp_path / "traces_dst0.npz"), np.load(tmp_path / "traces_dst1.npz")
+    ts = [np.load(tmp_path / f"traces{r}.npz") for r in range(world)]
+    ds = [np.load(tmp_path / f"traces_dst{r}.npz") for r in range(world)]
+    t0 = ts[0]
     for k in ("cols", "off", "comp"):
-        assert (t0[k] == t1[k]).all()
-    assert d0["cols"].size == 0 and (d1["cols"] == t0["cols"]).all() and (d0["off"] == t0["off"]).all()
+        assert all((t[k] == t0[k]).all() for t in ts)
+    # dst=1: only rank 1 holds the columns, every rank the offsets
+    assert all(ds[r]["cols"].size == 0 for r in range(world) if r != 1)
+    assert (ds[1]["cols"] == t0["cols"]).all() and all((d["off"] == t0["off"]).all() for d in ds)
     for p in range(10):
         a, sa = workloads.decode_protein(res, cls, off, int(pa[p]))
         b, sb = workloads.decode_protein(res, cls, off, int(pb[p]))
