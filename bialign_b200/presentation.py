@@ -115,15 +115,15 @@ def read_molecule(content, type):
 
 
 def read_molecule_from_file(filename, type):
+    """[sequence, structure] of a CFSSP-format file (nonpyx:80-93).  Like the reference's, this never raises for an
+    unreadable input: a missing file and any other I/O problem (incl. a molecule type read_molecule has no file format
+    for) print their message, then the exception text, and end the process with status -1."""
     try:
         with open(filename, "r") as fh:
-            return read_molecule(fh.read(), type)
-    except FileNotFoundError as e:
-        print("Input file not found.")
-        print(e)
-        sys.exit(-1)
-    except IOError as e:
-        print(f"Cannot read input file {filename}.")
+            text = fh.read()
+        return read_molecule(text, type)
+    except OSError as e:  # IOError is OSError; FileNotFoundError is the one case with a message of its own
+        print("Input file not found." if isinstance(e, FileNotFoundError) else f"Cannot read input file {filename}.")
         print(e)
         sys.exit(-1)
 

@@ -171,6 +171,23 @@ def test_cfssp_reader_on_synthetic_report(tmp_path):
     assert ba.read_molecule_from_file(str(f), "Protein") == ["MVQIPAK", "EEHHCCC"]
 
 
+def test_read_molecule_from_file_error_paths(tmp_path, capsys):
+    """Messages of nonpyx:80-93 (compared with the compiled reference when this was written: same text on stdout; the
+    reference then dies with a NameError because its module never imports sys -- here the intended exit status -1)."""
+    from bialign_b200 import bialignment as ba
+
+    f = tmp_path / "x.cfssp"
+    f.write_text("Query 1   MV 2 \nStruc 1   EE 2 \n")
+    cases = [(str(tmp_path / "missing"), "Protein", "Input file not found.\n[Errno 2] No such file or directory: '%s'\n" % (tmp_path / "missing")),
+             (str(tmp_path), "Protein", "Cannot read input file %s.\n[Errno 21] Is a directory: '%s'\n" % (tmp_path, tmp_path)),
+             (str(f), "RNA", "Cannot read input file %s.\nCannot read files of type RNA\n" % f)]
+    for name, kind, text in cases:
+        with pytest.raises(SystemExit) as ex:
+            ba.read_molecule_from_file(name, kind)
+        assert ex.value.code == -1
+        assert capsys.readouterr().out == text
+
+
 def test_compact_shard_keeps_sequences():
     from bialign_b200 import workloads
     from bialign_b200.batch import compact_shard
