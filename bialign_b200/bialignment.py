@@ -91,18 +91,13 @@ class BiAligner:
     }
 
     def __init__(self, seqA, seqB, strA, strB, **params):
+        # parameter capture of pyx:179-193: molecule A before molecule B, then the three costs, then the matrix -- a missing
+        # key raises KeyError at the same point as in the reference
         self._params = params
-        self.molA = self._preprocess_seq(seqA, strA)
-        self.molB = self._preprocess_seq(seqB, strB)
-        self.gamma = self._params["gap_cost"]
-        self.beta = self._params["gap_opening_cost"]
-        self.max_shift = self._params["max_shift"]
-        if self._params["simmatrix"]:
-            self._simmatrix = read_simmatrix(self._params["simmatrix"])
-        else:
-            self._simmatrix = None
-        self._score = None
-        self._trace = None
+        self.molA, self.molB = [self._preprocess_seq(q, st) for q, st in ((seqA, strA), (seqB, strB))]
+        self.gamma, self.beta, self.max_shift = [params[key] for key in ("gap_cost", "gap_opening_cost", "max_shift")]
+        self._simmatrix = read_simmatrix(params["simmatrix"]) if params["simmatrix"] else None
+        self._score = self._trace = None
         self._complete = True
 
     # ------------------------------------------------------------------ helpers of the surface
@@ -120,34 +115,37 @@ class BiAligner:
         sys.exit(-1)
 
     def _preprocess_seq(self, sequence, structure):
-        x = {"seq": str(sequence)}
-        x["len"] = len(x["seq"])
-        if structure is None:
-            if self._is_rna:
-                # No structure: base-pair probabilities from ViennaRNA, exactly the calls of pyx:345-353 (ModuleNotFoundError
-                # when the module is absent, like the reference).  The probabilistic structure similarity is evaluated on the
-                # host with the reference's floating-point formula and handed to the engine as an integer matrix.
-                import RNA
-
-                fc = RNA.fold_compound(str(sequence))
-                x["mfe"] = fc.mfe()
-                x["pf"] = fc.pf()
-                x["sbpp"] = _symmetric_pair_matrix(fc.bpp())
-                x["mea"] = mea(x["sbpp"])
-                x["structure"] = x["pf"][0]
-                x["predicted"] = True
-            else:
-                self.error("Structures have to be provided when aligning proteins")
-        else:
+        """The molecule record the rest of the class works on (pyx:340-376): sequence, length, structure and -- for RNAs --
+        the pairing profile of every position, from the supplied dot-bracket string or from ViennaRNA."""
+        mol = {"seq": str(sequence)}
+        mol["len"] = len(mol["seq"])
+        if structure is not None:
             if len(structure) != len(sequence):
                 self.error("Provided structure and sequence must have the same length.")
-            x["structure"] = structure
+            mol["structure"] = structure
             if self._is_rna:
-                x["partner"] = encoding.dotbracket_partners(structure)
-                x["cls"] = encoding.rna_structure_classes(structure)
+                mol["partner"] = encoding.dotbracket_partners(structure)
+                mol["cls"] = encoding.rna_structure_classes(structure)
+        elif not self._is_rna:
+            self.error("Structures have to be provided when aligning proteins")
+        else:
+            mol.update(self._predicted_structure(mol["seq"]))
         if self._is_rna:
-            x["up"], x["down"], x["unp"] = _pairing_profile(x)
-        return x
+            mol["up"], mol["down"], mol["unp"] = _pairing_profile(mol)
+        return mol
+
+    @staticmethod
+    def _predicted_structure(sequence):
+        """No structure supplied for an RNA: base-pair probabilities from ViennaRNA, the calls of pyx:345-353 in their order
+        (ModuleNotFoundError when the module is absent, like the reference).  The probabilistic structure similarity is
+        evaluated on the host with the reference's floating-point formula and handed to the engine as an integer matrix."""
+        import RNA
+
+        fc = RNA.fold_compound(sequence)
+        mfe = fc.mfe()
+        pf = fc.pf()
+        sbpp = _symmetric_pair_matrix(fc.bpp())
+        return {"mfe": mfe, "pf": pf, "sbpp": sbpp, "mea": mea(sbpp), "structure": pf[0], "predicted": True}
 
     # scoring functions, 1-based like the reference (pyx:405-440); used by eval_trace
     def mu1(self, i, j):
